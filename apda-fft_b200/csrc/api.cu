@@ -1,0 +1,533 @@
+// C ABI of libapda_b200.so (declared in include/apda_b200.h): context, twiddle tables, dispatch, host pipelines.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void apda_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int apda_cuda_fail(cudaError_t e, const char *what) {
+    apda_set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return APDA_ERR_CUDA;
+}
+extern "C" const char *apda_last_error(void) { return g_err; }
+extern "C" int apda_version(void) { return 100; }
+
+int apda_reserve(void **buf, size_t *have, size_t need) {
+    if (need <= *have) return APDA_OK;
+    if (*buf) APDA_CUDA(cudaFree(*buf));
+    *buf = nullptr;
+    *have = 0;
+    size_t want = need + need / 8;
+    cudaError_t e = cudaMalloc(buf, want);
+    if (e != cudaSuccess) {
+        want = need;
+        e = cudaMalloc(buf, want);
+    }
+    if (e != cudaSuccess) {
+        apda_set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return APDA_ERR_NOMEM;
+    }
+    *have = want;
+    return APDA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int apda_ctx_create(int device, apda_ctx **out) {
+    if (!out) {
+        apda_set_error("apda_ctx_create: out is NULL");
+        return APDA_ERR_INVALID;
+    }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        apda_set_error("no CUDA device available (%s); libapda_b200 has no CPU fallback",
+                       e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return APDA_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) {
+        apda_set_error("device %d out of range [0, %d)", device, count);
+        return APDA_ERR_INVALID;
+    }
+    cudaDeviceProp prop;
+    APDA_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        apda_set_error("device %d (%s) is compute capability %d.%d; this library is built for sm_100a only", device,
+                       prop.name, prop.major, prop.minor);
+        return APDA_ERR_NO_DEVICE;
+    }
+    APDA_CUDA(cudaSetDevice(device));
+    apda_ctx *ctx = new apda_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    APDA_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    for (int i = 0; i < 2; ++i) {
+        APDA_CUDA(cudaStreamCreateWithFlags(&ctx->pipe[i], cudaStreamNonBlocking));
+        APDA_CUDA(cudaEventCreateWithFlags(&ctx->pipe_done[i], cudaEventDisableTiming));
+    }
+    *out = ctx;
+    return APDA_OK;
+}
+
+extern "C" int apda_ctx_destroy(apda_ctx *ctx) {
+    if (!ctx) return APDA_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto &kv : ctx->twiddles) {
+        cudaFree(kv.second.d64);
+        cudaFree(kv.second.d32);
+    }
+    cudaFree(ctx->ws);
+    cudaFree(ctx->ws_small);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(ctx->ws_pipe[i]);
+        if (ctx->pipe[i]) cudaStreamDestroy(ctx->pipe[i]);
+        if (ctx->pipe_done[i]) cudaEventDestroy(ctx->pipe_done[i]);
+    }
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return APDA_OK;
+}
+
+extern "C" int apda_ctx_set_stream(apda_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return APDA_ERR_INVALID;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return APDA_OK;
+}
+
+extern "C" int apda_sync(apda_ctx *ctx) {
+    if (!ctx) return APDA_ERR_INVALID;
+    APDA_CUDA(cudaStreamSynchronize(ctx->stream));
+    return APDA_OK;
+}
+
+extern "C" int64_t apda_launch_count(apda_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// twiddle tables: the reference's recurrence (metrics/fft_iterativa.py:53,57,68) evaluated on the host with the same
+// libm cos/sin CPython's cmath.exp calls and separately rounded complex products, uploaded once per N.
+// ---------------------------------------------------------------------------------------------------------------
+int apda_get_twiddles(apda_ctx *ctx, int64_t N, TwiddleTables *out) {
+    auto it = ctx->twiddles.find(N);
+    if (it != ctx->twiddles.end()) {
+        *out = it->second;
+        return APDA_OK;
+    }
+    const size_t cnt = (size_t)std::max<int64_t>(N - 1, 1);
+    std::vector<double2> h(cnt);
+    std::vector<float2> hf(cnt);
+    h[0] = make_double2(1.0, 0.0);
+    const double pi = 3.141592653589793;  // cmath.pi
+    for (int64_t half = 1; half < N; half <<= 1) {
+        const double theta = (-2.0 * pi) / (double)(2 * half);
+        const volatile double cr = cos(theta), ci = sin(theta);
+        double wr = 1.0, wi = 0.0;
+        double2 *t = h.data() + (half - 1);
+        for (int64_t j = 0; j < half; ++j) {
+            t[j] = make_double2(wr, wi);
+            // volatile temporaries: every product and sum rounds on its own, as Python's complex product does
+            volatile double a = wr * cr, b = wi * ci, c = wr * ci, d = wi * cr;
+            double nr = a - b, ni = c + d;
+            wr = nr;
+            wi = ni;
+        }
+    }
+    for (size_t i = 0; i < cnt; ++i) hf[i] = make_float2((float)h[i].x, (float)h[i].y);
+    TwiddleTables tw;
+    APDA_CUDA(cudaMalloc(&tw.d64, cnt * sizeof(double2)));
+    APDA_CUDA(cudaMalloc(&tw.d32, cnt * sizeof(float2)));
+    APDA_CUDA(cudaMemcpy(tw.d64, h.data(), cnt * sizeof(double2), cudaMemcpyHostToDevice));
+    APDA_CUDA(cudaMemcpy(tw.d32, hf.data(), cnt * sizeof(float2), cudaMemcpyHostToDevice));
+    ctx->twiddles[N] = tw;
+    *out = tw;
+    return APDA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// argument checks and dispatch
+// ---------------------------------------------------------------------------------------------------------------
+static int check_fft_args(apda_ctx *ctx, const void *in, int64_t n_samples, int64_t ld, int64_t batch, int64_t N,
+                          int flags, const void *out) {
+    if (!ctx || !in || !out) {
+        apda_set_error("fft: NULL argument");
+        return APDA_ERR_INVALID;
+    }
+    if (batch < 0 || batch > 0x7fffffff) {
+        apda_set_error("fft: batch %lld out of range", (long long)batch);
+        return APDA_ERR_INVALID;
+    }
+    if (!is_pow2_i64(N) || N < 2 || N > (int64_t(1) << 30)) {
+        apda_set_error("fft: N=%lld must be a power of two in [2, 2^30]", (long long)N);
+        return APDA_ERR_INVALID;
+    }
+    if (n_samples < 1 || n_samples > N || ld < n_samples) {
+        apda_set_error("fft: need 1 <= n_samples (%lld) <= N (%lld) and ld (%lld) >= n_samples", (long long)n_samples,
+                       (long long)N, (long long)ld);
+        return APDA_ERR_INVALID;
+    }
+    if (flags != APDA_CENTER_MEDIAN && flags != APDA_CENTER_MEAN && flags != APDA_CENTER_NONE) {
+        apda_set_error("fft: unknown flags %d", flags);
+        return APDA_ERR_INVALID;
+    }
+    if (flags == APDA_CENTER_MEAN && n_samples != N) {
+        apda_set_error("fft: APDA_CENTER_MEAN is only legal when n_samples == N (padding needs the exact median)");
+        return APDA_ERR_INVALID;
+    }
+    return APDA_OK;
+}
+
+static int check_peaks_args(apda_ctx *ctx, const void *spec, int64_t n, int64_t batch, int k, int rec_cap,
+                            const void *rec) {
+    if (!ctx || !spec || !rec) {
+        apda_set_error("peaks: NULL argument");
+        return APDA_ERR_INVALID;
+    }
+    if (batch < 0 || batch > 0x7fffffff || n < 0 || n > (int64_t(1) << 31)) {
+        apda_set_error("peaks: batch/n out of range");
+        return APDA_ERR_INVALID;
+    }
+    if (n / 2 < 1) {
+        apda_set_error("mean requires at least one data point");
+        return APDA_ERR_STATS_MEAN;
+    }
+    if (n / 2 < 2) {
+        apda_set_error("stdev requires at least two data points");
+        return APDA_ERR_STATS_STDEV;
+    }
+    if (k < 1 || rec_cap < k || rec_cap > APDA_MAX_REC_CAP) {
+        apda_set_error("peaks: need 1 <= k (%d) <= rec_cap (%d) <= %d", k, rec_cap, APDA_MAX_REC_CAP);
+        return APDA_ERR_INVALID;
+    }
+    return APDA_OK;
+}
+
+template <typename T>
+static int fft_dispatch(apda_ctx *ctx, cudaStream_t st, const T *d_samples, int64_t n_samples, int64_t ld,
+                        int64_t batch, int64_t N, int flags, T *d_spec, bool complex_in) {
+    if (batch == 0) return APDA_OK;
+    if (sizeof(T) == 8 && flags == APDA_CENTER_MEAN) {
+        apda_set_error("fft: APDA_CENTER_MEAN is an fp32-only option; the fp64 path is bit-faithful to the reference");
+        return APDA_ERR_INVALID;
+    }
+    if (N <= fft_smem_max_n<T>(ctx)) return launch_fft_smem<T>(ctx, st, d_samples, n_samples, ld, batch, N, flags, d_spec, complex_in);
+    return launch_fft_large<T>(ctx, st, d_samples, n_samples, ld, batch, N, flags, d_spec, complex_in);
+}
+
+template <typename T>
+static int peaks_dispatch(apda_ctx *ctx, cudaStream_t st, const T *d_spec, int64_t n, int64_t batch, double fs,
+                          const double *d_fs, int k, int rec_cap, int flexible, void *d_rec, void **ws, size_t *ws_bytes,
+                          size_t ws_offset) {
+    if (batch == 0) return APDA_OK;
+    size_t need = peaks_mag_workspace_bytes<T>(ctx, n, batch);
+    void *mag_ws = nullptr;
+    if (need) {
+        if (*ws_bytes < ws_offset + need) {
+            apda_set_error("peaks: internal workspace too small");
+            return APDA_ERR_NOMEM;
+        }
+        mag_ws = (char *)*ws + ws_offset;
+    }
+    return launch_peaks<T>(ctx, st, d_spec, n, batch, fs, d_fs, k, rec_cap, flexible, d_rec, mag_ws);
+}
+
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// device-pointer entry points
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+static int fft_dev(apda_ctx *ctx, const T *d_samples, int64_t n_samples, int64_t ld, int64_t batch, int64_t N, int flags,
+                   T *d_spec) {
+    APDA_TRY(check_fft_args(ctx, d_samples, n_samples, ld, batch, N, flags, d_spec));
+    APDA_CUDA(cudaSetDevice(ctx->device));
+    return fft_dispatch<T>(ctx, ctx->stream, d_samples, n_samples, ld, batch, N, flags, d_spec, false);
+}
+extern "C" int apda_fft_f64_dev(apda_ctx *ctx, const double *d_samples, int64_t n_samples, int64_t ld, int64_t batch,
+                                int64_t N, int flags, double *d_spec) {
+    return fft_dev<double>(ctx, d_samples, n_samples, ld, batch, N, flags, d_spec);
+}
+extern "C" int apda_fft_f32_dev(apda_ctx *ctx, const float *d_samples, int64_t n_samples, int64_t ld, int64_t batch,
+                                int64_t N, int flags, float *d_spec) {
+    return fft_dev<float>(ctx, d_samples, n_samples, ld, batch, N, flags, d_spec);
+}
+
+template <typename T>
+static int peaks_dev(apda_ctx *ctx, const T *d_spec, int64_t n, int64_t batch, double fs, const double *d_fs, int k,
+                     int rec_cap, int flexible, void *d_rec) {
+    APDA_TRY(check_peaks_args(ctx, d_spec, n, batch, k, rec_cap, d_rec));
+    APDA_CUDA(cudaSetDevice(ctx->device));
+    size_t need = peaks_mag_workspace_bytes<T>(ctx, n, batch);
+    if (need) {
+        if (need > ctx->ws_bytes) APDA_CUDA(cudaStreamSynchronize(ctx->stream));  // old workspace may be in use
+        APDA_TRY(apda_reserve(&ctx->ws, &ctx->ws_bytes, need));
+    }
+    return peaks_dispatch<T>(ctx, ctx->stream, d_spec, n, batch, fs, d_fs, k, rec_cap, flexible, d_rec, &ctx->ws,
+                             &ctx->ws_bytes, 0);
+}
+extern "C" int apda_peaks_prominence_f64_dev(apda_ctx *ctx, const double *d_spec, int64_t n, int64_t batch, double fs,
+                                             const double *d_fs, int k, int rec_cap, void *d_rec) {
+    return peaks_dev<double>(ctx, d_spec, n, batch, fs, d_fs, k, rec_cap, 1, d_rec);
+}
+extern "C" int apda_peaks_prominence_f32_dev(apda_ctx *ctx, const float *d_spec, int64_t n, int64_t batch, double fs,
+                                             const double *d_fs, int k, int rec_cap, void *d_rec) {
+    return peaks_dev<float>(ctx, d_spec, n, batch, fs, d_fs, k, rec_cap, 1, d_rec);
+}
+extern "C" int apda_peaks_resolution_f64_dev(apda_ctx *ctx, const double *d_spec, int64_t n, int64_t batch, double fs,
+                                             const double *d_fs, int k, int rec_cap, void *d_rec) {
+    return peaks_dev<double>(ctx, d_spec, n, batch, fs, d_fs, k, rec_cap, 0, d_rec);
+}
+extern "C" int apda_peaks_resolution_f32_dev(apda_ctx *ctx, const float *d_spec, int64_t n, int64_t batch, double fs,
+                                             const double *d_fs, int k, int rec_cap, void *d_rec) {
+    return peaks_dev<float>(ctx, d_spec, n, batch, fs, d_fs, k, rec_cap, 0, d_rec);
+}
+
+template <typename T>
+static int analyze_dev(apda_ctx *ctx, const T *d_samples, int64_t n_samples, int64_t ld, int64_t batch, int64_t N,
+                       int flags, int flexible, double fs, const double *d_fs, int k, int rec_cap, T *d_spec_ws,
+                       void *d_rec) {
+    APDA_TRY(check_fft_args(ctx, d_samples, n_samples, ld, batch, N, flags, d_rec));
+    APDA_TRY(check_peaks_args(ctx, d_samples, N, batch, k, rec_cap, d_rec));
+    APDA_CUDA(cudaSetDevice(ctx->device));
+    const size_t spec_bytes = d_spec_ws ? 0 : align256((size_t)batch * (size_t)N * 2 * sizeof(T));
+    const size_t mag_bytes = peaks_mag_workspace_bytes<T>(ctx, N, batch);
+    if (spec_bytes + mag_bytes > ctx->ws_bytes) {
+        APDA_CUDA(cudaStreamSynchronize(ctx->stream));
+        APDA_TRY(apda_reserve(&ctx->ws, &ctx->ws_bytes, spec_bytes + mag_bytes));
+    }
+    T *spec = d_spec_ws ? d_spec_ws : reinterpret_cast<T *>(ctx->ws);
+    APDA_TRY(fft_dispatch<T>(ctx, ctx->stream, d_samples, n_samples, ld, batch, N, flags, spec, false));
+    return peaks_dispatch<T>(ctx, ctx->stream, spec, N, batch, fs, d_fs, k, rec_cap, flexible, d_rec, &ctx->ws,
+                             &ctx->ws_bytes, spec_bytes);
+}
+extern "C" int apda_analyze_f64_dev(apda_ctx *ctx, const double *d_samples, int64_t n_samples, int64_t ld,
+                                    int64_t batch, int64_t N, int flags, int flexible, double fs, const double *d_fs,
+                                    int k, int rec_cap, double *d_spec_ws, void *d_rec) {
+    return analyze_dev<double>(ctx, d_samples, n_samples, ld, batch, N, flags, flexible, fs, d_fs, k, rec_cap, d_spec_ws,
+                               d_rec);
+}
+extern "C" int apda_analyze_f32_dev(apda_ctx *ctx, const float *d_samples, int64_t n_samples, int64_t ld, int64_t batch,
+                                    int64_t N, int flags, int flexible, double fs, const double *d_fs, int k,
+                                    int rec_cap, float *d_spec_ws, void *d_rec) {
+    return analyze_dev<float>(ctx, d_samples, n_samples, ld, batch, N, flags, flexible, fs, d_fs, k, rec_cap, d_spec_ws,
+                              d_rec);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host-pointer entry points: chunked two-stream pipeline (H2D of chunk c+1 overlaps the kernels / D2H of chunk c)
+// ---------------------------------------------------------------------------------------------------------------
+enum HostMode { kFftOnly, kPeaksOnly, kAnalyze };
+
+template <typename T>
+static int host_pipeline(apda_ctx *ctx, HostMode mode, const T *h_in, int64_t n_samples, int64_t ld, int64_t batch,
+                         int64_t N, int flags, int flexible, double fs, const double *h_fs, int k, int rec_cap,
+                         bool complex_in, T *h_spec_out, void *h_rec_out) {
+    APDA_CUDA(cudaSetDevice(ctx->device));
+    if (batch == 0) return APDA_OK;
+    const size_t rec_bytes = (size_t)APDA_REC_BYTES(rec_cap);
+    const size_t in_elems = mode == kPeaksOnly ? (size_t)N * 2 : (complex_in ? (size_t)N * 2 : (size_t)n_samples);
+    const size_t in_ld = mode == kPeaksOnly ? (size_t)N * 2 : (complex_in ? (size_t)N * 2 : (size_t)ld);
+    const size_t spec_elems = (size_t)N * 2;
+    // chunk: ~96 MB of spectrum per stream, at least one window
+    int64_t chunk = std::max<int64_t>(1, (int64_t)((96u << 20) / (spec_elems * sizeof(T))));
+    chunk = std::min<int64_t>(chunk, batch);
+    if (batch > chunk && batch < 2 * chunk) chunk = (batch + 1) / 2;
+
+    const size_t in_bytes = align256(chunk * in_elems * sizeof(T));
+    const size_t spec_bytes = mode == kPeaksOnly ? 0 : align256(chunk * spec_elems * sizeof(T));
+    const size_t recs_bytes = mode == kFftOnly ? 0 : align256(chunk * rec_bytes);
+    const size_t fs_bytes = (h_fs && mode != kFftOnly) ? align256(chunk * sizeof(double)) : 0;
+    const size_t mag_bytes = mode == kFftOnly ? 0 : align256(peaks_mag_workspace_bytes<T>(ctx, N, chunk));
+    const size_t total = in_bytes + spec_bytes + recs_bytes + fs_bytes + mag_bytes;
+    for (int s = 0; s < 2; ++s) {
+        if (total > ctx->ws_pipe_bytes[s]) {
+            APDA_CUDA(cudaStreamSynchronize(ctx->pipe[s]));
+            APDA_TRY(apda_reserve(&ctx->ws_pipe[s], &ctx->ws_pipe_bytes[s], total));
+        }
+        if (batch <= chunk) break;  // single chunk: one stream is enough
+    }
+
+    int status = APDA_OK;
+    int64_t done = 0;
+    for (int c = 0; done < batch && status == APDA_OK; ++c) {
+        const int s = c & 1;
+        cudaStream_t st = ctx->pipe[s];
+        const int64_t cnt = std::min<int64_t>(chunk, batch - done);
+        char *base = (char *)ctx->ws_pipe[s];
+        T *d_in = (T *)base;
+        T *d_spec = (T *)(base + in_bytes);
+        void *d_rec = base + in_bytes + spec_bytes;
+        double *d_fs = fs_bytes ? (double *)(base + in_bytes + spec_bytes + recs_bytes) : nullptr;
+        void *mag_ws = mag_bytes ? base + in_bytes + spec_bytes + recs_bytes + fs_bytes : nullptr;
+        size_t mag_have = mag_bytes;
+
+        const T *src = h_in + (size_t)done * in_ld;
+        if (in_ld == in_elems) {
+            APDA_CUDA(cudaMemcpyAsync(d_in, src, cnt * in_elems * sizeof(T), cudaMemcpyHostToDevice, st));
+        } else {
+            APDA_CUDA(cudaMemcpy2DAsync(d_in, in_elems * sizeof(T), src, in_ld * sizeof(T), in_elems * sizeof(T), cnt,
+                                        cudaMemcpyHostToDevice, st));
+        }
+        if (d_fs) APDA_CUDA(cudaMemcpyAsync(d_fs, h_fs + done, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+
+        const T *spec_for_peaks = d_in;
+        if (mode != kPeaksOnly) {
+            status = fft_dispatch<T>(ctx, st, d_in, n_samples, (int64_t)in_elems, cnt, N, flags, d_spec, complex_in);
+            spec_for_peaks = d_spec;
+            if (status == APDA_OK && mode == kFftOnly)
+                APDA_CUDA(cudaMemcpyAsync(h_spec_out + (size_t)done * spec_elems, d_spec, cnt * spec_elems * sizeof(T),
+                                          cudaMemcpyDeviceToHost, st));
+        }
+        if (status == APDA_OK && mode != kFftOnly) {
+            status = peaks_dispatch<T>(ctx, st, spec_for_peaks, N, cnt, fs, d_fs, k, rec_cap, flexible, d_rec, &mag_ws,
+                                       &mag_have, 0);
+            if (status == APDA_OK)
+                APDA_CUDA(cudaMemcpyAsync((char *)h_rec_out + (size_t)done * rec_bytes, d_rec, cnt * rec_bytes,
+                                          cudaMemcpyDeviceToHost, st));
+        }
+        done += cnt;
+    }
+    cudaError_t e0 = cudaStreamSynchronize(ctx->pipe[0]);
+    cudaError_t e1 = cudaStreamSynchronize(ctx->pipe[1]);
+    if (status != APDA_OK) return status;
+    if (e0 != cudaSuccess) return apda_cuda_fail(e0, "host pipeline (stream 0)");
+    if (e1 != cudaSuccess) return apda_cuda_fail(e1, "host pipeline (stream 1)");
+    return APDA_OK;
+}
+
+extern "C" int apda_fft_f64_host(apda_ctx *ctx, const double *h_samples, int64_t n_samples, int64_t ld, int64_t batch,
+                                 int64_t N, int flags, double *h_spec) {
+    APDA_TRY(check_fft_args(ctx, h_samples, n_samples, ld, batch, N, flags, h_spec));
+    return host_pipeline<double>(ctx, kFftOnly, h_samples, n_samples, ld, batch, N, flags, 0, 0.0, nullptr, 1, 5, false,
+                                 h_spec, nullptr);
+}
+extern "C" int apda_fft_f32_host(apda_ctx *ctx, const float *h_samples, int64_t n_samples, int64_t ld, int64_t batch,
+                                 int64_t N, int flags, float *h_spec) {
+    APDA_TRY(check_fft_args(ctx, h_samples, n_samples, ld, batch, N, flags, h_spec));
+    return host_pipeline<float>(ctx, kFftOnly, h_samples, n_samples, ld, batch, N, flags, 0, 0.0, nullptr, 1, 5, false,
+                                h_spec, nullptr);
+}
+extern "C" int apda_fft_c2c_f64_host(apda_ctx *ctx, const double *h_in, int64_t batch, int64_t N, double *h_out) {
+    APDA_TRY(check_fft_args(ctx, h_in, N, N, batch, N, APDA_CENTER_NONE, h_out));
+    return host_pipeline<double>(ctx, kFftOnly, h_in, N, N, batch, N, APDA_CENTER_NONE, 0, 0.0, nullptr, 1, 5, true,
+                                 h_out, nullptr);
+}
+extern "C" int apda_peaks_prominence_f64_host(apda_ctx *ctx, const double *h_spec, int64_t n, int64_t batch, double fs,
+                                              const double *h_fs, int k, int rec_cap, void *h_rec) {
+    APDA_TRY(check_peaks_args(ctx, h_spec, n, batch, k, rec_cap, h_rec));
+    return host_pipeline<double>(ctx, kPeaksOnly, h_spec, 0, 0, batch, n, 0, 1, fs, h_fs, k, rec_cap, false, nullptr,
+                                 h_rec);
+}
+extern "C" int apda_peaks_resolution_f64_host(apda_ctx *ctx, const double *h_spec, int64_t n, int64_t batch, double fs,
+                                              const double *h_fs, int k, int rec_cap, void *h_rec) {
+    APDA_TRY(check_peaks_args(ctx, h_spec, n, batch, k, rec_cap, h_rec));
+    return host_pipeline<double>(ctx, kPeaksOnly, h_spec, 0, 0, batch, n, 0, 0, fs, h_fs, k, rec_cap, false, nullptr,
+                                 h_rec);
+}
+extern "C" int apda_analyze_f64_host(apda_ctx *ctx, const double *h_samples, int64_t n_samples, int64_t ld,
+                                     int64_t batch, int64_t N, int flags, int flexible, double fs, const double *h_fs,
+                                     int k, int rec_cap, void *h_rec) {
+    APDA_TRY(check_fft_args(ctx, h_samples, n_samples, ld, batch, N, flags, h_rec));
+    APDA_TRY(check_peaks_args(ctx, h_samples, N, batch, k, rec_cap, h_rec));
+    return host_pipeline<double>(ctx, kAnalyze, h_samples, n_samples, ld, batch, N, flags, flexible, fs, h_fs, k, rec_cap,
+                                 false, nullptr, h_rec);
+}
+extern "C" int apda_analyze_f32_host(apda_ctx *ctx, const float *h_samples, int64_t n_samples, int64_t ld, int64_t batch,
+                                     int64_t N, int flags, int flexible, double fs, const double *h_fs, int k,
+                                     int rec_cap, void *h_rec) {
+    APDA_TRY(check_fft_args(ctx, h_samples, n_samples, ld, batch, N, flags, h_rec));
+    APDA_TRY(check_peaks_args(ctx, h_samples, N, batch, k, rec_cap, h_rec));
+    return host_pipeline<float>(ctx, kAnalyze, h_samples, n_samples, ld, batch, N, flags, flexible, fs, h_fs, k, rec_cap,
+                                false, nullptr, h_rec);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// small helpers on host lists
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int apda_center_f64_host(apda_ctx *ctx, const double *h_in, int64_t n, double *h_out) {
+    if (!ctx || !h_in || !h_out || n < 1 || n > (int64_t(1) << 28)) {
+        apda_set_error("center: bad arguments");
+        return APDA_ERR_INVALID;
+    }
+    APDA_CUDA(cudaSetDevice(ctx->device));
+    APDA_TRY(apda_reserve(&ctx->ws_small, &ctx->ws_small_bytes, (size_t)n * 3 * sizeof(double)));
+    double *d_in = (double *)ctx->ws_small, *d_out = d_in + n;
+    cudaStream_t st = ctx->pipe[0];
+    APDA_CUDA(cudaMemcpyAsync(d_in, h_in, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    APDA_TRY(launch_center_f64(ctx, st, d_in, n, d_out));
+    APDA_CUDA(cudaMemcpyAsync(h_out, d_out, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    APDA_CUDA(cudaStreamSynchronize(st));
+    return APDA_OK;
+}
+
+static int mag_helpers(apda_ctx *ctx, const double *h_mags, int64_t n, int64_t idx, double prom_in, double out3[3]) {
+    if (!ctx || !h_mags || n < 1 || idx < 0 || idx >= n || n > (int64_t(1) << 30)) {
+        apda_set_error("magnitude helper: bad arguments (n=%lld idx=%lld)", (long long)n, (long long)idx);
+        return APDA_ERR_INVALID;
+    }
+    APDA_CUDA(cudaSetDevice(ctx->device));
+    APDA_TRY(apda_reserve(&ctx->ws_small, &ctx->ws_small_bytes, (size_t)(n + 4) * sizeof(double)));
+    double *d_mags = (double *)ctx->ws_small, *d_out = d_mags + n;
+    cudaStream_t st = ctx->pipe[0];
+    APDA_CUDA(cudaMemcpyAsync(d_mags, h_mags, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    APDA_TRY(launch_mag_helpers_f64(ctx, st, d_mags, n, idx, prom_in, d_out));
+    APDA_CUDA(cudaMemcpyAsync(out3, d_out, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    APDA_CUDA(cudaStreamSynchronize(st));
+    return APDA_OK;
+}
+extern "C" int apda_prominence_f64_host(apda_ctx *ctx, const double *h_mags, int64_t n, int64_t idx, double *out) {
+    double r[3];
+    APDA_TRY(mag_helpers(ctx, h_mags, n, idx, 0.0, r));
+    *out = r[0];
+    return APDA_OK;
+}
+extern "C" int apda_half_power_bins_f64_host(apda_ctx *ctx, const double *h_mags, int64_t n, double prominence,
+                                             int64_t idx, int64_t *bins) {
+    double r[3];
+    APDA_TRY(mag_helpers(ctx, h_mags, n, idx, prominence, r));
+    *bins = (int64_t)r[1];
+    return APDA_OK;
+}
+extern "C" int apda_half_height_bins_f64_host(apda_ctx *ctx, const double *h_mags, int64_t n, int64_t idx,
+                                              int64_t *bins) {
+    double r[3];
+    APDA_TRY(mag_helpers(ctx, h_mags, n, idx, 0.0, r));
+    *bins = (int64_t)r[2];
+    return APDA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// synthetic input
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int apda_synth_f64_dev(apda_ctx *ctx, int64_t first_window, int64_t count, int64_t N, uint64_t seed,
+                                  int on_bin, double *d_out) {
+    if (!ctx || !d_out || count < 0 || N < 2) return APDA_ERR_INVALID;
+    APDA_CUDA(cudaSetDevice(ctx->device));
+    return launch_synth<double>(ctx, ctx->stream, first_window, count, N, seed, on_bin, d_out);
+}
+extern "C" int apda_synth_f32_dev(apda_ctx *ctx, int64_t first_window, int64_t count, int64_t N, uint64_t seed,
+                                  int on_bin, float *d_out) {
+    if (!ctx || !d_out || count < 0 || N < 2) return APDA_ERR_INVALID;
+    APDA_CUDA(cudaSetDevice(ctx->device));
+    return launch_synth<float>(ctx, ctx->stream, first_window, count, N, seed, on_bin, d_out);
+}

@@ -1,0 +1,39 @@
+"""Per-window peak records (include/apda_b200.h: apda_peak_rec) <-> the reference's list-of-dict results.
+
+The device decides WHICH peaks are reported (all comparisons, the rounded-magnitude ordering, the hump
+exclusion, the resolution criterion).  The presentation fields the reference derives with Python's
+round()/float arithmetic (freq, damping, q-factor) are recomputed here from (idx, width_bins, mag,
+prominence, fs, n) in the reference's operation order, so they are the same doubles.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def record_dtype(rec_cap: int = 5) -> np.dtype:
+    peak = np.dtype([("idx", "<i4"), ("width_bins", "<i4"), ("mag", "<f8"), ("prominence", "<f8")])
+    dt = np.dtype([("count", "<i4"), ("status", "<i4"), ("pk", peak, (rec_cap,))])
+    assert dt.itemsize == 8 + 24 * rec_cap
+    return dt
+
+
+def prominence_dicts(rec, fs: float, n: int) -> list[dict]:
+    """utils/get_peak_prominence.py:187-194 record layout (reference), one window."""
+    out = []
+    df = fs / n
+    for a in range(int(rec["count"])):
+        pk = rec["pk"][a]
+        idx = int(pk["idx"])
+        fn = idx * df
+        q_factor = fn / (int(pk["width_bins"]) * df)
+        damping = 1 / (2 * q_factor)
+        out.append({"freq": round(fn, 4), "mag": round(float(pk["mag"]), 4), "prominence": float(pk["prominence"]),
+                    "damping": round(damping * 100, 2), "q-factor": round(q_factor, 2), "idx": idx})
+    return out
+
+
+def resolution_dicts(rec, fs: float, n: int) -> list[dict]:
+    """utils/get_peak_resolution.py:113 record layout (reference), one window."""
+    df = fs / n
+    return [{"freq": int(pk["idx"]) * df, "mag": float(pk["mag"]), "idx": int(pk["idx"])}
+            for pk in rec["pk"][: int(rec["count"])]]

@@ -1,0 +1,145 @@
+/* apda_b200.h - C ABI of libapda_b200.so: the B200 (sm_100a) implementation of APDA-FFT's spectral hot path.
+ *
+ * The reference (Copojacaab/APDA-FFT) has no FFI layer: its hot path is three plain-Python modules.  Each entry
+ * point below names the reference interface it stands in for (paths relative to the reference checkout); the
+ * Python mirror in apda-fft_b200/{metrics,utils}/ binds them with ctypes.
+ *
+ * Conventions
+ *   - every function returns an int status: APDA_OK (0) or a negative APDA_ERR_*; apda_last_error() gives the
+ *     thread-local message of the last failure.  No exceptions, no exit(), no CPU fallback: without an sm_100
+ *     device apda_ctx_create fails with APDA_ERR_NO_DEVICE.
+ *   - an apda_ctx belongs to one host thread and one device.  "_dev" entry points take DEVICE pointers, enqueue
+ *     on the context stream and return without synchronising (apda_sync waits).  "_host" entry points take HOST
+ *     pointers, run H2D -> kernels -> D2H in a chunked two-stream pipeline and return when the results are in
+ *     the caller's buffers.
+ *   - spectra are interleaved (re, im) pairs, N bins per window, window b at offset b*2*N reals.
+ *   - N is a power of two; n_samples <= N real samples per window are median-centred, then zero padded to N.
+ */
+#ifndef APDA_B200_H
+#define APDA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APDA_OK 0
+#define APDA_ERR_INVALID (-1)      /* bad argument (NULL, non power-of-two N, n_samples > N, k out of range ...) */
+#define APDA_ERR_NO_DEVICE (-2)    /* no CUDA device / not compute capability 10.x */
+#define APDA_ERR_CUDA (-3)         /* a CUDA runtime call or kernel failed; message holds cudaGetErrorString */
+#define APDA_ERR_NOMEM (-4)
+#define APDA_ERR_UNSUPPORTED (-5)  /* size outside what the kernels cover */
+#define APDA_ERR_STATS_MEAN (-6)   /* half spectrum empty: reference raises StatisticsError('mean requires at least one data point') */
+#define APDA_ERR_STATS_STDEV (-7)  /* half spectrum has 1 bin: StatisticsError('stdev requires at least two data points') */
+
+/* flags of apda_fft_* */
+#define APDA_CENTER_MEDIAN 0  /* exact statistics.median of the n_samples real samples (reference behaviour, default) */
+#define APDA_CENTER_MEAN 1    /* fp32 only, only legal when n_samples == N: block mean; bins >= 1 are unaffected */
+#define APDA_CENTER_NONE 2    /* input already centred by the caller */
+
+/* One detected peak.  width_bins: flexible picker = max(right-left,1) of the half-power walk;
+ * rigid picker = half-height width of the candidate when it was accepted.  prominence is 0 for the rigid picker. */
+typedef struct apda_peak {
+    int32_t idx;
+    int32_t width_bins;
+    double mag;        /* raw |X[idx]| (fp32 paths widen to double) */
+    double prominence; /* raw, flexible picker only */
+} apda_peak; /* 24 bytes */
+
+/* Fixed 128-byte per-window record (rec_cap == 5).  For rec_cap != 5 a record is 8 + 24*rec_cap bytes with the
+ * same header.  Peaks are in the reference's output order (flexible: descending rounded magnitude; rigid: discovery). */
+typedef struct apda_peak_rec {
+    int32_t count;  /* peaks found (<= k) */
+    int32_t status; /* 0 ok; bit0: internal candidate list overflowed (result truncated) */
+    apda_peak pk[5];
+} apda_peak_rec;
+
+#define APDA_REC_BYTES(rec_cap) (8 + 24 * (int64_t)(rec_cap))
+#define APDA_MAX_REC_CAP 64
+
+typedef struct apda_ctx apda_ctx;
+
+/* ---- context ---------------------------------------------------------------------------------------------- */
+int apda_ctx_create(int device, apda_ctx **out);
+int apda_ctx_destroy(apda_ctx *ctx);
+/* Run the _dev entry points on a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); NULL restores the context's own. */
+int apda_ctx_set_stream(apda_ctx *ctx, void *cuda_stream);
+int apda_sync(apda_ctx *ctx);
+const char *apda_last_error(void);
+int apda_version(void);
+/* number of kernels this library has launched through ctx since creation (bench.py's gpu_launches) */
+int64_t apda_launch_count(apda_ctx *ctx);
+
+/* ---- K1/K2: FFT --------------------------------------------------------------------------------------------
+ * replaces metrics/fft_iterativa.py:74-87 start_fft(samples, fs): median centre (:5-11), zero pad (:13-22),
+ * bit reversal (:24-36), radix-2 DIT butterflies with the recurrence twiddles (:38-70), bin 0 := 0 (:85).
+ * f64 is bit-faithful to the reference (no FMA, host-built recurrence twiddle table).  f32 is the fast path.
+ * N <= 2^13 (f64) / 2^14 (f32) runs one shared-memory kernel per window batch; larger N runs the multi-pass kernels. */
+int apda_fft_f64_dev(apda_ctx *ctx, const double *d_samples, int64_t n_samples, int64_t ld, int64_t batch,
+                     int64_t N, int flags, double *d_spec);
+int apda_fft_f32_dev(apda_ctx *ctx, const float *d_samples, int64_t n_samples, int64_t ld, int64_t batch,
+                     int64_t N, int flags, float *d_spec);
+int apda_fft_f64_host(apda_ctx *ctx, const double *h_samples, int64_t n_samples, int64_t ld, int64_t batch,
+                      int64_t N, int flags, double *h_spec);
+int apda_fft_f32_host(apda_ctx *ctx, const float *h_samples, int64_t n_samples, int64_t ld, int64_t batch,
+                      int64_t N, int flags, float *h_spec);
+/* replaces metrics/fft_iterativa.py:38-70 fft(x) on complex input (no centring, no DC zeroing), N = 2^k */
+int apda_fft_c2c_f64_host(apda_ctx *ctx, const double *h_in, int64_t batch, int64_t N, double *h_out);
+/* replaces metrics/fft_iterativa.py:5-11 remove_dc_component(samples) */
+int apda_center_f64_host(apda_ctx *ctx, const double *h_in, int64_t n, double *h_out);
+
+/* ---- K3: peak pickers --------------------------------------------------------------------------------------
+ * n = bins per window in the spectrum (the pickers read bins [0, n/2)); fs: one value for all windows when
+ * d_fs/h_fs is NULL.  k <= rec_cap <= APDA_MAX_REC_CAP; out: batch records of APDA_REC_BYTES(rec_cap).
+ * prominence: replaces utils/get_peak_prominence.py:149-226 get_top_peaks_prominence(res_fft, fs, k=4)
+ * resolution: replaces utils/get_peak_resolution.py:80-128 get_top_peaks_resolution(fft_res, fs, k=5) */
+int apda_peaks_prominence_f64_dev(apda_ctx *ctx, const double *d_spec, int64_t n, int64_t batch, double fs,
+                                  const double *d_fs, int k, int rec_cap, void *d_rec);
+int apda_peaks_prominence_f32_dev(apda_ctx *ctx, const float *d_spec, int64_t n, int64_t batch, double fs,
+                                  const double *d_fs, int k, int rec_cap, void *d_rec);
+int apda_peaks_resolution_f64_dev(apda_ctx *ctx, const double *d_spec, int64_t n, int64_t batch, double fs,
+                                  const double *d_fs, int k, int rec_cap, void *d_rec);
+int apda_peaks_resolution_f32_dev(apda_ctx *ctx, const float *d_spec, int64_t n, int64_t batch, double fs,
+                                  const double *d_fs, int k, int rec_cap, void *d_rec);
+int apda_peaks_prominence_f64_host(apda_ctx *ctx, const double *h_spec, int64_t n, int64_t batch, double fs,
+                                   const double *h_fs, int k, int rec_cap, void *h_rec);
+int apda_peaks_resolution_f64_host(apda_ctx *ctx, const double *h_spec, int64_t n, int64_t batch, double fs,
+                                   const double *h_fs, int k, int rec_cap, void *h_rec);
+
+/* ---- pipeline: samples -> records, spectra never leave HBM -------------------------------------------------
+ * replaces the body of GT_FFT_v5.py:635-642 (start_fft followed by the picker selected by is_flexibile_structure).
+ * flexible != 0 -> prominence picker, else resolution picker.  d_spec_ws: caller-provided spectrum workspace of
+ * batch*2*N reals, or NULL to use the context's own. */
+int apda_analyze_f64_dev(apda_ctx *ctx, const double *d_samples, int64_t n_samples, int64_t ld, int64_t batch,
+                         int64_t N, int flags, int flexible, double fs, const double *d_fs, int k, int rec_cap,
+                         double *d_spec_ws, void *d_rec);
+int apda_analyze_f32_dev(apda_ctx *ctx, const float *d_samples, int64_t n_samples, int64_t ld, int64_t batch,
+                         int64_t N, int flags, int flexible, double fs, const double *d_fs, int k, int rec_cap,
+                         float *d_spec_ws, void *d_rec);
+int apda_analyze_f64_host(apda_ctx *ctx, const double *h_samples, int64_t n_samples, int64_t ld, int64_t batch,
+                          int64_t N, int flags, int flexible, double fs, const double *h_fs, int k, int rec_cap,
+                          void *h_rec);
+int apda_analyze_f32_host(apda_ctx *ctx, const float *h_samples, int64_t n_samples, int64_t ld, int64_t batch,
+                          int64_t N, int flags, int flexible, double fs, const double *h_fs, int k, int rec_cap,
+                          void *h_rec);
+
+/* ---- picker helpers on a magnitude array (module-public functions of the reference) --------------------------
+ * utils/get_peak_prominence.py:32-54 calculate_prominence(magnitudes, peak_idx) */
+int apda_prominence_f64_host(apda_ctx *ctx, const double *h_mags, int64_t n, int64_t idx, double *out);
+/* utils/get_peak_prominence.py:89-112 calculate_half_power_width_prominenceBased: returns the bin count; Hz = bins*(fs/n) */
+int apda_half_power_bins_f64_host(apda_ctx *ctx, const double *h_mags, int64_t n, double prominence, int64_t idx,
+                                  int64_t *bins);
+/* utils/get_peak_resolution.py:30-44 width_half_magnitude(magnitudes, peak_idx) */
+int apda_half_height_bins_f64_host(apda_ctx *ctx, const double *h_mags, int64_t n, int64_t idx, int64_t *bins);
+
+/* ---- synthetic fleet windows generated on the device (bench input only) -------------- */
+int apda_synth_f64_dev(apda_ctx *ctx, int64_t first_window, int64_t count, int64_t N, uint64_t seed, int on_bin,
+                       double *d_out);
+int apda_synth_f32_dev(apda_ctx *ctx, int64_t first_window, int64_t count, int64_t N, uint64_t seed, int on_bin,
+                       float *d_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APDA_B200_H */

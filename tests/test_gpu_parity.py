@@ -1,0 +1,272 @@
+"""T2: CUDA path (through the C ABI) vs the oracle / the committed goldens.  Needs a B200: run with -m gpu.
+
+Bars (north_star): fp64 - spectrum bit-exact (SHA-256 of the doubles), peak indices/counts exact, magnitudes and
+prominences within rel 1e-12; fp32 - indices/counts exact on the well-separated inputs, values within rel 1e-5.
+"""
+import statistics
+
+import numpy as np
+import pytest
+
+import cases
+from oracle import c_oracle, ref_port
+
+pytestmark = pytest.mark.gpu
+
+TOL64 = 1e-12
+TOL32 = 1e-5
+
+
+@pytest.fixture(scope="module")
+def an():
+    import apda_fft_b200
+    return apda_fft_b200.Analyzer(0)
+
+
+def _dicts(rec, fs, n, flexible):
+    from apda_fft_b200.records import prominence_dicts, resolution_dicts
+    return prominence_dicts(rec, fs, n) if flexible else resolution_dicts(rec, fs, n)
+
+
+def assert_peaks_close(got, want, tol, what=""):
+    assert [p["idx"] for p in got] == [p["idx"] for p in want], what
+    for g, w in zip(got, want):
+        assert set(g) == set(w)
+        for key in w:
+            if key == "idx":
+                continue
+            assert cases.isclose_rel(g[key], w[key], tol), (what, key, g[key], w[key])
+
+
+FFT_CASES = [c for c in cases.CASES if c["id"] not in ("n1",)]
+
+
+@pytest.mark.parametrize("spec", FFT_CASES, ids=[c["id"] for c in FFT_CASES])
+def test_fft_f64_bit_exact_and_peaks(spec, golden, an):
+    g = golden["cases"][spec["id"]]
+    x, fs = cases.build_samples(spec)
+    n = g["n_fft"]
+    spectrum = an.fft(x)[0]
+    assert spectrum.shape == (n,)
+    assert cases.spectrum_sha16(spectrum) == g["spectrum_sha"], "fp64 spectrum is not bit-identical to the reference"
+    for flexible, key in ((True, "prominence"), (False, "resolution")):
+        if "error" in g[key]:
+            with pytest.raises(statistics.StatisticsError):
+                an.peaks(spectrum, fs, flexible=flexible)
+            continue
+        rec = an.peaks(spectrum, fs, flexible=flexible)[0]
+        assert rec["status"] == 0
+        assert_peaks_close(_dicts(rec, fs, n, flexible), g[key]["ok"], TOL64, (spec["id"], key))
+        # fused pipeline entry point gives the same record
+        rec2 = an.analyze(x, fs, flexible=flexible)[0]
+        assert rec2.tobytes() == rec.tobytes()
+
+
+def test_fp64_values_are_exact_on_kats(golden, an):
+    """Stronger than the 1e-12 bar: with glibc's hypot sequence and double-double statistics the fp64 tables are
+    the very same doubles as the reference's on the KATs."""
+    for cid in ("katA", "katB", "katC"):
+        g = golden["cases"][cid]
+        x, fs = cases.build_samples(g["spec"])
+        assert _dicts(an.analyze(x, fs, flexible=True)[0], fs, g["n_fft"], True) == g["prominence"]["ok"]
+        assert _dicts(an.analyze(x, fs, flexible=False)[0], fs, g["n_fft"], False) == g["resolution"]["ok"]
+
+
+@pytest.mark.parametrize("spec", cases.SPECTRA, ids=[c["id"] for c in cases.SPECTRA])
+def test_picker_only_spectra(spec, golden, an):
+    g = golden["spectra"][spec["id"]]
+    z, fs = cases.build_spectrum(spec)
+    for k in (4, 5, 12):
+        for flexible, key in ((True, "prominence"), (False, "resolution")):
+            rec = an.peaks(z, fs, flexible=flexible, k=k)[0]
+            assert_peaks_close(_dicts(rec, fs, len(z), flexible), g[f"{key}_k{k}"]["ok"], TOL64, (spec["id"], key, k))
+
+
+def test_k_variants(golden, an):
+    by_id = {c["id"]: c for c in cases.CASES}
+    for row in golden["k_variants"]:
+        x, fs = cases.build_samples(by_id[row["case"]])
+        n = c_oracle.padded_len(len(x))
+        for flexible, key in ((True, "prominence"), (False, "resolution")):
+            rec = an.analyze(x, fs, flexible=flexible, k=row["k"])[0]
+            assert_peaks_close(_dicts(rec, fs, n, flexible), row[key]["ok"], TOL64, (row["case"], key, row["k"]))
+
+
+def test_magnitudes_bit_identical_to_glibc_hypot(an):
+    """K3's magnitude follows glibc's hypot operation sequence; check through the prominence of an isolated peak:
+    prominence = mag[j] - mag[valley] is exact only if both magnitudes are the reference's doubles."""
+    rng = np.random.default_rng(5)
+    n = 2048
+    z = (rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 0.01
+    z[0] = 0
+    for j, amp in ((100, 50.0 + 3.3j), (400, -20.0 + 31.7j), (800, 7.77 - 19.1j)):
+        z[j] = amp
+    rec = an.peaks(z, 125.0, flexible=True, k=4)[0]
+    want = ref_port.top_peaks_prominence(z.tolist(), 125.0, 4)
+    assert _dicts(rec, 125.0, n, True) == want
+
+
+def test_fft_c2c_bit_exact(golden, an):
+    rng = np.random.default_rng(0)
+    z = np.round(rng.standard_normal(64) + 1j * rng.standard_normal(64), 6)
+    assert cases.spectrum_sha16(an.fft_c2c(z)[0]) == golden["fft_c2c_64"]["sha"]
+    z = np.round(rng.standard_normal(4096) + 1j * rng.standard_normal(4096), 6)
+    assert np.array_equal(an.fft_c2c(z)[0].view(np.float64), c_oracle.fft_c2c(z).view(np.float64))
+
+
+def test_batch_f64_vs_c_oracle_multichunk(an):
+    """3.5k windows x 4096 fp64 crosses the host pipeline's chunk boundary; spectra must match the C oracle bit for bit."""
+    import apda_fft_b200.synth as synth
+    b, n = 3500, 4096
+    x = synth.fleet_windows(5000, b, n)
+    spectra = an.fft(x)
+    want = c_oracle.start_fft_batch(x)
+    assert np.array_equal(spectra.view(np.float64), want.view(np.float64))
+    recs = an.analyze(x, 125.0, flexible=True)
+    assert (recs["count"] == 3).all() and (recs["status"] == 0).all()
+    recs_r = an.analyze(x, 125.0, flexible=False)
+    for w in list(range(0, 24)) + list(range(b - 24, b)) + [1535, 1536, 1537, 1750]:
+        assert_peaks_close(_dicts(recs[w], 125.0, n, True), c_oracle.peaks_prominence(want[w], 125.0), TOL64, w)
+        assert_peaks_close(_dicts(recs_r[w], 125.0, n, False), c_oracle.peaks_resolution(want[w], 125.0), TOL64, w)
+
+
+def test_per_window_fs(an):
+    import apda_fft_b200.synth as synth
+    x = synth.fleet_windows(0, 6, 1024)
+    fs = np.array([31.25, 62.5, 125.0, 250.0, 500.0, 44100.0])
+    recs = an.analyze(x, fs, flexible=True)
+    spectra = c_oracle.start_fft_batch(x)
+    for w in range(6):
+        assert_peaks_close(_dicts(recs[w], float(fs[w]), 1024, True), c_oracle.peaks_prominence(spectra[w], float(fs[w])),
+                           TOL64, w)
+
+
+F32_CASES = ["katA", "katB", "katC", "fleet4096_w0", "fleet4096_w0_onbin", "fleet8192_w7_onbin", "fleet1024_w1",
+             "fleet2048_w5", "fleet4096_w3", "fleet4096_w999999", "fleet16384_w9", "pad1000", "pad3000", "six_tones"]
+
+
+@pytest.mark.parametrize("cid", F32_CASES)
+def test_f32_indices_exact_values_1e5(cid, golden, an):
+    g = golden["cases"][cid]
+    x, fs = cases.build_samples(g["spec"])
+    x32 = x.astype(np.float32)
+    n = g["n_fft"]
+    spec32 = an.fft(x32)[0]
+    want = c_oracle.start_fft_batch(x)[0]
+    scale = np.abs(want).max()
+    assert np.abs(spec32.astype(np.complex128) - want).max() <= 2e-6 * scale
+    for flexible, key in ((True, "prominence"), (False, "resolution")):
+        rec = an.analyze(x32, fs, flexible=flexible)[0]
+        got = _dicts(rec, fs, n, flexible)
+        assert [p["idx"] for p in got] == [p["idx"] for p in g[key]["ok"]], (cid, key)
+        for gp, wp in zip(got, g[key]["ok"]):
+            assert cases.isclose_rel(gp["mag"], wp["mag"], TOL32 + 1e-4 / max(abs(wp["mag"]), 1.0) * flexible)
+            if flexible:
+                assert cases.isclose_rel(gp["prominence"], wp["prominence"], TOL32)
+
+
+def test_f32_mean_centering_equals_median_when_unpadded(an):
+    """SURVEY finding 5: without padding the centring constant only moves bin 0, which is zeroed."""
+    import apda_fft_b200
+    import apda_fft_b200.synth as synth
+    x = synth.fleet_windows(40, 32, 4096, dtype=np.float32)
+    a = an.analyze(x, 125.0, flexible=True, center=apda_fft_b200._cabi.CENTER_MEDIAN)
+    b = an.analyze(x, 125.0, flexible=True, center=apda_fft_b200._cabi.CENTER_MEAN)
+    assert (a["count"] == b["count"]).all() and (a["pk"]["idx"] == b["pk"]["idx"]).all()
+    live = a["pk"]["idx"] >= 0
+    assert np.allclose(a["pk"]["mag"][live], b["pk"]["mag"][live], rtol=1e-5)
+    with pytest.raises(ValueError):
+        an.analyze(x[:, :3000], 125.0, center=apda_fft_b200._cabi.CENTER_MEAN)
+
+
+def test_helper_functions(golden, an):
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "apda-fft_b200"))
+    from utils.get_peak_prominence import calculate_half_power_width_prominenceBased, calculate_prominence
+    from utils.get_peak_resolution import resolution, width_half_magnitude
+    for blk in golden["helpers"]:
+        mags = cases.mags_case(blk["seed"], blk["n"], blk["style"]).tolist()
+        for row in blk["rows"]:
+            j = row["j"]
+            assert calculate_prominence(mags, j) == row["prominence"]
+            assert calculate_half_power_width_prominenceBased(mags, row["prominence"], j, blk["fs"], blk["n_fft"]) == row["width_hz"]
+            assert width_half_magnitude(mags, j) == row["whm"]
+            assert resolution(mags, j, row["other"]) == row["rs"]
+
+
+def test_device_pointer_api_and_synth(an):
+    """The _dev entry points on torch-owned memory and stream; device generator vs host generator."""
+    import torch
+    import apda_fft_b200.synth as synth
+    from apda_fft_b200.records import record_dtype
+    b, n = 64, 4096
+    dev = torch.device("cuda:0")
+    stream = torch.cuda.current_stream(dev)
+    an.use_stream(stream.cuda_stream)
+    try:
+        for dtype, tdt in (("f64", torch.float64), ("f32", torch.float32)):
+            d_x = torch.empty((b, n), dtype=tdt, device=dev)
+            an.synth_device(1000, b, n, dtype, d_x.data_ptr())
+            d_rec = torch.zeros((b, 128), dtype=torch.uint8, device=dev)
+            d_spec = torch.empty((b, n, 2), dtype=tdt, device=dev)
+            an.analyze_device(d_x.data_ptr(), b, n, n, dtype, 125.0, d_rec.data_ptr(), d_spec_ws=d_spec.data_ptr())
+            torch.cuda.synchronize()
+            x = d_x.cpu().numpy()
+            host = synth.fleet_windows(1000, b, n)
+            assert np.abs(x - host).max() <= 1.000001e-6 and (x.astype(np.float64) == host.astype(x.dtype)).mean() > 0.999
+            recs = d_rec.cpu().numpy().view(record_dtype(5)).reshape(b)
+            want = c_oracle.start_fft_batch(x.astype(np.float64))
+            if dtype == "f64":
+                assert np.array_equal(d_spec.cpu().numpy().reshape(b, 2 * n), want.view(np.float64))
+            for w in range(0, b, 7):
+                ref = c_oracle.peaks_prominence(want[w], 125.0)
+                got = _dicts(recs[w], 125.0, n, True)
+                assert [p["idx"] for p in got] == [p["idx"] for p in ref]
+    finally:
+        an.use_stream(None)
+
+
+def test_dropin_call_sequence(tmp_path, golden):
+    """The call sequence of the reference's only caller (GT_FFT_v5.py:627-659) on the drop-in modules."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "apda-fft_b200"))
+    from metrics.fft_iterativa import fft, remove_dc_component, start_fft
+    from utils.get_peak_prominence import get_top_peaks_prominence
+    from utils.get_peak_resolution import get_top_peaks_resolution
+    from utils.load_data import load_sensor
+
+    g = golden["cases"]["katA"]
+    x, fs = cases.build_samples(g["spec"])
+    path = tmp_path / "0013a20041e7f6b7_Xaxis.log"
+    rows = ["2_11_22_18_20_32;2 g;125.0 Hz;X axis;", "Synced;", "25.010;-0.0222;0.0110;0.9981;85.0;", "0.268262;0.0;1.0;"]
+    vals = ["%8.6f" % v for v in x]
+    rows += [";".join(vals[i:i + 60]) + ";" for i in range(0, len(vals), 60)]
+    rows.insert(9, "* MISSING PACKETS 3-4 *")
+    path.write_text("\n".join(rows) + "\n")
+
+    data = load_sensor(str(path))
+    samples, fs_file, axis = data["samples"], data["metadata"]["fs"], data["metadata"]["axis"]
+    assert (len(samples), fs_file, axis) == (1024, 125.0, "X")
+    keep = list(samples)
+    res_fft = start_fft(samples, fs_file)
+    assert samples == keep and isinstance(res_fft, list) and res_fft[0] == 0 and type(res_fft[0]) is int
+    assert cases.spectrum_sha16(res_fft) == g["spectrum_sha"]
+    assert get_top_peaks_prominence(res_fft, fs_file) == g["prominence"]["ok"]
+    assert get_top_peaks_resolution(res_fft, fs_file) == g["resolution"]["ok"]
+    assert get_top_peaks_prominence(list(res_fft), fs_file) == g["prominence"]["ok"]      # plain list path
+    peaks = get_top_peaks_prominence(res_fft, fs_file)
+    entry = {"peak_freq": peaks[0]["freq"], "max_mag": peaks[0]["mag"]}
+    assert entry == {"peak_freq": 3.0518, "max_mag": 195.833}
+    # edge behaviour of the reference
+    assert start_fft([], 1.0) == [0] and start_fft([1.0], 1.0) == [0]
+    assert start_fft([1.0, 2.0], 1.0) == [0, (-1 + 0j)]
+    with pytest.raises(statistics.StatisticsError, match="mean requires"):
+        get_top_peaks_prominence([0], 1.0)
+    with pytest.raises(statistics.StatisticsError, match="stdev requires"):
+        get_top_peaks_resolution([0, (-1 + 0j)], 1.0)
+    assert get_top_peaks_prominence(start_fft([1.0, -2.0, 3.5, 0.25], 1.0), 1.0) == []
+    med = remove_dc_component([3.0, 1.0, 2.0, 10.0])
+    assert med == [0.5, -1.5, -0.5, 7.5]
+    z = [complex(i, -i) for i in range(8)]
+    assert fft(list(z)) == ref_port.dit_radix2(z)
+    assert start_fft(keep, fs_file)[1] == complex(*g["bins"]["1"])
