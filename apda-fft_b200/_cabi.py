@@ -26,6 +26,7 @@ SIGNATURES = {
     "apda_ctx_create": (_int, [_int, _c.POINTER(_p)]),
     "apda_ctx_destroy": (_int, [_p]),
     "apda_ctx_set_stream": (_int, [_p, _p]),
+    "apda_ctx_reset_stream": (_int, [_p]),
     "apda_sync": (_int, [_p]),
     "apda_last_error": (_c.c_char_p, []),
     "apda_version": (_int, []),
@@ -114,7 +115,11 @@ class Context:
         check(getattr(self._lib, name)(self._h, *args))
 
     def set_stream(self, cuda_stream: int | None) -> None:
-        self.call("apda_ctx_set_stream", _p(cuda_stream or 0))
+        """cuda_stream: raw cudaStream_t value (0 is the legacy default stream); None -> the context's own stream."""
+        if cuda_stream is None:
+            self.call("apda_ctx_reset_stream")
+        else:
+            self.call("apda_ctx_set_stream", _p(int(cuda_stream)))
 
     def sync(self) -> None:
         self.call("apda_sync")

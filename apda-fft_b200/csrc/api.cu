@@ -112,7 +112,13 @@ extern "C" int apda_ctx_destroy(apda_ctx *ctx) {
 
 extern "C" int apda_ctx_set_stream(apda_ctx *ctx, void *cuda_stream) {
     if (!ctx) return APDA_ERR_INVALID;
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return APDA_OK;
+}
+
+extern "C" int apda_ctx_reset_stream(apda_ctx *ctx) {
+    if (!ctx) return APDA_ERR_INVALID;
+    ctx->stream = ctx->own_stream;
     return APDA_OK;
 }
 

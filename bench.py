@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py - FFT+peak windows/sec at N=4096 on 1..8 B200 (BASELINE.json metric), one JSON line on rank 0.
+
+A "step" is one pass of the hot path over one shard of synthetic windows that is already resident in HBM:
+K1 (FFT, samples -> N complex bins) then K3 (picker, half spectrum -> 128-byte record), then - for N>1 GPUs - the
+gather of the records to rank 0.  Weak scaling: every rank owns --windows windows (default 1M: BASELINE.json's
+"Fleet sweep: 1M windows N=4096 fp32" is the N=1 workload); no collective touches the data path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Extra keys: roofline (dominant kernel K1, timed live with CUDA events), pipeline (whole step vs B_alg), e2e (host
+buffers through the C ABI, H2D/D2H inside the clock), cpu_baseline (oracle port on the host cores), clocks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "FFT+peak windows/sec at N=4096"
+UNIT = "windows/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--windows", type=int, default=1_000_000, help="windows per GPU (weak scaling)")
+    ap.add_argument("--n", type=int, default=4096, help="FFT length / samples per window")
+    ap.add_argument("--dtype", choices=["f32", "f64"], default="f32")
+    ap.add_argument("--picker", choices=["flexible", "rigid"], default="flexible")
+    ap.add_argument("--center", choices=["median", "mean"], default="median")
+    ap.add_argument("--e2e-windows", type=int, default=131072, help="windows per GPU of the host-buffer (e2e) leg")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU work budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU legs (oracle port): the reference's own algorithm on the host cores
+# ---------------------------------------------------------------------------------------------------------------
+def _cpu_worker(task):
+    first, count, n, flexible = task
+    import apda_fft_b200.synth as synth
+    from oracle import ref_port
+    done = 0
+    for w in range(first, first + count):
+        x = synth.fleet_window(w, n).tolist()
+        spec = ref_port.start_fft(x, 125.0)
+        peaks = ref_port.top_peaks_prominence(spec, 125.0) if flexible else ref_port.top_peaks_resolution(spec, 125.0)
+        done += 1 if peaks is not None else 0
+    return done
+
+
+def _cpu_gen_worker(task):
+    first, count, n, _ = task
+    import apda_fft_b200.synth as synth
+    for w in range(first, first + count):
+        synth.fleet_window(w, n).tolist()
+    return count
+
+
+def cpu_port_throughput(n: int, flexible: bool, windows_per_core: int, cores: int, pool=None):
+    """windows/s of ref_port.start_fft + picker over `cores` processes; input generation is timed separately and
+    subtracted (the GPU legs also start with resident inputs)."""
+    import multiprocessing as mp
+    own = pool is None
+    if own:
+        pool = mp.get_context("spawn").Pool(cores)
+    try:
+        tasks = [(10_000_000 + c * windows_per_core, windows_per_core, n, flexible) for c in range(cores)]
+        pool.map(_cpu_gen_worker, [(0, 1, n, flexible)] * cores)           # warm the workers (imports)
+        t0 = time.perf_counter()
+        pool.map(_cpu_gen_worker, tasks)
+        t_gen = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        done = sum(pool.map(_cpu_worker, tasks))
+        t_all = time.perf_counter() - t0
+    finally:
+        if own:
+            pool.close()
+            pool.join()
+    t = max(t_all - t_gen, 1e-9)
+    return done / t, done, t
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference is pure Python and cannot travel
+    to the GPU box) on all host cores, same metric/config; each step is a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    flexible = args.picker == "flexible"
+    per_core = 4
+    pool = mp.get_context("spawn").Pool(cores)
+    try:
+        for _ in range(args.warmup):
+            cpu_port_throughput(args.n, flexible, 1, cores, pool)
+        rates, total_t, total_w = [], 0.0, 0
+        for _ in range(args.steps):
+            r, done, t = cpu_port_throughput(args.n, flexible, per_core, cores, pool)
+            rates.append(r)
+            total_t += t
+            total_w += done
+    finally:
+        pool.close()
+        pool.join()
+    value = total_w / total_t
+    sample = f"{per_core * cores} windows per step ({per_core} per core), fp64 (the reference has no fp32 path)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"fleet sweep: {args.windows} windows/GPU x N={args.n} {args.dtype}, {args.picker} picker "
+                    f"(k={'4' if args.picker == 'flexible' else '5'}), K1 FFT + K3 peaks + gather of 128 B records",
+        "windows_per_gpu": args.windows, "n_fft": args.n, "picker": args.picker, "centering": args.center,
+        "parallelism": f"batch-sharded x{world}, records gathered to rank 0",
+        "l2": "inputs (windows*N*s bytes) and spectra far exceed the 126 MB L2; no flush needed",
+    }
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel_key: str):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            return json.load(fh).get(kernel_key)
+    except Exception:
+        return None
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import apda_fft_b200
+    from apda_fft_b200 import _cabi
+    from apda_fft_b200.fleet import gather_records
+    from apda_fft_b200.records import record_dtype
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    s_bytes = 4 if args.dtype == "f32" else 8
+    tdt = torch.float32 if args.dtype == "f32" else torch.float64
+    n, b = args.n, args.windows
+    flexible = args.picker == "flexible"
+    k = 4 if flexible else 5
+    center = _cabi.CENTER_MEDIAN if args.center == "median" else _cabi.CENTER_MEAN
+    fs = 125.0
+
+    an = apda_fft_b200.Analyzer(local)
+    stream = torch.cuda.current_stream(dev)
+    an.use_stream(stream.cuda_stream)
+
+    d_x = torch.empty((b, n), dtype=tdt, device=dev)
+    d_spec = torch.empty((b, n, 2), dtype=tdt, device=dev)
+    d_rec = torch.zeros((b, 128), dtype=torch.uint8, device=dev)
+    an.synth_device(rank * b, b, n, args.dtype, d_x.data_ptr())
+    torch.cuda.synchronize()
+
+    k1_events = []
+
+    def step(record_k1: bool):
+        if record_k1:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+        an.fft_device(d_x.data_ptr(), b, n, n, args.dtype, d_spec.data_ptr(), center=center)
+        if record_k1:
+            e1.record(stream)
+            k1_events.append((e0, e1))
+        an.peaks_device(d_spec.data_ptr(), b, n, args.dtype, fs, d_rec.data_ptr(), flexible=flexible, k=k, rec_cap=5)
+        if world > 1:
+            return gather_records(d_rec, b * world, dst=0)
+        return d_rec
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    fence()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = an.launch_count()
+    t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record(stream)
+    table = None
+    for _ in range(args.steps):
+        table = step(True)
+    t_stop.record(stream)
+    fence()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = an.launch_count() - launches0
+    elapsed_ms = t_start.elapsed_time(t_stop)
+    k1_ms = sum(a.elapsed_time(z) for a, z in k1_events) / max(len(k1_events), 1)
+    red = torch.tensor([elapsed_ms, k1_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+    elapsed_ms, k1_ms = float(red[0]), float(red[1])
+
+    # sanity of the result actually produced in the timed region (rank 0 sees the gathered table)
+    summary = None
+    if rank == 0:
+        recs = table.cpu().numpy().view(record_dtype(5)).reshape(-1)
+        summary = {"windows_in_table": int(recs.shape[0]), "mean_peaks_per_window": float(recs["count"].mean()),
+                   "status_nonzero": int((recs["status"] != 0).sum())}
+
+    # ---- e2e: host buffers through the C ABI, copies inside the clock ------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        eb = min(args.e2e_windows, b)
+        h_x = torch.empty((eb, n), dtype=tdt).pin_memory()
+        h_x.copy_(d_x[:eb])
+        h_rec = torch.zeros((eb, 128), dtype=torch.uint8).pin_memory()
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            an.analyze_host_ptr(h_x.data_ptr(), eb, n, n, args.dtype, fs, h_rec.data_ptr(), flexible=flexible, k=k,
+                                rec_cap=5, center=center)
+
+        e2e_step()
+        fence()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        same = bool((h_rec.numpy() == d_rec[:eb].cpu().numpy()).all())
+        e2e = {"value": eb * world * args.e2e_steps / float(t_e2e[0]), "unit": UNIT,
+               "h2d_bytes_per_step": eb * n * s_bytes, "d2h_bytes_per_step": eb * 128,
+               "windows_per_gpu_per_step": eb, "records_equal_device_path": same,
+               "api": f"apda_analyze_{args.dtype}_host (pinned host buffers, chunked 2-stream H2D/compute/D2H)"}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        k1_bytes = 3 * s_bytes * n * b
+        b_alg = (4 * s_bytes * n + 128) * b
+        value = b * world * args.steps / (elapsed_ms * 1e-3)
+        k1_gbs = k1_bytes / (k1_ms * 1e-3) / 1e9
+        step_ms = elapsed_ms / args.steps
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, world),
+            "roofline": {"bound": "hbm", "kernel": "K1 fft (samples -> N complex bins)", "achieved": k1_gbs,
+                         "peak": peak, "unit": "GB/s", "frac": k1_gbs / peak, "peak_source": peak_src,
+                         "bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms,
+                         "traffic": ncu_traffic(f"k1_{args.dtype}_n{n}")},
+            "pipeline": {"b_alg_bytes_per_window": 4 * s_bytes * n + 128,
+                         "achieved_gbs_per_gpu": b_alg / (step_ms * 1e-3) / 1e9,
+                         "frac_of_peak": b_alg / (step_ms * 1e-3) / 1e9 / peak,
+                         "k1_share_of_step": k1_ms / step_ms},
+            "e2e": e2e, "gpu_launches": int(launches) * world, "clocks": clocks, "result_check": summary,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            per_core = max(2, int(args.cpu_seconds / 0.019 / cores))
+            rate, done, t = cpu_port_throughput(args.n, flexible, per_core, cores)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{done} windows of the same generator ({per_core} per core) in {t:.1f} s; "
+                                              "oracle/ref_port.py (pure-Python restatement, fp64)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

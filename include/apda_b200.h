@@ -63,8 +63,10 @@ typedef struct apda_ctx apda_ctx;
 /* ---- context ---------------------------------------------------------------------------------------------- */
 int apda_ctx_create(int device, apda_ctx **out);
 int apda_ctx_destroy(apda_ctx *ctx);
-/* Run the _dev entry points on a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); NULL restores the context's own. */
+/* Run the _dev entry points on a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream; the value 0
+ * is CUDA's legacy default stream).  apda_ctx_reset_stream goes back to the context's own non-blocking stream. */
 int apda_ctx_set_stream(apda_ctx *ctx, void *cuda_stream);
+int apda_ctx_reset_stream(apda_ctx *ctx);
 int apda_sync(apda_ctx *ctx);
 const char *apda_last_error(void);
 int apda_version(void);
