@@ -98,6 +98,7 @@ extern "C" int apda_ctx_destroy(apda_ctx *ctx) {
         cudaFree(kv.second.d64);
         cudaFree(kv.second.d32);
     }
+    fft_f32_fast_release(ctx);
     cudaFree(ctx->ws);
     cudaFree(ctx->ws_small);
     for (int i = 0; i < 2; ++i) {
@@ -236,6 +237,9 @@ static int fft_dispatch(apda_ctx *ctx, cudaStream_t st, const T *d_samples, int6
         apda_set_error("fft: APDA_CENTER_MEAN is an fp32-only option; the fp64 path is bit-faithful to the reference");
         return APDA_ERR_INVALID;
     }
+    if (sizeof(T) == 4 && !complex_in && fft_f32_fast_supports(N))
+        return launch_fft_f32_fast(ctx, st, reinterpret_cast<const float *>(d_samples), n_samples, ld, batch, N, flags,
+                                   reinterpret_cast<float *>(d_spec));
     if (N <= fft_smem_max_n<T>(ctx)) return launch_fft_smem<T>(ctx, st, d_samples, n_samples, ld, batch, N, flags, d_spec, complex_in);
     return launch_fft_large<T>(ctx, st, d_samples, n_samples, ld, batch, N, flags, d_spec, complex_in);
 }

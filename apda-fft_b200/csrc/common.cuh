@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <map>
+#include <vector>
 #include <string>
 
 #include "../../include/apda_b200.h"
@@ -75,6 +76,10 @@ int launch_synth(apda_ctx *ctx, cudaStream_t st, int64_t first, int64_t count, i
                  T *d_out);
 template <typename T>
 int64_t fft_smem_max_n(apda_ctx *ctx);
+bool fft_f32_fast_supports(int64_t N);
+int launch_fft_f32_fast(apda_ctx *ctx, cudaStream_t st, const float *d_samples, int64_t n_samples, int64_t ld,
+                        int64_t batch, int64_t N, int flags, float *d_spec);
+void fft_f32_fast_release(apda_ctx *ctx);
 int launch_center_f64(apda_ctx *ctx, cudaStream_t st, const double *d_in, int64_t n, double *d_out);
 int launch_mag_helpers_f64(apda_ctx *ctx, cudaStream_t st, const double *d_mags, int64_t n, int64_t idx, double prom_in,
                            double *d_out3);

@@ -270,3 +270,25 @@ def test_dropin_call_sequence(tmp_path, golden):
     z = [complex(i, -i) for i in range(8)]
     assert fft(list(z)) == ref_port.dit_radix2(z)
     assert start_fft(keep, fs_file)[1] == complex(*g["bins"]["1"])
+
+
+@pytest.mark.parametrize("n_fft", [1024, 2048, 4096, 8192])
+def test_f32_fast_kernel_median_and_padding(n_fft, an):
+    """The fp32 fast kernel's in-register exact median: skewed, heavily tied data, odd/even/padded lengths.
+    A wrong order statistic moves the low bins by ~1e-2 of the scale; the bound below is 3e-6."""
+    rng = np.random.default_rng(n_fft)
+    for n_samples in (n_fft, n_fft - 1, n_fft - 2, (3 * n_fft) // 4 + 1, n_fft // 2 + 1, n_fft // 2 + 2):
+        rows = []
+        rows.append(np.round(np.exp(rng.standard_normal(n_samples)), 2))                 # skewed, many ties
+        rows.append(np.round(rng.standard_normal(n_samples) * 0.3 + 5.0, 3))             # large offset
+        rows.append((rng.random(n_samples) < 0.5).astype(np.float64))                    # two values only
+        rows.append(np.round(np.sin(np.arange(n_samples) * 0.05) + 0.2 * rng.standard_normal(n_samples), 6))
+        rows.append(np.zeros(n_samples))                                                 # constant
+        x = np.stack(rows).astype(np.float32)
+        got = an.fft(x, n_fft=n_fft)
+        want = c_oracle.start_fft_batch(x.astype(np.float64), n_fft=n_fft)
+        for r in range(x.shape[0]):
+            scale = max(np.abs(want[r]).max(), 1e-3)
+            err = np.abs(got[r].astype(np.complex128) - want[r]).max()
+            # the fp32 median itself carries half an ulp of |x|, which n_samples samples add coherently into the low bins
+            assert err <= 3e-6 * scale + n_samples * float(np.abs(x[r]).max()) * 1.2e-7, (n_fft, n_samples, r, err, scale)
