@@ -27,6 +27,7 @@ SIGNATURES = {
     "apda_ctx_destroy": (_int, [_p]),
     "apda_ctx_set_stream": (_int, [_p, _p]),
     "apda_ctx_reset_stream": (_int, [_p]),
+    "apda_ctx_set_generic_only": (_int, [_p, _int]),
     "apda_sync": (_int, [_p]),
     "apda_last_error": (_c.c_char_p, []),
     "apda_version": (_int, []),
@@ -43,6 +44,8 @@ SIGNATURES = {
     "apda_peaks_resolution_f32_dev": (_int, [_p, _p, _i64, _i64, _dbl, _p, _int, _int, _p]),
     "apda_peaks_prominence_f64_host": (_int, [_p, _p, _i64, _i64, _dbl, _p, _int, _int, _p]),
     "apda_peaks_resolution_f64_host": (_int, [_p, _p, _i64, _i64, _dbl, _p, _int, _int, _p]),
+    "apda_peaks_prominence_f32_host": (_int, [_p, _p, _i64, _i64, _dbl, _p, _int, _int, _p]),
+    "apda_peaks_resolution_f32_host": (_int, [_p, _p, _i64, _i64, _dbl, _p, _int, _int, _p]),
     "apda_analyze_f64_dev": (_int, [_p, _p, _i64, _i64, _i64, _i64, _int, _int, _dbl, _p, _int, _int, _p, _p]),
     "apda_analyze_f32_dev": (_int, [_p, _p, _i64, _i64, _i64, _i64, _int, _int, _dbl, _p, _int, _int, _p, _p]),
     "apda_analyze_f64_host": (_int, [_p, _p, _i64, _i64, _i64, _i64, _int, _int, _dbl, _p, _int, _int, _p]),
@@ -120,6 +123,9 @@ class Context:
             self.call("apda_ctx_reset_stream")
         else:
             self.call("apda_ctx_set_stream", _p(int(cuda_stream)))
+
+    def set_generic_only(self, on: bool) -> None:
+        self.call("apda_ctx_set_generic_only", int(bool(on)))
 
     def sync(self) -> None:
         self.call("apda_sync")

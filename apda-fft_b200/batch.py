@@ -55,14 +55,16 @@ class Analyzer:
 
     def peaks(self, spectra: np.ndarray, fs, flexible: bool = True, k: int | None = None,
               rec_cap: int | None = None) -> np.ndarray:
-        """[B, n] complex128 spectra -> records[B]."""
-        z = np.ascontiguousarray(np.atleast_2d(spectra), dtype=np.complex128)
+        """[B, n] complex spectra -> records[B]; complex64 input runs the fp32 kernels, anything else the fp64 ones."""
+        z = np.atleast_2d(spectra)
+        sfx = "f32" if z.dtype == np.complex64 else "f64"
+        z = np.ascontiguousarray(z, dtype=np.complex64 if sfx == "f32" else np.complex128)
         b, n = z.shape
         k = (4 if flexible else 5) if k is None else int(k)
         cap = max(5, k) if rec_cap is None else int(rec_cap)
         recs = np.zeros(b, dtype=record_dtype(cap))
         fs_scalar, fs_arr = self._fs(fs, b)
-        name = "apda_peaks_prominence_f64_host" if flexible else "apda_peaks_resolution_f64_host"
+        name = f"apda_peaks_prominence_{sfx}_host" if flexible else f"apda_peaks_resolution_{sfx}_host"
         self.ctx.call(name, _p(z.ctypes.data), n, b, fs_scalar, _p(fs_arr.ctypes.data if fs_arr is not None else 0),
                       k, cap, _p(recs.ctypes.data))
         return recs

@@ -123,6 +123,12 @@ extern "C" int apda_ctx_reset_stream(apda_ctx *ctx) {
     return APDA_OK;
 }
 
+extern "C" int apda_ctx_set_generic_only(apda_ctx *ctx, int on) {
+    if (!ctx) return APDA_ERR_INVALID;
+    ctx->generic_only = on ? 1 : 0;
+    return APDA_OK;
+}
+
 extern "C" int apda_sync(apda_ctx *ctx) {
     if (!ctx) return APDA_ERR_INVALID;
     APDA_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -237,7 +243,7 @@ static int fft_dispatch(apda_ctx *ctx, cudaStream_t st, const T *d_samples, int6
         apda_set_error("fft: APDA_CENTER_MEAN is an fp32-only option; the fp64 path is bit-faithful to the reference");
         return APDA_ERR_INVALID;
     }
-    if (sizeof(T) == 4 && !complex_in && fft_f32_fast_supports(N))
+    if (sizeof(T) == 4 && !complex_in && !ctx->generic_only && fft_f32_fast_supports(N))
         return launch_fft_f32_fast(ctx, st, reinterpret_cast<const float *>(d_samples), n_samples, ld, batch, N, flags,
                                    reinterpret_cast<float *>(d_spec));
     if (N <= fft_smem_max_n<T>(ctx)) return launch_fft_smem<T>(ctx, st, d_samples, n_samples, ld, batch, N, flags, d_spec, complex_in);
@@ -453,6 +459,18 @@ extern "C" int apda_peaks_resolution_f64_host(apda_ctx *ctx, const double *h_spe
     APDA_TRY(check_peaks_args(ctx, h_spec, n, batch, k, rec_cap, h_rec));
     return host_pipeline<double>(ctx, kPeaksOnly, h_spec, 0, 0, batch, n, 0, 0, fs, h_fs, k, rec_cap, false, nullptr,
                                  h_rec);
+}
+extern "C" int apda_peaks_prominence_f32_host(apda_ctx *ctx, const float *h_spec, int64_t n, int64_t batch, double fs,
+                                              const double *h_fs, int k, int rec_cap, void *h_rec) {
+    APDA_TRY(check_peaks_args(ctx, h_spec, n, batch, k, rec_cap, h_rec));
+    return host_pipeline<float>(ctx, kPeaksOnly, h_spec, 0, 0, batch, n, 0, 1, fs, h_fs, k, rec_cap, false, nullptr,
+                                h_rec);
+}
+extern "C" int apda_peaks_resolution_f32_host(apda_ctx *ctx, const float *h_spec, int64_t n, int64_t batch, double fs,
+                                              const double *h_fs, int k, int rec_cap, void *h_rec) {
+    APDA_TRY(check_peaks_args(ctx, h_spec, n, batch, k, rec_cap, h_rec));
+    return host_pipeline<float>(ctx, kPeaksOnly, h_spec, 0, 0, batch, n, 0, 0, fs, h_fs, k, rec_cap, false, nullptr,
+                                h_rec);
 }
 extern "C" int apda_analyze_f64_host(apda_ctx *ctx, const double *h_samples, int64_t n_samples, int64_t ld,
                                      int64_t batch, int64_t N, int flags, int flexible, double fs, const double *h_fs,

@@ -456,6 +456,9 @@ template <typename T>
 int launch_peaks(apda_ctx *ctx, cudaStream_t st, const T *d_spec, int64_t n, int64_t batch, double fs,
                  const double *d_fs, int k, int rec_cap, int flexible, void *d_rec, void *d_mag_ws) {
     using V2 = typename vec2<T>::type;
+    if (sizeof(T) == 4 && !ctx->generic_only && peaks_f32_fast_supports(n, k, rec_cap))
+        return launch_peaks_f32_fast(ctx, st, reinterpret_cast<const float *>(d_spec), n, batch, fs, d_fs, k, flexible,
+                                     d_rec);
     const int half = (int)(n / 2);
     const Layout lay = make_layout<T>(half);
     const bool in_smem = lay.bytes + 4096 <= (size_t)ctx->smem_optin;

@@ -1,0 +1,440 @@
+// K3 (fp32 fast form) for n = 1024 / 2048 / 4096 / 8192 bins per window, k <= 5, 128-byte records: the headline picker.
+//
+// One WARP per window, four windows per CTA, no block-level barrier.
+//   phase 1  32 lanes stream the half spectrum with coalesced 128-bit loads (8 in flight per lane), take magnitudes,
+//            accumulate sum / sum of squares in registers and stage the magnitudes in shared memory;
+//   phase 2  every lane re-reads one CONTIGUOUS chunk of HALF/32 bins (conflict-free 128-bit LDS thanks to a 4-word
+//            pad per chunk), keeps the chunk's max and min in registers and appends the few bins above
+//            mean + 2 sigma ("hot" bins, < 20 % of the bins by Cantelli's inequality, typically ~10) to a slot list;
+//   flexible picker: for every hot strict local maximum the prominence walk runs on the chunk summaries - whole
+//            chunks are skipped with one ballot over the lanes' chunk maxima, only the two boundary chunks are
+//            scanned (warp-cooperatively, 32 bins per step); the scalar epilogue (half-power width, damping gate,
+//            decimal rounding) runs lane-parallel, one candidate per lane; a warp arg-max extracts the order
+//            "descending round(mag, 4), ascending idx" for the greedy hump exclusion;
+//   rigid picker: the iterative arg-max / resolution test / +-2 % zeroing loop works on the hot list only (zeroing
+//            can only create new maxima among bins that were already above the threshold).
+// The record (128 B) is assembled in shared memory and written with one coalesced 128-byte store.
+//
+// Decision semantics are those of peaks.cu (the general kernel), which documents the reference line by line:
+//   utils/get_peak_prominence.py:149-226, utils/get_peak_resolution.py:80-128.
+#include "common.cuh"
+
+namespace {
+
+struct Slot {
+    uint16_t idx;
+    uint16_t width;  // flexible: half-power bins if the candidate passed every gate, else 0
+    float prom;
+};
+
+template <int HALF>
+struct K3 {
+    static constexpr int C = HALF / 32;                // bins per lane chunk
+    static constexpr int MAGW = HALF + 4 * 32;         // magnitude words incl. 4-word pad per chunk
+    static constexpr int SLOTS = ((HALF / 5 + 8) + 1) & ~1;
+    static constexpr int REC_OFF = MAGW * 4 + SLOTS * 8;
+    static constexpr int BYTES = (REC_OFF + 128 + 15) & ~15;
+    __device__ static __forceinline__ int addr(int b) { return b + 4 * (b / C); }
+};
+
+__device__ __forceinline__ double round_dec4_d(double x) {  // exact emulation of Python round(x, 4); see peaks.cu
+    const double p = 1e4;
+    double hi = mul_rn(x, p);
+    double lo = __fma_rn(x, p, -hi);
+    double n = rint(hi);
+    double d = sub_rn(hi, n);
+    if (d == 0.5 && lo > 0.0) n += 1.0;
+    if (d == -0.5 && lo < 0.0) n -= 1.0;
+    return div_rn(n, p);
+}
+
+__device__ __forceinline__ float4 ldg_stream(const float4 *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// one direction of the prominence walk inside [lo_b, hi_b] (a piece of one chunk), 32 bins per step.
+// DIR = -1: from hi_b downwards, +1: from lo_b upwards.  Returns true when a bin strictly higher than p stopped it.
+template <int HALF, int DIR>
+__device__ __forceinline__ bool scan_piece(const float *mags, int lo_b, int hi_b, float p, float &floor_lane, int lane) {
+    if (DIR < 0) {
+        for (int base = hi_b; base >= lo_b; base -= 32) {
+            const int i = base - lane;
+            const bool valid = i >= lo_b;
+            const float v = valid ? mags[K3<HALF>::addr(i)] : p;
+            const unsigned higher = __ballot_sync(0xffffffffu, valid && v > p);
+            const int stop = higher ? (__ffs(higher) - 1) : 32;
+            if (lane < stop && v < floor_lane) floor_lane = v;
+            if (higher) return true;
+        }
+    } else {
+        for (int base = lo_b; base <= hi_b; base += 32) {
+            const int i = base + lane;
+            const bool valid = i <= hi_b;
+            const float v = valid ? mags[K3<HALF>::addr(i)] : p;
+            const unsigned higher = __ballot_sync(0xffffffffu, valid && v > p);
+            const int stop = higher ? (__ffs(higher) - 1) : 32;
+            if (lane < stop && v < floor_lane) floor_lane = v;
+            if (higher) return true;
+        }
+    }
+    return false;
+}
+
+// utils/get_peak_prominence.py:32-54 on the chunk summaries (cmax/cmin: this lane's chunk maximum / minimum)
+template <int HALF>
+__device__ float coop_prominence(const float *mags, int j, float cmax, float cmin, int lane) {
+    constexpr int C = K3<HALF>::C;
+    const float p = mags[K3<HALF>::addr(j)];
+    const int cj = j / C;
+    const unsigned above = __ballot_sync(0xffffffffu, cmax > p);
+    float fl = p, fr = p;
+    if (!scan_piece<HALF, -1>(mags, C * cj, j - 1, p, fl, lane)) {
+        const unsigned hl = above & ((1u << cj) - 1u);
+        const int L = hl ? 31 - __clz(hl) : -1;
+        if (lane > L && lane < cj && cmin < fl) fl = cmin;
+        if (L >= 0) scan_piece<HALF, -1>(mags, C * L, C * (L + 1) - 1, p, fl, lane);
+    }
+    if (!scan_piece<HALF, +1>(mags, j + 1, C * (cj + 1) - 1, p, fr, lane)) {
+        const unsigned hr = above & ~((2u << cj) - 1u);
+        const int R = hr ? __ffs(hr) - 1 : 32;
+        if (lane > cj && lane < R && cmin < fr) fr = cmin;
+        if (R < 32) scan_piece<HALF, +1>(mags, C * R, C * (R + 1) - 1, p, fr, lane);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        fl = fminf(fl, __shfl_xor_sync(0xffffffffu, fl, o));
+        fr = fminf(fr, __shfl_xor_sync(0xffffffffu, fr, o));
+    }
+    return __fsub_rn(p, fmaxf(fl, fr));
+}
+
+template <int HALF>
+__device__ __forceinline__ int half_power_bins_f(const float *mags, float prom, int j) {
+    const float top = mags[K3<HALF>::addr(j)];
+    const float level = __fadd_rn(__fsub_rn(top, prom), __fmul_rn(prom, 0.707f));
+    int lo = j;
+    while (lo > 0 && mags[K3<HALF>::addr(lo)] > level) {
+        if (mags[K3<HALF>::addr(lo)] > top) break;
+        --lo;
+    }
+    int hi = j;
+    while (hi < HALF - 1 && mags[K3<HALF>::addr(hi)] > level) {
+        if (mags[K3<HALF>::addr(hi)] > top) break;
+        ++hi;
+    }
+    const int w = hi - lo;
+    return w > 1 ? w : 1;
+}
+
+template <int HALF>
+__device__ __forceinline__ int half_height_bins_f(const float *mags, int j) {
+    const float level = __fmul_rn(0.707f, mags[K3<HALF>::addr(j)]);
+    int lo = j;
+    while (lo > 0 && mags[K3<HALF>::addr(lo)] > level) --lo;
+    int hi = j;
+    while (hi < HALF && mags[K3<HALF>::addr(hi)] > level) ++hi;
+    return hi - lo;
+}
+
+template <int HALF, bool FLEX>
+__global__ void __launch_bounds__(128)
+peaks_f32_fast_kernel(const float2 *__restrict__ spec, int64_t batch, double fs_all, const double *__restrict__ d_fs,
+                      int k, unsigned char *__restrict__ recs) {
+    using P = K3<HALF>;
+    constexpr int C = P::C;
+    constexpr int N = 2 * HALF;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int nslot_s[4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t win = (int64_t)blockIdx.x * 4 + warp;
+    if (win >= batch) return;
+    unsigned char *base = smem_raw + warp * P::BYTES;
+    float *mags = reinterpret_cast<float *>(base);
+    Slot *slots = reinterpret_cast<Slot *>(base + P::MAGW * 4);
+    unsigned char *rec_s = base + P::REC_OFF;
+    if (lane == 0) nslot_s[warp] = 0;
+
+    // ---- phase 1: stream the half spectrum, magnitudes -> shared memory, statistics in registers -------------------
+    const float4 *src = reinterpret_cast<const float4 *>(spec + win * (int64_t)N);
+    float sum = 0.f, sumsq = 0.f;
+    constexpr int ROWS = HALF / 64, BATCH = ROWS < 8 ? ROWS : 8;
+#pragma unroll 1
+    for (int r0 = 0; r0 < ROWS; r0 += BATCH) {
+        float4 z[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) z[u] = ldg_stream(src + (r0 + u) * 32 + lane);
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) {
+            const float p0 = fmaf(z[u].x, z[u].x, z[u].y * z[u].y), p1 = fmaf(z[u].z, z[u].z, z[u].w * z[u].w);
+            const float m0 = sqrtf(p0), m1 = sqrtf(p1);
+            sum += m0 + m1;
+            sumsq += p0 + p1;
+            const int b = 64 * (r0 + u) + 2 * lane;
+            *reinterpret_cast<float2 *>(mags + P::addr(b)) = make_float2(m0, m1);
+        }
+    }
+    double S = (double)sum, Q = (double)sumsq;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        S += __shfl_xor_sync(0xffffffffu, S, o);
+        Q += __shfl_xor_sync(0xffffffffu, Q, o);
+    }
+    const double nn = (double)HALF;
+    const double mean = S / nn;
+    const double var = (Q - S * S / nn) / (nn - 1.0);
+    const double sd = var > 0.0 ? sqrt(var) : 0.0;
+    const double thr = mean + 2.0 * sd;
+    const float thr_f = __double2float_rd(thr);  // for floats m:  m > thr  <=>  m > thr_f
+    const double fs = d_fs ? d_fs[win] : fs_all;
+    const double df = div_rn(fs, (double)N);
+    __syncwarp();
+
+    // ---- phase 2: contiguous chunk per lane: chunk max/min, hot bins -> slot list -------------------------------------
+    float cmax = -CUDART_INF_F, cmin = CUDART_INF_F;
+    {
+        const float4 *ch = reinterpret_cast<const float4 *>(mags + P::addr(C * lane));
+#pragma unroll 4
+        for (int q = 0; q < C / 4; ++q) {
+            const float4 v = ch[q];
+            const float m4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+            cmax = fmaxf(cmax, m4);
+            cmin = fminf(cmin, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
+            if (m4 > thr_f) {
+                const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (e[u] > thr_f) {
+                        const int j = C * lane + 4 * q + u;
+                        bool take = true;
+                        if (FLEX)  // strict local maximum, candidates j in [1, HALF-2]
+                            take = j >= 1 && j <= HALF - 2 && e[u] > mags[P::addr(j - 1)] && e[u] > mags[P::addr(j + 1)];
+                        if (take) {
+                            const int pos = atomicAdd(&nslot_s[warp], 1);
+                            if (pos < P::SLOTS) slots[pos].idx = (uint16_t)j;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    const int nslot_raw = nslot_s[warp];
+    const int nslot = min(nslot_raw, P::SLOTS);
+    const int status = nslot_raw > P::SLOTS ? 1 : 0;
+
+    int na = 0;
+    if (FLEX) {
+        // ---- A: cooperative prominence per candidate -----------------------------------------------------------------
+        for (int c = 0; c < nslot; ++c) {
+            const int j = slots[c].idx;
+            const float prom = coop_prominence<HALF>(mags, j, cmax, cmin, lane);
+            if (lane == 0) slots[c].prom = prom;
+        }
+        __syncwarp();
+        // ---- B: lane-parallel gates (one candidate per lane) ---------------------------------------------------------
+        const double half_sd = mul_rn(0.5, sd);
+        for (int c = lane; c < nslot; c += 32) {
+            const int j = slots[c].idx;
+            const float prom = slots[c].prom;
+            int width = 0;
+            if ((double)prom > half_sd) {
+                const int bins = half_power_bins_f<HALF>(mags, prom, j);
+                const double width_hz = mul_rn((double)bins, df);
+                if (width_hz > 0.0) {
+                    const double fn = mul_rn((double)j, df);
+                    const double q = div_rn(fn, width_hz);
+                    const double damping = div_rn(1.0, mul_rn(2.0, q));
+                    if (0.001 <= damping && damping <= 0.07) width = bins;
+                }
+            }
+            slots[c].width = (uint16_t)width;
+        }
+        __syncwarp();
+        // ---- C: extract "descending round(mag,4), ascending idx", greedy hump exclusion, stop at k -------------------
+        double prev_mag = CUDART_INF;
+        int prev_idx = -1;
+        int acc_idx[5];
+        float acc_prom[5];
+        int acc_w[5];
+#pragma unroll
+        for (int a = 0; a < 5; ++a) acc_idx[a] = -1, acc_prom[a] = 0.f, acc_w[a] = 0;
+        while (na < k) {
+            double best = -1.0;
+            int best_idx = 0x7fffffff, best_e = -1;
+            for (int e = lane; e < nslot; e += 32) {
+                if (slots[e].width == 0) continue;
+                const int ix = slots[e].idx;
+                const double r = round_dec4_d((double)mags[P::addr(ix)]);
+                const bool after_prev = r < prev_mag || (r == prev_mag && ix > prev_idx);
+                if (after_prev && (r > best || (r == best && ix < best_idx))) {
+                    best = r;
+                    best_idx = ix;
+                    best_e = e;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double r = __shfl_xor_sync(0xffffffffu, best, o);
+                const int ix = __shfl_xor_sync(0xffffffffu, best_idx, o);
+                const int e = __shfl_xor_sync(0xffffffffu, best_e, o);
+                if (e >= 0 && (best_e < 0 || r > best || (r == best && ix < best_idx))) {
+                    best = r;
+                    best_idx = ix;
+                    best_e = e;
+                }
+            }
+            if (best_e < 0) break;
+            prev_mag = best;
+            prev_idx = best_idx;
+            const float cprom = slots[best_e].prom;
+            bool hump = false;
+            if (na > 0) {
+                const double cf = round_dec4_d(mul_rn((double)best_idx, df));
+#pragma unroll
+                for (int a = 0; a < 5; ++a) {
+                    if (a < na && !hump) {
+                        const double af = round_dec4_d(mul_rn((double)acc_idx[a], df));
+                        const double rel = div_rn(fabs(sub_rn(cf, af)), af);
+                        if (rel < 0.05 && div_rn((double)cprom, best) < 0.10) hump = true;
+                    }
+                }
+            }
+            if (!hump) {
+#pragma unroll
+                for (int a = 0; a < 5; ++a)
+                    if (a == na) acc_idx[a] = best_idx, acc_prom[a] = cprom, acc_w[a] = slots[best_e].width;
+                ++na;
+            }
+        }
+        if (lane == 0) {
+            reinterpret_cast<int *>(rec_s)[0] = na;
+            reinterpret_cast<int *>(rec_s)[1] = status;
+#pragma unroll
+            for (int a = 0; a < 5; ++a) {
+                unsigned char *pk = rec_s + 8 + 24 * a;
+                const bool on = a < na;
+                reinterpret_cast<int *>(pk)[0] = on ? acc_idx[a] : -1;
+                reinterpret_cast<int *>(pk)[1] = on ? acc_w[a] : 0;
+                reinterpret_cast<double *>(pk + 8)[0] = on ? (double)mags[P::addr(acc_idx[a])] : 0.0;
+                reinterpret_cast<double *>(pk + 8)[1] = on ? (double)acc_prom[a] : 0.0;
+            }
+        }
+    } else {
+        // ---- rigid picker on the hot list ---------------------------------------------------------------------------------
+        const double distance = sub_rn(mul_rn(2.0, df), mul_rn(1.0, df));
+        int acc_idx[5];
+#pragma unroll
+        for (int a = 0; a < 5; ++a) acc_idx[a] = -1;
+        if (lane == 0) {
+#pragma unroll
+            for (int a = 0; a < 5; ++a) {
+                unsigned char *pk = rec_s + 8 + 24 * a;
+                reinterpret_cast<int *>(pk)[0] = -1;
+                reinterpret_cast<int *>(pk)[1] = 0;
+                reinterpret_cast<double *>(pk + 8)[0] = 0.0;
+                reinterpret_cast<double *>(pk + 8)[1] = 0.0;
+            }
+        }
+        while (na < k) {
+            float bm = -1.f;
+            int bj = -1;
+            for (int e = lane; e < nslot; e += 32) {
+                const int j = slots[e].idx;
+                const float m = mags[P::addr(j)];
+                if (j >= 1 && j <= HALF - 2 && m > thr_f && m > mags[P::addr(j - 1)] && m > mags[P::addr(j + 1)] &&
+                    (m > bm || (m == bm && j < bj))) {
+                    bm = m;
+                    bj = j;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float m2 = __shfl_xor_sync(0xffffffffu, bm, o);
+                const int j2 = __shfl_xor_sync(0xffffffffu, bj, o);
+                if (j2 >= 0 && (bj < 0 || m2 > bm || (m2 == bm && j2 < bj))) {
+                    bm = m2;
+                    bj = j2;
+                }
+            }
+            if (bj < 0) break;
+            const int w2 = half_height_bins_f<HALF>(mags, bj);
+            bool separated = true;
+#pragma unroll
+            for (int a = 0; a < 5; ++a) {
+                if (a < na && separated) {
+                    const int w1 = half_height_bins_f<HALF>(mags, acc_idx[a]);
+                    double rs = 0.0;
+                    if (w1 + w2 != 0) rs = div_rn(mul_rn(1.18, (double)abs(bj - acc_idx[a])), (double)(w1 + w2));
+                    if (!(rs >= 1.5)) separated = false;
+                }
+            }
+            if (separated) {
+                if (lane == 0) {
+                    unsigned char *pk = rec_s + 8 + 24 * na;
+                    reinterpret_cast<int *>(pk)[0] = bj;
+                    reinterpret_cast<int *>(pk)[1] = w2;
+                    reinterpret_cast<double *>(pk + 8)[0] = (double)bm;
+                }
+#pragma unroll
+                for (int a = 0; a < 5; ++a)
+                    if (a == na) acc_idx[a] = bj;
+                ++na;
+            }
+            const double f = mul_rn((double)bj, df);
+            double reach_d = rint(div_rn(mul_rn(f, 0.02), distance));
+            if (!(reach_d >= 0.0)) reach_d = 0.0;
+            if (reach_d > (double)HALF) reach_d = (double)HALF;
+            const int reach = (int)reach_d;
+            const int z0 = max(0, bj - reach), z1 = min(HALF, bj + reach + 1);
+            __syncwarp();
+            for (int b = z0 + lane; b < z1; b += 32) mags[P::addr(b)] = 0.f;
+            __syncwarp();
+        }
+        if (lane == 0) {
+            reinterpret_cast<int *>(rec_s)[0] = na;
+            reinterpret_cast<int *>(rec_s)[1] = status;
+        }
+    }
+    __syncwarp();
+    if (lane < 16) {
+        const double2 *s2 = reinterpret_cast<const double2 *>(rec_s);
+        (void)s2;
+        reinterpret_cast<uint64_t *>(recs + win * 128)[lane] = reinterpret_cast<const uint64_t *>(rec_s)[lane];
+    }
+}
+
+template <int HALF>
+int launch_half(apda_ctx *ctx, cudaStream_t st, const float *d_spec, int64_t batch, double fs, const double *d_fs,
+                int k, int flexible, void *d_rec) {
+    const int smem = 4 * K3<HALF>::BYTES;
+    auto kern = flexible ? peaks_f32_fast_kernel<HALF, true> : peaks_f32_fast_kernel<HALF, false>;
+    APDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int64_t blocks = (batch + 3) / 4;
+    kern<<<(unsigned)blocks, 128, smem, st>>>(reinterpret_cast<const float2 *>(d_spec), batch, fs, d_fs, k,
+                                              reinterpret_cast<unsigned char *>(d_rec));
+    ctx->launches++;
+    APDA_CUDA(cudaGetLastError());
+    return APDA_OK;
+}
+
+}  // namespace
+
+bool peaks_f32_fast_supports(int64_t n, int k, int rec_cap) {
+    return (n == 1024 || n == 2048 || n == 4096 || n == 8192) && rec_cap == 5 && k >= 1 && k <= 5;
+}
+
+int launch_peaks_f32_fast(apda_ctx *ctx, cudaStream_t st, const float *d_spec, int64_t n, int64_t batch, double fs,
+                          const double *d_fs, int k, int flexible, void *d_rec) {
+    switch (n) {
+        case 1024: return launch_half<512>(ctx, st, d_spec, batch, fs, d_fs, k, flexible, d_rec);
+        case 2048: return launch_half<1024>(ctx, st, d_spec, batch, fs, d_fs, k, flexible, d_rec);
+        case 4096: return launch_half<2048>(ctx, st, d_spec, batch, fs, d_fs, k, flexible, d_rec);
+        case 8192: return launch_half<4096>(ctx, st, d_spec, batch, fs, d_fs, k, flexible, d_rec);
+    }
+    apda_set_error("peaks_f32_fast: unsupported n=%lld", (long long)n);
+    return APDA_ERR_UNSUPPORTED;
+}

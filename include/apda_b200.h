@@ -67,6 +67,8 @@ int apda_ctx_destroy(apda_ctx *ctx);
  * is CUDA's legacy default stream).  apda_ctx_reset_stream goes back to the context's own non-blocking stream. */
 int apda_ctx_set_stream(apda_ctx *ctx, void *cuda_stream);
 int apda_ctx_reset_stream(apda_ctx *ctx);
+/* Test/debug switch: on != 0 routes fp32 work through the general kernels instead of the specialised N=1024..8192 ones. */
+int apda_ctx_set_generic_only(apda_ctx *ctx, int on);
 int apda_sync(apda_ctx *ctx);
 const char *apda_last_error(void);
 int apda_version(void);
@@ -107,6 +109,10 @@ int apda_peaks_resolution_f32_dev(apda_ctx *ctx, const float *d_spec, int64_t n,
 int apda_peaks_prominence_f64_host(apda_ctx *ctx, const double *h_spec, int64_t n, int64_t batch, double fs,
                                    const double *h_fs, int k, int rec_cap, void *h_rec);
 int apda_peaks_resolution_f64_host(apda_ctx *ctx, const double *h_spec, int64_t n, int64_t batch, double fs,
+                                   const double *h_fs, int k, int rec_cap, void *h_rec);
+int apda_peaks_prominence_f32_host(apda_ctx *ctx, const float *h_spec, int64_t n, int64_t batch, double fs,
+                                   const double *h_fs, int k, int rec_cap, void *h_rec);
+int apda_peaks_resolution_f32_host(apda_ctx *ctx, const float *h_spec, int64_t n, int64_t batch, double fs,
                                    const double *h_fs, int k, int rec_cap, void *h_rec);
 
 /* ---- pipeline: samples -> records, spectra never leave HBM -------------------------------------------------

@@ -292,3 +292,55 @@ def test_f32_fast_kernel_median_and_padding(n_fft, an):
             err = np.abs(got[r].astype(np.complex128) - want[r]).max()
             # the fp32 median itself carries half an ulp of |x|, which n_samples samples add coherently into the low bins
             assert err <= 3e-6 * scale + n_samples * float(np.abs(x[r]).max()) * 1.2e-7, (n_fft, n_samples, r, err, scale)
+
+
+def _real_spiky_spectra(rng, b, n):
+    """Purely real bins -> magnitudes are exact in fp32 and fp64, so every picker comparison is decided identically."""
+    half = n // 2
+    z = np.zeros((b, n), dtype=np.complex64)
+    mags = np.exp(1.6 * rng.standard_normal((b, half))).astype(np.float32)
+    mags[:, 0] = 0
+    z[:, :half] = mags * np.where(rng.random((b, half)) < 0.5, -1, 1)
+    return z
+
+
+@pytest.mark.parametrize("n", [1024, 2048, 4096, 8192])
+def test_f32_fast_picker_vs_oracle_spiky(n, an):
+    """Heavy-tailed spectra: many candidates whose prominence walks stop in every chunk position (exercises the
+    chunk-summary skipping of the warp-per-window kernel) - decisions must equal the oracle's exactly."""
+    rng = np.random.default_rng(n + 1)
+    b = 96
+    z = _real_spiky_spectra(rng, b, n)
+    for flexible in (True, False):
+        recs = an.peaks(z, 250.0, flexible=flexible)
+        assert (recs["status"] == 0).all()
+        for w in range(b):
+            zl = z[w].astype(np.complex128).tolist()
+            want = ref_port.top_peaks_prominence(zl, 250.0) if flexible else ref_port.top_peaks_resolution(zl, 250.0)
+            got = _dicts(recs[w], 250.0, n, flexible)
+            assert [p["idx"] for p in got] == [p["idx"] for p in want], (n, flexible, w)
+            for g, wt in zip(got, want):
+                if flexible:
+                    assert g["damping"] == wt["damping"] and g["q-factor"] == wt["q-factor"]
+                    assert cases.isclose_rel(g["prominence"], wt["prominence"], 2e-6)
+                assert cases.isclose_rel(g["mag"], wt["mag"], 1e-6)
+
+
+def test_f32_fast_kernels_equal_general_kernels(an):
+    """Specialised fp32 kernels vs the general ones (apda_ctx_set_generic_only) on tone and noise windows."""
+    import apda_fft_b200.synth as synth
+    for n in (1024, 4096, 8192):
+        tones = synth.fleet_windows(300, 128, n, dtype=np.float32)
+        noise = np.stack([synth.noise_window(w, n) for w in range(32)]).astype(np.float32)
+        for x, min_same in ((tones, 1.0), (noise, 0.9)):
+            for flexible in (True, False):
+                fast = an.analyze(x, 125.0, flexible=flexible)
+                an.ctx.set_generic_only(True)
+                try:
+                    slow = an.analyze(x, 125.0, flexible=flexible)
+                finally:
+                    an.ctx.set_generic_only(False)
+                same = [(fast[w]["count"] == slow[w]["count"]) and (fast[w]["pk"]["idx"] == slow[w]["pk"]["idx"]).all()
+                        for w in range(x.shape[0])]
+                assert np.mean(same) >= min_same, (n, flexible, np.mean(same))
+                assert (fast["status"] == 0).all()
