@@ -101,6 +101,7 @@ extern "C" int apda_ctx_destroy(apda_ctx *ctx) {
     fft_f32_fast_release(ctx);
     cudaFree(ctx->ws);
     cudaFree(ctx->ws_small);
+    cudaFree(ctx->repair);
     for (int i = 0; i < 2; ++i) {
         cudaFree(ctx->ws_pipe[i]);
         if (ctx->pipe[i]) cudaStreamDestroy(ctx->pipe[i]);

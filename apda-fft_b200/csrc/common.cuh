@@ -34,6 +34,8 @@ struct apda_ctx {
     void *ws_small = nullptr;  // per-window fs array etc.
     size_t ws_small_bytes = 0;
     int64_t launches = 0;
+    int *repair = nullptr;  // K3 fast path: windows handed over to the general kernel
+    size_t repair_bytes = 0;
     int generic_only = 0;  // debug/test switch: bypass the specialised fp32 kernels
 };
 
@@ -82,6 +84,8 @@ int launch_fft_f32_fast(apda_ctx *ctx, cudaStream_t st, const float *d_samples, 
                         int64_t batch, int64_t N, int flags, float *d_spec);
 void fft_f32_fast_release(apda_ctx *ctx);
 bool peaks_f32_fast_supports(int64_t n, int k, int rec_cap);
+int launch_peaks_general_listed(apda_ctx *ctx, cudaStream_t st, const float *d_spec, int64_t n, int64_t batch, double fs,
+                                const double *d_fs, int k, int rec_cap, int flexible, void *d_rec, const int *list);
 int launch_peaks_f32_fast(apda_ctx *ctx, cudaStream_t st, const float *d_spec, int64_t n, int64_t batch, double fs,
                           const double *d_fs, int k, int flexible, void *d_rec);
 int launch_center_f64(apda_ctx *ctx, cudaStream_t st, const double *d_in, int64_t n, double *d_out);

@@ -133,7 +133,7 @@ __device__ __forceinline__ float next_above(float v) {  // smallest float strict
 // the key space, which bounds the worst case).  When at most 32 values remain in the bracket one warp ranks them.
 // Exact for any input; the estimates only steer the pivots.  Padding slots (index >= n_valid) must hold +inf.
 // Returns statistics.median: the middle value (odd n) or the mean of the two middle values (even n).
-template <int T>
+template <int T, bool FULL>
 __device__ float select_median(const float2 (&v2)[16], int n_valid, uint32_t *sh /* 64 words */, int t, int slot) {
 #define VAL(i) (((i) & 1) ? v2[(i) >> 1].y : v2[(i) >> 1].x)
     constexpr int NW = (T + 31) / 32;
@@ -141,34 +141,35 @@ __device__ float select_median(const float2 (&v2)[16], int n_valid, uint32_t *sh
     const int r_lo = (n_valid - 1) >> 1, r_hi = n_valid >> 1;  // 0-based ranks of the two middle order statistics
     float *shf = reinterpret_cast<float *>(sh);
 
-    // mean and standard deviation steer the first two pivots
-    float s1 = 0.f, s2 = 0.f;
+    // mean and standard deviation only steer the first two pivots: warp 0's quarter of the window (every 4th block of
+    // 64 samples) is a good enough estimate, the other warps skip the pass
+    if (warp == 0) {
+        float s1 = 0.f, s2 = 0.f;
+        int cntv = 0;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        const float x = VAL(i) < CUDART_INF_F ? VAL(i) : 0.f;
-        s1 += x;
-        s2 = fmaf(x, x, s2);
-    }
+        for (int i = 0; i < 32; ++i) {
+            const bool ok = FULL || VAL(i) < CUDART_INF_F;
+            const float x = ok ? VAL(i) : 0.f;
+            s1 += x;
+            s2 = fmaf(x, x, s2);
+            cntv += ok;
+        }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    }
-    if (lane == 0) {
-        shf[warp] = s1;
-        shf[8 + warp] = s2;
+        for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            cntv += __shfl_xor_sync(0xffffffffu, cntv, o);
+        }
+        if (lane == 0) {
+            const float nv = (float)max(cntv, 1);
+            const float m = s1 / nv;
+            shf[0] = m;
+            shf[1] = sqrtf(fmaxf(s2 / nv - m * m, 0.f));
+        }
     }
     group_sync<T>(slot);
-    s1 = 0.f;
-    s2 = 0.f;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) {
-        s1 += shf[w];
-        s2 += shf[8 + w];
-    }
+    const float mean = shf[0], sd = shf[1];
     group_sync<T>(slot);
-    const float mean = s1 / (float)n_valid;
-    const float sd = sqrtf(fmaxf(s2 / (float)n_valid - mean * mean, 0.f));
     const float density = (float)n_valid / fmaxf(2.5f * sd, 1e-30f);  // values per unit near the centre
 
     float lo = -CUDART_INF_F, hi = CUDART_INF_F;  // bracket [lo, hi): c_lo = #(v < lo) <= r_lo, c_hi = #(v < hi) > r_hi
@@ -249,28 +250,33 @@ __device__ float select_median(const float2 (&v2)[16], int n_valid, uint32_t *sh
     }
     group_sync<T>(slot);
     const int cnt = (int)sh[16];
-    float med;
-    if (cnt > 32) {
-        med = lo;  // every value in the bracket equals lo
-    } else {
-        const float mine = lane < cnt ? shf[32 + lane] : CUDART_INF_F;
-        int rank = 0;
-        for (int j = 0; j < cnt; ++j) {
-            const float other = shf[32 + j];
-            rank += (other < mine) || (other == mine && j < lane);
+    if (warp == 0) {
+        float med;
+        if (cnt > 32) {
+            med = lo;  // every value in the bracket equals lo
+        } else {
+            const float mine = lane < cnt ? shf[32 + lane] : CUDART_INF_F;
+            int rank = 0;
+            for (int j = 0; j < cnt; ++j) {
+                const float other = shf[32 + j];
+                rank += (other < mine) || (other == mine && j < lane);
+            }
+            const uint32_t m_lo = __ballot_sync(0xffffffffu, lane < cnt && rank == r_lo - c_lo);
+            const uint32_t m_hi = __ballot_sync(0xffffffffu, lane < cnt && rank == r_hi - c_lo);
+            const float a = __shfl_sync(0xffffffffu, mine, __ffs(m_lo) - 1);
+            const float b = __shfl_sync(0xffffffffu, mine, __ffs(m_hi) - 1);
+            med = (a + b) * 0.5f;
         }
-        const uint32_t m_lo = __ballot_sync(0xffffffffu, lane < cnt && rank == r_lo - c_lo);
-        const uint32_t m_hi = __ballot_sync(0xffffffffu, lane < cnt && rank == r_hi - c_lo);
-        const float a = __shfl_sync(0xffffffffu, mine, __ffs(m_lo) - 1);
-        const float b = __shfl_sync(0xffffffffu, mine, __ffs(m_hi) - 1);
-        med = (a + b) * 0.5f;
+        if (lane == 0) shf[17] = med;
     }
+    group_sync<T>(slot);
+    const float med = shf[17];
     group_sync<T>(slot);
     return med;
 }
 #undef VAL
 
-template <int N, int CENTER>
+template <int N, int CENTER, bool FULL>
 __global__ void __launch_bounds__(Plan<N>::WPB *(N / 32))
 fft_f32_fast_kernel(const float *__restrict__ samples, int n_samples, int64_t ld, int64_t batch,
                     const float2 *__restrict__ tw1,  // [R1][S1]: W_M^{c*k1}
@@ -298,8 +304,7 @@ fft_f32_fast_kernel(const float *__restrict__ samples, int n_samples, int64_t ld
     // ---------------- pass 1: load (coalesced 64-bit), centre, radix R1, twiddle, store [k1][c] ---------------------
     const float *x = samples + winc * ld;
     const float2 *z = reinterpret_cast<const float2 *>(x);
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(x) & 7u) == 0);
-    const bool full = (n_samples == N);
+    const bool full = FULL;  // n_samples == N and 8-byte aligned rows: no predicates on the hot path
 #pragma unroll
     for (int g = 0; g < G1; ++g) {
         const int c = t + T * g;
@@ -307,7 +312,7 @@ fft_f32_fast_kernel(const float *__restrict__ samples, int n_samples, int64_t ld
         for (int n1 = 0; n1 < R1; ++n1) {
             const int zi = n1 * S1 + c;
             float2 val;
-            if (full && vec_ok) {
+            if (FULL) {
                 val = __ldg(z + zi);
             } else {
                 val.x = (2 * zi < n_samples) ? __ldg(x + 2 * zi) : 0.f;
@@ -328,7 +333,7 @@ fft_f32_fast_kernel(const float *__restrict__ samples, int n_samples, int64_t ld
                     if (2 * zi + 1 >= n_samples) v[g * R1 + n1].y = CUDART_INF_F;
                 }
         }
-        shift = select_median<T>(v, n_samples, sel[wslot], t, wslot);
+        shift = select_median<T, FULL>(v, n_samples, sel[wslot], t, wslot);
         if (!full) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -486,9 +491,12 @@ static int launch_fast_n(apda_ctx *ctx, cudaStream_t st, const float *d_samples,
     APDA_TRY(fast_tables<N>(ctx, &ft));
     const int threads = P::WPB * (N / 32);
     const int64_t blocks = (batch + P::WPB - 1) / P::WPB;
-    auto kern = flags == APDA_CENTER_MEDIAN ? fft_f32_fast_kernel<N, APDA_CENTER_MEDIAN>
-                : flags == APDA_CENTER_MEAN ? fft_f32_fast_kernel<N, APDA_CENTER_MEAN>
-                                            : fft_f32_fast_kernel<N, APDA_CENTER_NONE>;
+    const bool full = n_samples == N && (reinterpret_cast<uintptr_t>(d_samples) & 7u) == 0 && (ld & 1) == 0;
+    auto kern = flags == APDA_CENTER_MEDIAN
+                    ? (full ? fft_f32_fast_kernel<N, APDA_CENTER_MEDIAN, true> : fft_f32_fast_kernel<N, APDA_CENTER_MEDIAN, false>)
+                : flags == APDA_CENTER_MEAN
+                    ? (full ? fft_f32_fast_kernel<N, APDA_CENTER_MEAN, true> : fft_f32_fast_kernel<N, APDA_CENTER_MEAN, false>)
+                    : (full ? fft_f32_fast_kernel<N, APDA_CENTER_NONE, true> : fft_f32_fast_kernel<N, APDA_CENTER_NONE, false>);
     kern<<<(unsigned)blocks, threads, 0, st>>>(d_samples, (int)n_samples, ld, batch, ft.tw1, ft.twu,
                                                reinterpret_cast<float2 *>(d_spec));
     ctx->launches++;

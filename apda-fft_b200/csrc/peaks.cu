@@ -11,6 +11,8 @@
 // evaluate the statistics and the damping / exclusion / zeroing arithmetic in fp64.
 #include <math_constants.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -206,8 +208,8 @@ __host__ __device__ inline Layout make_layout(int half) {
 
 // ---- flexible-structure picker ------------------------------------------------------------------------------------
 template <typename T, bool SMEM>
-__global__ void peaks_prominence_kernel(const typename vec2<T>::type *__restrict__ spec, int64_t n, int half,
-                                        double fs_all, const double *__restrict__ d_fs, int k, int rec_cap,
+__device__ void peaks_prominence_window(const int64_t win, const typename vec2<T>::type *__restrict__ spec, int64_t n,
+                                        int half, double fs_all, const double *__restrict__ d_fs, int k, int rec_cap,
                                         unsigned char *__restrict__ recs, unsigned char *__restrict__ ws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ dd red[64];
@@ -220,7 +222,6 @@ __global__ void peaks_prominence_kernel(const typename vec2<T>::type *__restrict
     Found *found = reinterpret_cast<Found *>(base + lay.found_off);
     int *cand = reinterpret_cast<int *>(base + lay.cand_off);
     const int tid = threadIdx.x;
-    const int64_t win = blockIdx.x;
     unsigned char *rec = recs + win * APDA_REC_BYTES(rec_cap);
     const double fs = d_fs ? d_fs[win] : fs_all;
     const double df = div_rn(fs, (double)n);
@@ -330,8 +331,8 @@ __global__ void peaks_prominence_kernel(const typename vec2<T>::type *__restrict
 
 // ---- rigid-structure picker -----------------------------------------------------------------------------------------
 template <typename T, bool SMEM>
-__global__ void peaks_resolution_kernel(const typename vec2<T>::type *__restrict__ spec, int64_t n, int half,
-                                        double fs_all, const double *__restrict__ d_fs, int k, int rec_cap,
+__device__ void peaks_resolution_window(const int64_t win, const typename vec2<T>::type *__restrict__ spec, int64_t n,
+                                        int half, double fs_all, const double *__restrict__ d_fs, int k, int rec_cap,
                                         unsigned char *__restrict__ recs, unsigned char *__restrict__ ws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ dd red[64];
@@ -344,7 +345,6 @@ __global__ void peaks_resolution_kernel(const typename vec2<T>::type *__restrict
     unsigned char *base = SMEM ? smem_raw : ws + (size_t)blockIdx.x * lay.bytes;
     T *mags = reinterpret_cast<T *>(base + lay.mags_off);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-    const int64_t win = blockIdx.x;
     unsigned char *rec = recs + win * APDA_REC_BYTES(rec_cap);
     const double fs = d_fs ? d_fs[win] : fs_all;
     const double df = div_rn(fs, (double)n);
@@ -430,6 +430,27 @@ __global__ void peaks_resolution_kernel(const typename vec2<T>::type *__restrict
     }
 }
 
+// One CTA per window; with a repair list (list[0] = count, list[1..] = window ids, written by the fp32 fast kernel) the
+// CTAs stride over the listed windows instead.
+template <typename T, bool SMEM, bool FLEX>
+__global__ void peaks_kernel(const typename vec2<T>::type *__restrict__ spec, int64_t n, int half, int64_t batch,
+                             double fs_all, const double *__restrict__ d_fs, int k, int rec_cap,
+                             unsigned char *__restrict__ recs, unsigned char *__restrict__ ws,
+                             const int *__restrict__ list) {
+    for (int64_t it = blockIdx.x;; it += gridDim.x) {
+        int64_t win = it;
+        if (list) {
+            if (it >= list[0]) break;
+            win = list[1 + it];
+        } else if (it >= batch) {
+            break;
+        }
+        if (FLEX) peaks_prominence_window<T, SMEM>(win, spec, n, half, fs_all, d_fs, k, rec_cap, recs, ws);
+        else peaks_resolution_window<T, SMEM>(win, spec, n, half, fs_all, d_fs, k, rec_cap, recs, ws);
+        __syncthreads();
+    }
+}
+
 // ---- module-public helper functions of the reference, on a caller-supplied magnitude list ---------------------------
 // out[0] = calculate_prominence(mags, idx); out[1] = half-power bin count for prominence prom_in; out[2] = width_half_magnitude
 __global__ void mag_helpers_kernel(const double *__restrict__ mags, int n, int idx, double prom_in, double *out) {
@@ -453,33 +474,47 @@ template size_t peaks_mag_workspace_bytes<double>(apda_ctx *, int64_t, int64_t);
 template size_t peaks_mag_workspace_bytes<float>(apda_ctx *, int64_t, int64_t);
 
 template <typename T>
-int launch_peaks(apda_ctx *ctx, cudaStream_t st, const T *d_spec, int64_t n, int64_t batch, double fs,
-                 const double *d_fs, int k, int rec_cap, int flexible, void *d_rec, void *d_mag_ws) {
+static int launch_peaks_general(apda_ctx *ctx, cudaStream_t st, const T *d_spec, int64_t n, int64_t batch, double fs,
+                                const double *d_fs, int k, int rec_cap, int flexible, void *d_rec, void *d_mag_ws,
+                                const int *list) {
     using V2 = typename vec2<T>::type;
-    if (sizeof(T) == 4 && !ctx->generic_only && peaks_f32_fast_supports(n, k, rec_cap))
-        return launch_peaks_f32_fast(ctx, st, reinterpret_cast<const float *>(d_spec), n, batch, fs, d_fs, k, flexible,
-                                     d_rec);
     const int half = (int)(n / 2);
     const Layout lay = make_layout<T>(half);
     const bool in_smem = lay.bytes + 4096 <= (size_t)ctx->smem_optin;
     const V2 *spec = reinterpret_cast<const V2 *>(d_spec);
     unsigned char *recs = reinterpret_cast<unsigned char *>(d_rec);
     unsigned char *ws = reinterpret_cast<unsigned char *>(d_mag_ws);
+    const unsigned grid = list ? (unsigned)std::min<int64_t>(batch, 2 * (int64_t)ctx->sm_count) : (unsigned)batch;
     if (in_smem) {
-        auto kern = flexible ? peaks_prominence_kernel<T, true> : peaks_resolution_kernel<T, true>;
+        auto kern = flexible ? peaks_kernel<T, true, true> : peaks_kernel<T, true, false>;
         APDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.bytes));
-        kern<<<(unsigned)batch, 256, lay.bytes, st>>>(spec, n, half, fs, d_fs, k, rec_cap, recs, nullptr);
+        kern<<<grid, 256, lay.bytes, st>>>(spec, n, half, batch, fs, d_fs, k, rec_cap, recs, nullptr, list);
     } else {
         if (!ws) {
             apda_set_error("launch_peaks: magnitude workspace missing for n=%lld", (long long)n);
             return APDA_ERR_INVALID;
         }
-        auto kern = flexible ? peaks_prominence_kernel<T, false> : peaks_resolution_kernel<T, false>;
-        kern<<<(unsigned)batch, 1024, 0, st>>>(spec, n, half, fs, d_fs, k, rec_cap, recs, ws);
+        auto kern = flexible ? peaks_kernel<T, false, true> : peaks_kernel<T, false, false>;
+        kern<<<grid, 1024, 0, st>>>(spec, n, half, batch, fs, d_fs, k, rec_cap, recs, ws, list);
     }
     ctx->launches++;
     APDA_CUDA(cudaGetLastError());
     return APDA_OK;
+}
+
+int launch_peaks_general_listed(apda_ctx *ctx, cudaStream_t st, const float *d_spec, int64_t n, int64_t batch, double fs,
+                                const double *d_fs, int k, int rec_cap, int flexible, void *d_rec, const int *list) {
+    return launch_peaks_general<float>(ctx, st, d_spec, n, batch, fs, d_fs, k, rec_cap, flexible, d_rec, nullptr, list);
+}
+
+template <typename T>
+int launch_peaks(apda_ctx *ctx, cudaStream_t st, const T *d_spec, int64_t n, int64_t batch, double fs,
+                 const double *d_fs, int k, int rec_cap, int flexible, void *d_rec, void *d_mag_ws) {
+    using V2 = typename vec2<T>::type;
+    if (sizeof(T) == 4 && !ctx->generic_only && peaks_f32_fast_supports(n, k, rec_cap))
+        return launch_peaks_f32_fast(ctx, st, reinterpret_cast<const float *>(d_spec), n, batch, fs, d_fs, k, flexible,
+                                     d_rec);
+    return launch_peaks_general<T>(ctx, st, d_spec, n, batch, fs, d_fs, k, rec_cap, flexible, d_rec, d_mag_ws, nullptr);
 }
 template int launch_peaks<double>(apda_ctx *, cudaStream_t, const double *, int64_t, int64_t, double, const double *, int,
                                   int, int, void *, void *);

@@ -21,6 +21,8 @@
 
 namespace {
 
+constexpr int kWPC = 2;  // windows (warps) per CTA
+
 struct Slot {
     uint16_t idx;
     uint16_t width;  // flexible: half-power bins if the candidate passed every gate, else 0
@@ -31,7 +33,7 @@ template <int HALF>
 struct K3 {
     static constexpr int C = HALF / 32;                // bins per lane chunk
     static constexpr int MAGW = HALF + 4 * 32;         // magnitude words incl. 4-word pad per chunk
-    static constexpr int SLOTS = ((HALF / 5 + 8) + 1) & ~1;
+    static constexpr int SLOTS = 96;                   // candidates / hot bins kept on chip; more -> repair list (general kernel)
     static constexpr int REC_OFF = MAGW * 4 + SLOTS * 8;
     static constexpr int BYTES = (REC_OFF + 128 + 15) & ~15;
     __device__ static __forceinline__ int addr(int b) { return b + 4 * (b / C); }
@@ -46,6 +48,32 @@ __device__ __forceinline__ double round_dec4_d(double x) {  // exact emulation o
     if (d == 0.5 && lo > 0.0) n += 1.0;
     if (d == -0.5 && lo < 0.0) n -= 1.0;
     return div_rn(n, p);
+}
+
+__device__ __forceinline__ float sqrt_fast(float x) {  // MUFU.SQRT: <= 1 ulp, far inside the fp32 path's 1e-5 contract
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// div_rn(x, y) < c, decided by one multiplication unless the quotient is within a few ulps of c (then by the division)
+__device__ __forceinline__ bool ratio_lt(double x, double y, double c) {
+    const double t = c * y;
+    if (y > 0.0 && x < t * (1.0 - 0x1p-48)) return true;
+    if (y > 0.0 && x > t * (1.0 + 0x1p-48)) return false;
+    return div_rn(x, y) < c;
+}
+
+// integer n with round(x, 4) == n / 1e4 (see round_dec4_d); ordering by n == ordering by the rounded value
+__device__ __forceinline__ double round_dec4_units(double x) {
+    const double p = 1e4;
+    double hi = mul_rn(x, p);
+    double lo = __fma_rn(x, p, -hi);
+    double n = rint(hi);
+    double d = sub_rn(hi, n);
+    if (d == 0.5 && lo > 0.0) n += 1.0;
+    if (d == -0.5 && lo < 0.0) n -= 1.0;
+    return n;
 }
 
 __device__ __forceinline__ float4 ldg_stream(const float4 *p) {
@@ -141,16 +169,16 @@ __device__ __forceinline__ int half_height_bins_f(const float *mags, int j) {
 }
 
 template <int HALF, bool FLEX>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32 * kWPC)
 peaks_f32_fast_kernel(const float2 *__restrict__ spec, int64_t batch, double fs_all, const double *__restrict__ d_fs,
-                      int k, unsigned char *__restrict__ recs) {
+                      int k, unsigned char *__restrict__ recs, int *__restrict__ repair) {
     using P = K3<HALF>;
     constexpr int C = P::C;
     constexpr int N = 2 * HALF;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int nslot_s[4];
+    __shared__ int nslot_s[kWPC];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t win = (int64_t)blockIdx.x * 4 + warp;
+    const int64_t win = (int64_t)blockIdx.x * kWPC + warp;
     if (win >= batch) return;
     unsigned char *base = smem_raw + warp * P::BYTES;
     float *mags = reinterpret_cast<float *>(base);
@@ -170,7 +198,7 @@ peaks_f32_fast_kernel(const float2 *__restrict__ spec, int64_t batch, double fs_
 #pragma unroll
         for (int u = 0; u < BATCH; ++u) {
             const float p0 = fmaf(z[u].x, z[u].x, z[u].y * z[u].y), p1 = fmaf(z[u].z, z[u].z, z[u].w * z[u].w);
-            const float m0 = sqrtf(p0), m1 = sqrtf(p1);
+            const float m0 = sqrt_fast(p0), m1 = sqrt_fast(p1);
             sum += m0 + m1;
             sumsq += p0 + p1;
             const int b = 64 * (r0 + u) + 2 * lane;
@@ -197,25 +225,30 @@ peaks_f32_fast_kernel(const float2 *__restrict__ spec, int64_t batch, double fs_
     float cmax = -CUDART_INF_F, cmin = CUDART_INF_F;
     {
         const float4 *ch = reinterpret_cast<const float4 *>(mags + P::addr(C * lane));
-#pragma unroll 4
+        unsigned hotq = 0;  // bit q: the q-th float4 of this chunk holds a bin above the threshold (C/4 <= 32 groups)
+#pragma unroll 8
         for (int q = 0; q < C / 4; ++q) {
             const float4 v = ch[q];
             const float m4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
             cmax = fmaxf(cmax, m4);
             cmin = fminf(cmin, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
-            if (m4 > thr_f) {
-                const float e[4] = {v.x, v.y, v.z, v.w};
+            hotq |= (m4 > thr_f ? 1u : 0u) << q;
+        }
+        while (hotq) {  // rare: a handful of bins per window
+            const int q = __ffs(hotq) - 1;
+            hotq &= hotq - 1;
+            const float4 v = ch[q];
+            const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (e[u] > thr_f) {
-                        const int j = C * lane + 4 * q + u;
-                        bool take = true;
-                        if (FLEX)  // strict local maximum, candidates j in [1, HALF-2]
-                            take = j >= 1 && j <= HALF - 2 && e[u] > mags[P::addr(j - 1)] && e[u] > mags[P::addr(j + 1)];
-                        if (take) {
-                            const int pos = atomicAdd(&nslot_s[warp], 1);
-                            if (pos < P::SLOTS) slots[pos].idx = (uint16_t)j;
-                        }
+            for (int u = 0; u < 4; ++u) {
+                if (e[u] > thr_f) {
+                    const int j = C * lane + 4 * q + u;
+                    bool take = true;
+                    if (FLEX)  // strict local maximum, candidates j in [1, HALF-2]
+                        take = j >= 1 && j <= HALF - 2 && e[u] > mags[P::addr(j - 1)] && e[u] > mags[P::addr(j + 1)];
+                    if (take) {
+                        const int pos = atomicAdd(&nslot_s[warp], 1);
+                        if (pos < P::SLOTS) slots[pos].idx = (uint16_t)j;
                     }
                 }
             }
@@ -223,8 +256,12 @@ peaks_f32_fast_kernel(const float2 *__restrict__ spec, int64_t batch, double fs_
     }
     __syncwarp();
     const int nslot_raw = nslot_s[warp];
-    const int nslot = min(nslot_raw, P::SLOTS);
-    const int status = nslot_raw > P::SLOTS ? 1 : 0;
+    if (nslot_raw > P::SLOTS) {  // more candidates than the on-chip list holds: hand the window to the general kernel
+        if (lane == 0) repair[1 + atomicAdd(&repair[0], 1)] = (int)win;
+        return;
+    }
+    const int nslot = nslot_raw;
+    const int status = 0;
 
     int na = 0;
     if (FLEX) {
@@ -254,59 +291,68 @@ peaks_f32_fast_kernel(const float2 *__restrict__ spec, int64_t batch, double fs_
             slots[c].width = (uint16_t)width;
         }
         __syncwarp();
-        // ---- C: extract "descending round(mag,4), ascending idx", greedy hump exclusion, stop at k -------------------
-        double prev_mag = CUDART_INF;
-        int prev_idx = -1;
-        int acc_idx[5];
+        // ---- C: order "descending round(mag,4), ascending idx" (stable sort of the reference), greedy hump exclusion ------
+        // Every lane owns up to three slots (SLOTS = 96); the sort key of a slot is the integer round(mag*1e4).  A slot's
+        // position in the order is its rank = number of passing slots that precede it, computed once.
+        int acc_idx[5], acc_w[5];
         float acc_prom[5];
-        int acc_w[5];
+        double acc_f[5];
 #pragma unroll
-        for (int a = 0; a < 5; ++a) acc_idx[a] = -1, acc_prom[a] = 0.f, acc_w[a] = 0;
-        while (na < k) {
-            double best = -1.0;
-            int best_idx = 0x7fffffff, best_e = -1;
-            for (int e = lane; e < nslot; e += 32) {
-                if (slots[e].width == 0) continue;
-                const int ix = slots[e].idx;
-                const double r = round_dec4_d((double)mags[P::addr(ix)]);
-                const bool after_prev = r < prev_mag || (r == prev_mag && ix > prev_idx);
-                if (after_prev && (r > best || (r == best && ix < best_idx))) {
-                    best = r;
-                    best_idx = ix;
-                    best_e = e;
-                }
-            }
+        for (int a = 0; a < 5; ++a) acc_idx[a] = -1, acc_prom[a] = 0.f, acc_w[a] = 0, acc_f[a] = 0.0;
+        constexpr int PER = P::SLOTS / 32;
+        double key[PER];
+        int sidx[PER], srank[PER];
+        unsigned passm[PER];
+        int npass = 0;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double r = __shfl_xor_sync(0xffffffffu, best, o);
-                const int ix = __shfl_xor_sync(0xffffffffu, best_idx, o);
-                const int e = __shfl_xor_sync(0xffffffffu, best_e, o);
-                if (e >= 0 && (best_e < 0 || r > best || (r == best && ix < best_idx))) {
-                    best = r;
-                    best_idx = ix;
-                    best_e = e;
-                }
+        for (int r = 0; r < PER; ++r) {
+            const int e = lane + 32 * r;
+            const bool ok = e < nslot && slots[e].width != 0;
+            sidx[r] = ok ? (int)slots[e].idx : 0x7fffffff;
+            key[r] = ok ? round_dec4_units((double)mags[P::addr(sidx[r] & (HALF - 1))]) : -1.0;
+            passm[r] = __ballot_sync(0xffffffffu, ok);
+            npass += __popc(passm[r]);
+            srank[r] = 0;
+        }
+#pragma unroll
+        for (int r2 = 0; r2 < PER; ++r2) {
+            for (unsigned m = passm[r2]; m; m &= m - 1) {
+                const int src = __ffs(m) - 1;
+                const double ko = __shfl_sync(0xffffffffu, key[r2], src);
+                const int io = __shfl_sync(0xffffffffu, sidx[r2], src);
+#pragma unroll
+                for (int r = 0; r < PER; ++r) srank[r] += (ko > key[r]) || (ko == key[r] && io < sidx[r]);
             }
-            if (best_e < 0) break;
-            prev_mag = best;
-            prev_idx = best_idx;
-            const float cprom = slots[best_e].prom;
+        }
+        for (int pos = 0; pos < npass && na < k; ++pos) {
+            // fetch the pos-th slot of the order
+            int e_sel = -1;
+#pragma unroll
+            for (int r = 0; r < PER; ++r) {
+                const unsigned hit = __ballot_sync(0xffffffffu, (passm[r] >> lane & 1u) && srank[r] == pos);
+                if (hit) e_sel = (__ffs(hit) - 1) + 32 * r;
+            }
+            const int c_idx = slots[e_sel].idx;
+            const float cprom = slots[e_sel].prom;
+            const int c_w = slots[e_sel].width;
+            const double cf = round_dec4_d(mul_rn((double)c_idx, df));
             bool hump = false;
             if (na > 0) {
-                const double cf = round_dec4_d(mul_rn((double)best_idx, df));
+                const double rmag_units = round_dec4_units((double)mags[P::addr(c_idx)]);
 #pragma unroll
                 for (int a = 0; a < 5; ++a) {
                     if (a < na && !hump) {
-                        const double af = round_dec4_d(mul_rn((double)acc_idx[a], df));
-                        const double rel = div_rn(fabs(sub_rn(cf, af)), af);
-                        if (rel < 0.05 && div_rn((double)cprom, best) < 0.10) hump = true;
+                        if (ratio_lt(fabs(sub_rn(cf, acc_f[a])), acc_f[a], 0.05)) {
+                            // prominence / round(mag, 4) < 0.10
+                            if (div_rn((double)cprom, div_rn(rmag_units, 1e4)) < 0.10) hump = true;
+                        }
                     }
                 }
             }
             if (!hump) {
 #pragma unroll
                 for (int a = 0; a < 5; ++a)
-                    if (a == na) acc_idx[a] = best_idx, acc_prom[a] = cprom, acc_w[a] = slots[best_e].width;
+                    if (a == na) acc_idx[a] = c_idx, acc_prom[a] = cprom, acc_w[a] = c_w, acc_f[a] = cf;
                 ++na;
             }
         }
@@ -410,15 +456,23 @@ peaks_f32_fast_kernel(const float2 *__restrict__ spec, int64_t batch, double fs_
 template <int HALF>
 int launch_half(apda_ctx *ctx, cudaStream_t st, const float *d_spec, int64_t batch, double fs, const double *d_fs,
                 int k, int flexible, void *d_rec) {
-    const int smem = 4 * K3<HALF>::BYTES;
+    const int smem = kWPC * K3<HALF>::BYTES;
     auto kern = flexible ? peaks_f32_fast_kernel<HALF, true> : peaks_f32_fast_kernel<HALF, false>;
     APDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int64_t blocks = (batch + 3) / 4;
-    kern<<<(unsigned)blocks, 128, smem, st>>>(reinterpret_cast<const float2 *>(d_spec), batch, fs, d_fs, k,
-                                              reinterpret_cast<unsigned char *>(d_rec));
+    const int64_t blocks = (batch + kWPC - 1) / kWPC;
+    // repair list: [0] = count, [1..] = windows whose candidate list did not fit on chip
+    const size_t need = ((size_t)batch + 1) * sizeof(int);
+    if (need > ctx->repair_bytes) {
+        APDA_CUDA(cudaStreamSynchronize(st));
+        APDA_TRY(apda_reserve((void **)&ctx->repair, &ctx->repair_bytes, need));
+    }
+    APDA_CUDA(cudaMemsetAsync(ctx->repair, 0, sizeof(int), st));
+    kern<<<(unsigned)blocks, 32 * kWPC, smem, st>>>(reinterpret_cast<const float2 *>(d_spec), batch, fs, d_fs, k,
+                                                    reinterpret_cast<unsigned char *>(d_rec), ctx->repair);
     ctx->launches++;
     APDA_CUDA(cudaGetLastError());
-    return APDA_OK;
+    // the general kernel re-does the listed windows (grid-stride over the device-side count; exits at once if empty)
+    return launch_peaks_general_listed(ctx, st, d_spec, 2 * HALF, batch, fs, d_fs, k, 5, flexible, d_rec, ctx->repair);
 }
 
 }  // namespace

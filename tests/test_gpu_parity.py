@@ -323,7 +323,7 @@ def test_f32_fast_picker_vs_oracle_spiky(n, an):
                 if flexible:
                     assert g["damping"] == wt["damping"] and g["q-factor"] == wt["q-factor"]
                     assert cases.isclose_rel(g["prominence"], wt["prominence"], 2e-6)
-                assert cases.isclose_rel(g["mag"], wt["mag"], 1e-6)
+                assert abs(g["mag"] - wt["mag"]) <= 1e-4 + 1e-6 * abs(wt["mag"])   # MUFU sqrt: 1 ulp before round(., 4)
 
 
 def test_f32_fast_kernels_equal_general_kernels(an):
