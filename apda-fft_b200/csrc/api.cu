@@ -102,6 +102,7 @@ extern "C" int apda_ctx_destroy(apda_ctx *ctx) {
     cudaFree(ctx->ws);
     cudaFree(ctx->ws_small);
     cudaFree(ctx->repair);
+    for (auto &kv : ctx->stream_scratch) cudaFree(kv.second.first);
     for (int i = 0; i < 2; ++i) {
         cudaFree(ctx->ws_pipe[i]);
         if (ctx->pipe[i]) cudaStreamDestroy(ctx->pipe[i]);

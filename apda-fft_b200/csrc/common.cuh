@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <map>
+#include <utility>
 #include <vector>
 #include <string>
 
@@ -34,6 +35,7 @@ struct apda_ctx {
     void *ws_small = nullptr;  // per-window fs array etc.
     size_t ws_small_bytes = 0;
     int64_t launches = 0;
+    std::map<cudaStream_t, std::pair<void *, size_t>> stream_scratch;  // K2 median state, one per stream
     int *repair = nullptr;  // K3 fast path: windows handed over to the general kernel
     size_t repair_bytes = 0;
     int generic_only = 0;  // debug/test switch: bypass the specialised fp32 kernels

@@ -344,3 +344,37 @@ def test_f32_fast_kernels_equal_general_kernels(an):
                         for w in range(x.shape[0])]
                 assert np.mean(same) >= min_same, (n, flexible, np.mean(same))
                 assert (fast["status"] == 0).all()
+
+
+@pytest.mark.parametrize("log2n,n_samples", [(14, None), (15, 20000), (16, None), (18, 200001), (20, None)])
+def test_fft_large_f64_bit_exact(log2n, n_samples, an):
+    """K2 (multi-pass): fp64 spectra of N > 2^13 are bit-identical to the reference restatement, padding included."""
+    n = 1 << log2n
+    ns = n if n_samples is None else n_samples
+    i = np.arange(ns, dtype=np.float64)
+    rng = np.random.default_rng(log2n)
+    x = np.round(0.5 * np.sin(2 * np.pi * 101.6 * i / n) + 0.3 * np.sin(2 * np.pi * 252.4 * i / n + 0.3)
+                 + 0.2 * np.sin(2 * np.pi * 498.0 * i / n + 1.1) + 0.01 * rng.uniform(-1, 1, ns) + 0.25, 6)
+    got = an.fft(x)[0]
+    want = c_oracle.start_fft_batch(x)[0]
+    assert got.shape == (n,)
+    assert np.array_equal(got.view(np.float64), want.view(np.float64))
+    if log2n <= 16:
+        rec = an.analyze(x, 250.0, flexible=True)[0]
+        assert _dicts(rec, 250.0, n, True) == c_oracle.peaks_prominence(want, 250.0)
+        rec = an.analyze(x, 250.0, flexible=False)[0]
+        assert _dicts(rec, 250.0, n, False) == c_oracle.peaks_resolution(want, 250.0)
+
+
+def test_fft_large_f32_and_c2c(an):
+    n = 1 << 17
+    i = np.arange(n, dtype=np.float64)
+    x = np.round(0.5 * np.sin(2 * np.pi * 1001.6 * i / n) + 0.3 * np.sin(2 * np.pi * 2520.4 * i / n + 0.3), 6)
+    want = c_oracle.start_fft_batch(x)[0]
+    got = an.fft(x.astype(np.float32))[0]
+    assert np.abs(got.astype(np.complex128) - want).max() <= 3e-6 * np.abs(want).max()
+    rec = an.analyze(x.astype(np.float32), 250.0, flexible=True)[0]
+    assert [p["idx"] for p in _dicts(rec, 250.0, n, True)] == [p["idx"] for p in c_oracle.peaks_prominence(want, 250.0)]
+    rng = np.random.default_rng(3)
+    z = np.round(rng.standard_normal(1 << 15) + 1j * rng.standard_normal(1 << 15), 6)
+    assert np.array_equal(an.fft_c2c(z)[0].view(np.float64), c_oracle.fft_c2c(z).view(np.float64))
