@@ -23,24 +23,52 @@
 
 namespace {
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Blackwell packed fp32 arithmetic (FADD2 / FMUL2 / FFMA2): one instruction per (re, im) pair.  The scalar 3-operand
+// FADD/FFMA issue at half rate on sm_100, so the butterflies' complex adds are written in packed form.
+__device__ __forceinline__ unsigned long long &u64(float2 &v) { return reinterpret_cast<unsigned long long &>(v); }
+__device__ __forceinline__ const unsigned long long &u64(const float2 &v) {
+    return reinterpret_cast<const unsigned long long &>(v);
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+    float2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(u64(r)) : "l"(u64(a)), "l"(u64(b)));
+    return r;
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+    float2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(u64(r)) : "l"(u64(a)), "l"(u64(b)));
+    return r;
+}
+__device__ __forceinline__ float2 pmul(float2 a, float2 b) {
+    float2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(u64(r)) : "l"(u64(a)), "l"(u64(b)));
+    return r;
+}
+__device__ __forceinline__ float2 pfma(float2 a, float2 b, float2 c) {
+    float2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(u64(r)) : "l"(u64(a)), "l"(u64(b)), "l"(u64(c)));
+    return r;
+}
 __device__ __forceinline__ float2 cmul(float2 a, float2 w) {
     return make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
 }
-__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
 
 #define SQRT1_2f 0.70710678118654752440f
 #define COS_PI_8f 0.92387953251128675613f
 #define SIN_PI_8f 0.38268343236508977173f
 
+// u + (-i)*d and u - (-i)*d for d = (d.x, d.y):  (-i)*d = (d.y, -d.x)
+__device__ __forceinline__ void add_sub_mi(float2 u, float2 d, float2 &plus, float2 &minus) {
+    plus = make_float2(u.x + d.y, u.y - d.x);
+    minus = make_float2(u.x - d.y, u.y + d.x);
+}
+
 // forward DFTs on register arrays, natural order in and out
 __device__ __forceinline__ void fft4(float2 &a0, float2 &a1, float2 &a2, float2 &a3) {
-    float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = mul_mi(csub(a1, a3));
+    const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), d = csub(a1, a3);
     a0 = cadd(t0, t2);
     a2 = csub(t0, t2);
-    a1 = cadd(t1, t3);
-    a3 = csub(t1, t3);
+    add_sub_mi(t1, d, a1, a3);
 }
 __device__ __forceinline__ void fft8(float2 *v) {  // v[0..7]
     float2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
@@ -48,15 +76,13 @@ __device__ __forceinline__ void fft8(float2 *v) {  // v[0..7]
     fft4(e0, e1, e2, e3);
     fft4(o0, o1, o2, o3);
     // W8^1 = (1 - i)/sqrt2, W8^2 = -i, W8^3 = (-1 - i)/sqrt2
-    o1 = make_float2((o1.x + o1.y) * SQRT1_2f, (o1.y - o1.x) * SQRT1_2f);
-    o2 = mul_mi(o2);
-    o3 = make_float2((o3.y - o3.x) * SQRT1_2f, -(o3.x + o3.y) * SQRT1_2f);
+    o1 = pmul(make_float2(o1.x + o1.y, o1.y - o1.x), make_float2(SQRT1_2f, SQRT1_2f));
+    o3 = pmul(make_float2(o3.y - o3.x, o3.x + o3.y), make_float2(SQRT1_2f, -SQRT1_2f));
     v[0] = cadd(e0, o0);
     v[4] = csub(e0, o0);
     v[1] = cadd(e1, o1);
     v[5] = csub(e1, o1);
-    v[2] = cadd(e2, o2);
-    v[6] = csub(e2, o2);
+    add_sub_mi(e2, o2, v[2], v[6]);
     v[3] = cadd(e3, o3);
     v[7] = csub(e3, o3);
 }
@@ -73,16 +99,19 @@ __device__ __forceinline__ void fft16(float2 *v) {  // v[0..15]
     const float2 w1 = make_float2(COS_PI_8f, -SIN_PI_8f), w3 = make_float2(SIN_PI_8f, -COS_PI_8f);
     const float2 w5 = make_float2(-SIN_PI_8f, -COS_PI_8f), w7 = make_float2(-COS_PI_8f, -SIN_PI_8f);
     o[1] = cmul(o[1], w1);
-    o[2] = make_float2((o[2].x + o[2].y) * SQRT1_2f, (o[2].y - o[2].x) * SQRT1_2f);
+    o[2] = pmul(make_float2(o[2].x + o[2].y, o[2].y - o[2].x), make_float2(SQRT1_2f, SQRT1_2f));
     o[3] = cmul(o[3], w3);
-    o[4] = mul_mi(o[4]);
     o[5] = cmul(o[5], w5);
-    o[6] = make_float2((o[6].y - o[6].x) * SQRT1_2f, -(o[6].x + o[6].y) * SQRT1_2f);
+    o[6] = pmul(make_float2(o[6].y - o[6].x, o[6].x + o[6].y), make_float2(SQRT1_2f, -SQRT1_2f));
     o[7] = cmul(o[7], w7);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        v[i] = cadd(e[i], o[i]);
-        v[i + 8] = csub(e[i], o[i]);
+        if (i == 4) {
+            add_sub_mi(e[4], o[4], v[4], v[12]);  // W16^4 = -i
+        } else {
+            v[i] = cadd(e[i], o[i]);
+            v[i + 8] = csub(e[i], o[i]);
+        }
     }
 }
 template <int R>
@@ -361,8 +390,12 @@ fft_f32_fast_kernel(const float *__restrict__ samples, int n_samples, int64_t ld
 #pragma unroll
             for (int n1 = 0; n1 < R1; ++n1) {
                 const int zi = n1 * S1 + c;
-                if (full || 2 * zi < n_samples) v[g * R1 + n1].x -= shift;
-                if (full || 2 * zi + 1 < n_samples) v[g * R1 + n1].y -= shift;
+                if (full) {
+                    v[g * R1 + n1] = csub(v[g * R1 + n1], make_float2(shift, shift));
+                } else {
+                    if (2 * zi < n_samples) v[g * R1 + n1].x -= shift;
+                    if (2 * zi + 1 < n_samples) v[g * R1 + n1].y -= shift;
+                }
             }
         }
         fft_r<R1>(v + g * R1);
@@ -419,13 +452,15 @@ fft_f32_fast_kernel(const float *__restrict__ samples, int n_samples, int64_t ld
         const float2 zb = s[M - 2 * p - 1];          // partner of bin 2p+1
         const float4 w = __ldg(twu4 + p);
         // S = Z[k] + conj(Z[M-k]),  D = Z[k] - conj(Z[M-k]);  X[k] = S/2 + Wt*D,  X[k+M] = S/2 - Wt*D
-        const float2 s0 = make_float2(zk.x + za.x, zk.y - za.y), d0 = make_float2(zk.x - za.x, zk.y + za.y);
-        const float2 s1 = make_float2(zk.z + zb.x, zk.w - zb.y), d1 = make_float2(zk.z - zb.x, zk.w + zb.y);
+        const float2 cj = make_float2(1.f, -1.f), ncj = make_float2(-1.f, 1.f), hf = make_float2(0.5f, 0.5f);
+        const float2 zk0 = make_float2(zk.x, zk.y), zk1 = make_float2(zk.z, zk.w);
+        const float2 s0 = pfma(za, cj, zk0), d0 = pfma(za, ncj, zk0);
+        const float2 s1 = pfma(zb, cj, zk1), d1 = pfma(zb, ncj, zk1);
         const float2 t0 = cmul(d0, make_float2(w.x, w.y)), t1 = cmul(d1, make_float2(w.z, w.w));
-        float4 lo4 = make_float4(fmaf(0.5f, s0.x, t0.x), fmaf(0.5f, s0.y, t0.y), fmaf(0.5f, s1.x, t1.x),
-                                 fmaf(0.5f, s1.y, t1.y));
-        float4 hi4 = make_float4(fmaf(0.5f, s0.x, -t0.x), fmaf(0.5f, s0.y, -t0.y), fmaf(0.5f, s1.x, -t1.x),
-                                 fmaf(0.5f, s1.y, -t1.y));
+        const float2 x0 = pfma(s0, hf, t0), x1 = pfma(s1, hf, t1);
+        const float2 y0 = pfma(s0, hf, make_float2(-t0.x, -t0.y)), y1 = pfma(s1, hf, make_float2(-t1.x, -t1.y));
+        float4 lo4 = make_float4(x0.x, x0.y, x1.x, x1.y);
+        float4 hi4 = make_float4(y0.x, y0.y, y1.x, y1.y);
         if (p == 0) lo4.x = lo4.y = 0.f;  // reference: res[0] = 0
         out[p] = lo4;
         out[M / 2 + p] = hi4;
