@@ -37,6 +37,8 @@ struct K3 {
     static constexpr int REC_OFF = MAGW * 4 + SLOTS * 8;
     static constexpr int BYTES = (REC_OFF + 128 + 15) & ~15;
     __device__ static __forceinline__ int addr(int b) { return b + 4 * (b / C); }
+    // word offset of the 64-bin row R (R = r0 + u with r0 a multiple of 8: row_off is additive in that split)
+    __device__ static __forceinline__ int row_off(int R) { return 64 * R + (C <= 64 ? 4 * (64 / C) * R : 4 * (R / (C / 64))); }
 };
 
 __device__ __forceinline__ double round_dec4_d(double x) {  // exact emulation of Python round(x, 4); see peaks.cu
@@ -168,9 +170,78 @@ __device__ __forceinline__ int half_height_bins_f(const float *mags, int j) {
     return hi - lo;
 }
 
+// The reference sorts the gated candidates by round(mag, 4) descending (stable: ties keep ascending idx) and walks that
+// order with the greedy "hump" exclusion.  Each lane owns PER slots; a slot's place in the order is its rank (number of
+// passing slots that precede it), computed once with shuffles.  Accepted peaks go straight into the record.
+template <int HALF, int PER>
+__device__ __forceinline__ int order_and_exclude(const Slot *slots, int nslot, const float *mags, unsigned char *rec_s,
+                                                 double df, int k, int lane) {
+    using P = K3<HALF>;
+    double key[PER];
+    int sidx[PER], srank[PER];
+    unsigned passm[PER];
+    int npass = 0;
+#pragma unroll
+    for (int r = 0; r < PER; ++r) {
+        const int e = lane + 32 * r;
+        const bool ok = e < nslot && slots[e].width != 0;
+        sidx[r] = ok ? (int)slots[e].idx : 0x7fffffff;
+        key[r] = -1.0;
+        if (ok) key[r] = round_dec4_units((double)mags[P::addr(sidx[r])]);
+        passm[r] = __ballot_sync(0xffffffffu, ok);
+        npass += __popc(passm[r]);
+        srank[r] = 0;
+    }
+#pragma unroll
+    for (int r2 = 0; r2 < PER; ++r2) {
+        for (unsigned m = passm[r2]; m; m &= m - 1) {
+            const int src = __ffs(m) - 1;
+            const double ko = __shfl_sync(0xffffffffu, key[r2], src);
+            const int io = __shfl_sync(0xffffffffu, sidx[r2], src);
+#pragma unroll
+            for (int r = 0; r < PER; ++r) srank[r] += (ko > key[r]) || (ko == key[r] && io < sidx[r]);
+        }
+    }
+    int na = 0;
+    for (int pos = 0; pos < npass && na < k; ++pos) {
+        int e_sel = -1;
+#pragma unroll
+        for (int r = 0; r < PER; ++r) {
+            const unsigned hit = __ballot_sync(0xffffffffu, (passm[r] >> lane & 1u) && srank[r] == pos);
+            if (hit) e_sel = (__ffs(hit) - 1) + 32 * r;
+        }
+        const int c_idx = slots[e_sel].idx;
+        const float cprom = slots[e_sel].prom;
+        const float cmag = mags[P::addr(c_idx)];
+        bool hump = false;
+        for (int a = 0; a < na && !hump; ++a) {
+            const int ja = reinterpret_cast<const int *>(rec_s + 8 + 24 * a)[0];
+            const double fc = mul_rn((double)c_idx, df), fa = mul_rn((double)ja, df);
+            // |round4(fc) - round4(fa)| >= |fc - fa| - 1e-4 and round4(fa) <= fa + 5e-5: most pairs are provably > 5 % apart
+            if (fabs(fc - fa) - 1.0e-4 > 0.05 * (fa + 5.0e-5) * (1.0 + 1e-9)) continue;
+            const double cf = round_dec4_d(fc), af = round_dec4_d(fa);
+            if (div_rn(fabs(sub_rn(cf, af)), af) < 0.05 &&
+                div_rn((double)cprom, div_rn(round_dec4_units((double)cmag), 1e4)) < 0.10)
+                hump = true;
+        }
+        if (!hump) {
+            if (lane == 0) {
+                unsigned char *pk = rec_s + 8 + 24 * na;
+                reinterpret_cast<int *>(pk)[0] = c_idx;
+                reinterpret_cast<int *>(pk)[1] = slots[e_sel].width;
+                reinterpret_cast<double *>(pk + 8)[0] = (double)cmag;
+                reinterpret_cast<double *>(pk + 8)[1] = (double)cprom;
+            }
+            ++na;
+            __syncwarp();
+        }
+    }
+    return na;
+}
+
 template <int HALF, bool FLEX>
 __global__ void __launch_bounds__(32 * kWPC)
-peaks_f32_fast_kernel(const float2 *__restrict__ spec, int64_t batch, double fs_all, const double *__restrict__ d_fs,
+peaks_f32_fast_kernel(const float2 *__restrict__ spec, int64_t batch, double df_all, const double *__restrict__ d_fs,
                       int k, unsigned char *__restrict__ recs, int *__restrict__ repair) {
     using P = K3<HALF>;
     constexpr int C = P::C;
@@ -185,24 +256,28 @@ peaks_f32_fast_kernel(const float2 *__restrict__ spec, int64_t batch, double fs_
     Slot *slots = reinterpret_cast<Slot *>(base + P::MAGW * 4);
     unsigned char *rec_s = base + P::REC_OFF;
     if (lane == 0) nslot_s[warp] = 0;
+    if (lane < 16)  // empty record: count/status 0, every peak {idx -1, width 0, mag 0, prominence 0}
+        reinterpret_cast<uint64_t *>(rec_s)[lane] = (lane % 3 == 1) ? 0x00000000ffffffffull : 0ull;
 
     // ---- phase 1: stream the half spectrum, magnitudes -> shared memory, statistics in registers -------------------
     const float4 *src = reinterpret_cast<const float4 *>(spec + win * (int64_t)N);
     float sum = 0.f, sumsq = 0.f;
     constexpr int ROWS = HALF / 64, BATCH = ROWS < 8 ? ROWS : 8;
+    // shared-memory word of bin b = 64*R + 2*lane is  row_off(R) + lane_off  (4-word pad per chunk of C bins)
+    const int lane_off = P::addr(2 * lane);
 #pragma unroll 1
     for (int r0 = 0; r0 < ROWS; r0 += BATCH) {
         float4 z[BATCH];
 #pragma unroll
         for (int u = 0; u < BATCH; ++u) z[u] = ldg_stream(src + (r0 + u) * 32 + lane);
+        float *dst = mags + lane_off + P::row_off(r0);
 #pragma unroll
         for (int u = 0; u < BATCH; ++u) {
             const float p0 = fmaf(z[u].x, z[u].x, z[u].y * z[u].y), p1 = fmaf(z[u].z, z[u].z, z[u].w * z[u].w);
             const float m0 = sqrt_fast(p0), m1 = sqrt_fast(p1);
             sum += m0 + m1;
             sumsq += p0 + p1;
-            const int b = 64 * (r0 + u) + 2 * lane;
-            *reinterpret_cast<float2 *>(mags + P::addr(b)) = make_float2(m0, m1);
+            *reinterpret_cast<float2 *>(dst + P::row_off(u)) = make_float2(m0, m1);
         }
     }
     double S = (double)sum, Q = (double)sumsq;
@@ -217,8 +292,7 @@ peaks_f32_fast_kernel(const float2 *__restrict__ spec, int64_t batch, double fs_
     const double sd = var > 0.0 ? sqrt(var) : 0.0;
     const double thr = mean + 2.0 * sd;
     const float thr_f = __double2float_rd(thr);  // for floats m:  m > thr  <=>  m > thr_f
-    const double fs = d_fs ? d_fs[win] : fs_all;
-    const double df = div_rn(fs, (double)N);
+    const double df = d_fs ? div_rn(d_fs[win], (double)N) : df_all;  // fs / n (host-side division when fs is shared)
     __syncwarp();
 
     // ---- phase 2: contiguous chunk per lane: chunk max/min, hot bins -> slot list -------------------------------------
@@ -226,13 +300,13 @@ peaks_f32_fast_kernel(const float2 *__restrict__ spec, int64_t batch, double fs_
     {
         const float4 *ch = reinterpret_cast<const float4 *>(mags + P::addr(C * lane));
         unsigned hotq = 0;  // bit q: the q-th float4 of this chunk holds a bin above the threshold (C/4 <= 32 groups)
-#pragma unroll 8
+#pragma unroll
         for (int q = 0; q < C / 4; ++q) {
             const float4 v = ch[q];
             const float m4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
             cmax = fmaxf(cmax, m4);
             cmin = fminf(cmin, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
-            hotq |= (m4 > thr_f ? 1u : 0u) << q;
+            if (m4 > thr_f) hotq |= 1u << q;
         }
         while (hotq) {  // rare: a handful of bins per window
             const int q = __ffs(hotq) - 1;
@@ -283,91 +357,26 @@ peaks_f32_fast_kernel(const float2 *__restrict__ spec, int64_t batch, double fs_
                 const double width_hz = mul_rn((double)bins, df);
                 if (width_hz > 0.0) {
                     const double fn = mul_rn((double)j, df);
-                    const double q = div_rn(fn, width_hz);
-                    const double damping = div_rn(1.0, mul_rn(2.0, q));
-                    if (0.001 <= damping && damping <= 0.07) width = bins;
+                    // 0.001 <= 1/(2*(fn/width_hz)) <= 0.07, decided by products unless within 1e-12 of a bound
+                    const double lo_b = 0.002 * fn, hi_b = 0.14 * fn;
+                    if (width_hz >= lo_b * (1.0 + 1e-12) && width_hz <= hi_b * (1.0 - 1e-12)) {
+                        width = bins;
+                    } else if (!(width_hz < lo_b * (1.0 - 1e-12) || width_hz > hi_b * (1.0 + 1e-12))) {
+                        const double q = div_rn(fn, width_hz);
+                        const double damping = div_rn(1.0, mul_rn(2.0, q));
+                        if (0.001 <= damping && damping <= 0.07) width = bins;
+                    }
                 }
             }
             slots[c].width = (uint16_t)width;
         }
         __syncwarp();
         // ---- C: order "descending round(mag,4), ascending idx" (stable sort of the reference), greedy hump exclusion ------
-        // Every lane owns up to three slots (SLOTS = 96); the sort key of a slot is the integer round(mag*1e4).  A slot's
-        // position in the order is its rank = number of passing slots that precede it, computed once.
-        int acc_idx[5], acc_w[5];
-        float acc_prom[5];
-        double acc_f[5];
-#pragma unroll
-        for (int a = 0; a < 5; ++a) acc_idx[a] = -1, acc_prom[a] = 0.f, acc_w[a] = 0, acc_f[a] = 0.0;
-        constexpr int PER = P::SLOTS / 32;
-        double key[PER];
-        int sidx[PER], srank[PER];
-        unsigned passm[PER];
-        int npass = 0;
-#pragma unroll
-        for (int r = 0; r < PER; ++r) {
-            const int e = lane + 32 * r;
-            const bool ok = e < nslot && slots[e].width != 0;
-            sidx[r] = ok ? (int)slots[e].idx : 0x7fffffff;
-            key[r] = ok ? round_dec4_units((double)mags[P::addr(sidx[r] & (HALF - 1))]) : -1.0;
-            passm[r] = __ballot_sync(0xffffffffu, ok);
-            npass += __popc(passm[r]);
-            srank[r] = 0;
-        }
-#pragma unroll
-        for (int r2 = 0; r2 < PER; ++r2) {
-            for (unsigned m = passm[r2]; m; m &= m - 1) {
-                const int src = __ffs(m) - 1;
-                const double ko = __shfl_sync(0xffffffffu, key[r2], src);
-                const int io = __shfl_sync(0xffffffffu, sidx[r2], src);
-#pragma unroll
-                for (int r = 0; r < PER; ++r) srank[r] += (ko > key[r]) || (ko == key[r] && io < sidx[r]);
-            }
-        }
-        for (int pos = 0; pos < npass && na < k; ++pos) {
-            // fetch the pos-th slot of the order
-            int e_sel = -1;
-#pragma unroll
-            for (int r = 0; r < PER; ++r) {
-                const unsigned hit = __ballot_sync(0xffffffffu, (passm[r] >> lane & 1u) && srank[r] == pos);
-                if (hit) e_sel = (__ffs(hit) - 1) + 32 * r;
-            }
-            const int c_idx = slots[e_sel].idx;
-            const float cprom = slots[e_sel].prom;
-            const int c_w = slots[e_sel].width;
-            const double cf = round_dec4_d(mul_rn((double)c_idx, df));
-            bool hump = false;
-            if (na > 0) {
-                const double rmag_units = round_dec4_units((double)mags[P::addr(c_idx)]);
-#pragma unroll
-                for (int a = 0; a < 5; ++a) {
-                    if (a < na && !hump) {
-                        if (ratio_lt(fabs(sub_rn(cf, acc_f[a])), acc_f[a], 0.05)) {
-                            // prominence / round(mag, 4) < 0.10
-                            if (div_rn((double)cprom, div_rn(rmag_units, 1e4)) < 0.10) hump = true;
-                        }
-                    }
-                }
-            }
-            if (!hump) {
-#pragma unroll
-                for (int a = 0; a < 5; ++a)
-                    if (a == na) acc_idx[a] = c_idx, acc_prom[a] = cprom, acc_w[a] = c_w, acc_f[a] = cf;
-                ++na;
-            }
-        }
+        na = nslot <= 32 ? order_and_exclude<HALF, 1>(slots, nslot, mags, rec_s, df, k, lane)
+                         : order_and_exclude<HALF, P::SLOTS / 32>(slots, nslot, mags, rec_s, df, k, lane);
         if (lane == 0) {
             reinterpret_cast<int *>(rec_s)[0] = na;
             reinterpret_cast<int *>(rec_s)[1] = status;
-#pragma unroll
-            for (int a = 0; a < 5; ++a) {
-                unsigned char *pk = rec_s + 8 + 24 * a;
-                const bool on = a < na;
-                reinterpret_cast<int *>(pk)[0] = on ? acc_idx[a] : -1;
-                reinterpret_cast<int *>(pk)[1] = on ? acc_w[a] : 0;
-                reinterpret_cast<double *>(pk + 8)[0] = on ? (double)mags[P::addr(acc_idx[a])] : 0.0;
-                reinterpret_cast<double *>(pk + 8)[1] = on ? (double)acc_prom[a] : 0.0;
-            }
         }
     } else {
         // ---- rigid picker on the hot list ---------------------------------------------------------------------------------
@@ -375,16 +384,7 @@ peaks_f32_fast_kernel(const float2 *__restrict__ spec, int64_t batch, double fs_
         int acc_idx[5];
 #pragma unroll
         for (int a = 0; a < 5; ++a) acc_idx[a] = -1;
-        if (lane == 0) {
-#pragma unroll
-            for (int a = 0; a < 5; ++a) {
-                unsigned char *pk = rec_s + 8 + 24 * a;
-                reinterpret_cast<int *>(pk)[0] = -1;
-                reinterpret_cast<int *>(pk)[1] = 0;
-                reinterpret_cast<double *>(pk + 8)[0] = 0.0;
-                reinterpret_cast<double *>(pk + 8)[1] = 0.0;
-            }
-        }
+        __syncwarp();
         while (na < k) {
             float bm = -1.f;
             int bj = -1;
@@ -467,7 +467,8 @@ int launch_half(apda_ctx *ctx, cudaStream_t st, const float *d_spec, int64_t bat
         APDA_TRY(apda_reserve((void **)&ctx->repair, &ctx->repair_bytes, need));
     }
     APDA_CUDA(cudaMemsetAsync(ctx->repair, 0, sizeof(int), st));
-    kern<<<(unsigned)blocks, 32 * kWPC, smem, st>>>(reinterpret_cast<const float2 *>(d_spec), batch, fs, d_fs, k,
+    kern<<<(unsigned)blocks, 32 * kWPC, smem, st>>>(reinterpret_cast<const float2 *>(d_spec), batch,
+                                                    fs / (double)(2 * HALF), d_fs, k,
                                                     reinterpret_cast<unsigned char *>(d_rec), ctx->repair);
     ctx->launches++;
     APDA_CUDA(cudaGetLastError());
