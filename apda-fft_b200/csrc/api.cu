@@ -248,6 +248,9 @@ static int fft_dispatch(apda_ctx *ctx, cudaStream_t st, const T *d_samples, int6
     if (sizeof(T) == 4 && !complex_in && !ctx->generic_only && fft_f32_fast_supports(N))
         return launch_fft_f32_fast(ctx, st, reinterpret_cast<const float *>(d_samples), n_samples, ld, batch, N, flags,
                                    reinterpret_cast<float *>(d_spec));
+    if (sizeof(T) == 8 && !complex_in && !ctx->generic_only && fft_f64_fast_supports(N))
+        return launch_fft_f64_fast(ctx, st, reinterpret_cast<const double *>(d_samples), n_samples, ld, batch, N, flags,
+                                   reinterpret_cast<double *>(d_spec));
     if (N <= fft_smem_max_n<T>(ctx)) return launch_fft_smem<T>(ctx, st, d_samples, n_samples, ld, batch, N, flags, d_spec, complex_in);
     return launch_fft_large<T>(ctx, st, d_samples, n_samples, ld, batch, N, flags, d_spec, complex_in);
 }

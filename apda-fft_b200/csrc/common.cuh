@@ -85,6 +85,9 @@ bool fft_f32_fast_supports(int64_t N);
 int launch_fft_f32_fast(apda_ctx *ctx, cudaStream_t st, const float *d_samples, int64_t n_samples, int64_t ld,
                         int64_t batch, int64_t N, int flags, float *d_spec);
 void fft_f32_fast_release(apda_ctx *ctx);
+bool fft_f64_fast_supports(int64_t N);
+int launch_fft_f64_fast(apda_ctx *ctx, cudaStream_t st, const double *d_samples, int64_t n_samples, int64_t ld,
+                        int64_t batch, int64_t N, int flags, double *d_spec);
 bool peaks_f32_fast_supports(int64_t n, int k, int rec_cap);
 int launch_peaks_general_listed(apda_ctx *ctx, cudaStream_t st, const float *d_spec, int64_t n, int64_t batch, double fs,
                                 const double *d_fs, int k, int rec_cap, int flexible, void *d_rec, const int *list);

@@ -1,0 +1,302 @@
+// K1 (fp64 bit-faithful, register blocked) for N = 1024 / 2048 / 4096 / 8192.
+//
+// Same dataflow graph, same recurrence twiddle table and the same individually rounded operations as the general
+// kernel (fft_smem.cu) - so the spectrum stays bit-identical to the reference (metrics/fft_iterativa.py:38-70) - but the
+// log2(N) radix-2 stages are executed 4 (or 3) at a time on 16 register-resident values per thread: only
+// ceil(log2 N / 4) - 1 shared-memory exchanges instead of log2(N) block-wide stages.
+//
+//   load      n_samples reals -> shared memory (coalesced), each thread gathers its 16 bit-reversed inputs
+//   median    exact counting selection on the register-resident values (statistics.median semantics)
+//   pass 0    stages 1..4 in registers (twiddles: 15 table entries shared by all threads), results -> shared memory
+//   pass p    stages s0+1..s0+q: 2^q values per work item with stride 2^s0, twiddles T_s[(r mod 2^(t-1))*2^s0 + lo]
+//             read coalesced through L1; in place in shared memory (index padded by idx>>4: conflict free)
+//   last pass results go straight from registers to HBM with coalesced 128-bit stores; bin 0 := 0.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void bfly(double2 &u, double2 &v, const double2 w) {
+    const double vr = sub_rn(mul_rn(v.x, w.x), mul_rn(v.y, w.y));
+    const double vi = add_rn(mul_rn(v.x, w.y), mul_rn(v.y, w.x));
+    const double2 a = make_double2(add_rn(u.x, vr), add_rn(u.y, vi));
+    const double2 b = make_double2(sub_rn(u.x, vr), sub_rn(u.y, vi));
+    u = a;
+    v = b;
+}
+
+template <int LOGN>
+struct Plan64 {
+    static constexpr int N = 1 << LOGN;
+    static constexpr int T = N / 16;  // threads per window
+    static constexpr int NP = (LOGN + 3) / 4;
+    // stages per pass: first pass always 4, the rest split the remainder as evenly as possible (4s first)
+    __host__ __device__ static constexpr int q(int p) {
+        return p == 0 ? 4 : ((LOGN - 4) / (NP - 1) + ((p - 1) < (LOGN - 4) % (NP - 1) ? 1 : 0));
+    }
+    __host__ __device__ static constexpr int s0(int p) { return p == 0 ? 0 : s0(p - 1) + q(p - 1); }
+    static constexpr int SM_ELEMS = N + N / 16;  // complex elements incl. padding
+};
+
+__device__ __forceinline__ int pad16(int idx) { return idx + (idx >> 4); }
+
+// exact statistics.median of the window; every thread holds 16 of its values (invalid slots: +inf)
+template <int T>
+__device__ double select_median_f64(const double (&val)[16], int n_valid, double *shd /* 64 doubles */, int tid) {
+    constexpr int NW = T / 32 > 0 ? T / 32 : 1;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int r_lo = (n_valid - 1) >> 1, r_hi = n_valid >> 1;
+    unsigned *shu = reinterpret_cast<unsigned *>(shd + 48);
+    if (warp == 0) {
+        double s1 = 0.0, s2 = 0.0;
+        int cv = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const bool ok = val[i] < CUDART_INF;
+            const double x = ok ? val[i] : 0.0;
+            s1 += x;
+            s2 += x * x;
+            cv += ok;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            cv += __shfl_xor_sync(0xffffffffu, cv, o);
+        }
+        if (lane == 0) {
+            const double nv = (double)max(cv, 1), m = s1 / nv;
+            shd[0] = m;
+            shd[1] = sqrt(fmax(s2 / nv - m * m, 0.0));
+        }
+    }
+    __syncthreads();
+    const double mean = shd[0], sd = shd[1];
+    __syncthreads();
+    const double density = (double)n_valid / fmax(2.5 * sd, 1e-300);
+    double lo = -CUDART_INF, hi = CUDART_INF;  // bracket [lo, hi): c_lo = #(v < lo) <= r_lo, c_hi = #(v < hi) > r_hi
+    int c_lo = 0, c_hi = n_valid;
+    double pivot = mean;
+    for (int round = 0;; ++round) {
+        if (round > 0) {
+            if (c_hi - c_lo <= 32) break;
+            double lo_next = -1.7976931348623157e308;
+            if (lo > -CUDART_INF) {
+                lo_next = key_value(ordered_key(lo) + 1ull, 0.0);
+                if (!(lo_next > lo)) lo_next = key_value(ordered_key(lo) + 2ull, 0.0);
+            }
+            if (!(lo_next < hi)) break;
+            const double want = (double)r_lo + 0.5;
+            if (lo == -CUDART_INF) {
+                pivot = hi - 1.5 * fmax((double)c_hi - want, 1.0) / density * (double)(1 << min(round - 1, 30));
+            } else if (hi == CUDART_INF) {
+                pivot = lo + 1.5 * fmax(want - (double)c_lo, 1.0) / density * (double)(1 << min(round - 1, 30));
+            } else if (round % 4 == 0) {  // key-space bisection bounds the worst case
+                const uint64_t a = ordered_key(lo), b = ordered_key(hi);
+                pivot = key_value(a + ((b - a) >> 1), 0.0);
+            } else {
+                pivot = lo + (hi - lo) * ((want - (double)c_lo) / (double)(c_hi - c_lo));
+            }
+            if (!(pivot > lo)) pivot = lo_next;
+            if (!(pivot < hi)) pivot = lo_next;
+        }
+        int cnt = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cnt += (val[i] < pivot);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) shu[warp] = (unsigned)cnt;
+        __syncthreads();
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) tot += (int)shu[w];
+        __syncthreads();
+        if (tot <= r_lo) {
+            lo = pivot;
+            c_lo = tot;
+        } else if (tot > r_hi) {
+            hi = pivot;
+            c_hi = tot;
+        } else {  // even n, the pivot separates the two middle values
+            double below = -CUDART_INF, above = CUDART_INF;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if (val[i] < pivot) below = fmax(below, val[i]);
+                else above = fmin(above, val[i]);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                below = fmax(below, __shfl_xor_sync(0xffffffffu, below, o));
+                above = fmin(above, __shfl_xor_sync(0xffffffffu, above, o));
+            }
+            if (lane == 0) {
+                shd[2 + warp] = below;
+                shd[2 + 16 + warp] = above;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                below = fmax(below, shd[2 + w]);
+                above = fmin(above, shd[2 + 16 + w]);
+            }
+            __syncthreads();
+            return div_rn(add_rn(below, above), 2.0);
+        }
+    }
+    if (tid == 0) shu[16] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        if (val[i] >= lo && val[i] < hi) {
+            const unsigned pos = atomicAdd(&shu[16], 1u);
+            if (pos < 32u) shd[2 + pos] = val[i];
+        }
+    }
+    __syncthreads();
+    const int cnt = (int)shu[16];
+    if (warp == 0) {
+        double med;
+        if (cnt > 32) {
+            med = lo;  // a single distinct value fills the bracket
+        } else {
+            const double mine = lane < cnt ? shd[2 + lane] : CUDART_INF;
+            int rank = 0;
+            for (int j = 0; j < cnt; ++j) {
+                const double other = shd[2 + j];
+                rank += (other < mine) || (other == mine && j < lane);
+            }
+            const unsigned m_lo = __ballot_sync(0xffffffffu, lane < cnt && rank == r_lo - c_lo);
+            const unsigned m_hi = __ballot_sync(0xffffffffu, lane < cnt && rank == r_hi - c_lo);
+            const double a = __shfl_sync(0xffffffffu, mine, __ffs(m_lo) - 1);
+            const double b = __shfl_sync(0xffffffffu, mine, __ffs(m_hi) - 1);
+            med = div_rn(add_rn(a, b), 2.0);
+        }
+        if (lane == 0) shd[40] = med;
+    }
+    __syncthreads();
+    const double med = shd[40];
+    __syncthreads();
+    return med;
+}
+
+// q radix-2 stages on 2^q register values of one work item (stride 2^s0, low index bits `lo`)
+template <int Q>
+__device__ __forceinline__ void stages(double2 *v, const double2 *__restrict__ tw, int s0, int lo) {
+#pragma unroll
+    for (int t = 1; t <= Q; ++t) {
+        const int h = 1 << (t - 1);
+        const double2 *tab = tw + (((1 << (s0 + t - 1)) - 1) + lo);
+        double2 w[8];
+#pragma unroll
+        for (int j = 0; j < h; ++j) w[j] = __ldg(tab + (j << s0));
+#pragma unroll
+        for (int r = 0; r < (1 << Q); ++r) {
+            if ((r & h) == 0) bfly(v[r], v[r + h], w[r & (h - 1)]);
+        }
+    }
+}
+
+template <int LOGN, int P, int Q>
+__device__ __forceinline__ void middle_or_last_pass(double2 *s, const double2 *__restrict__ tw, double2 *out, int t) {
+    using PL = Plan64<LOGN>;
+    constexpr int S0 = PL::s0(P), G = 16 >> Q, T = PL::T;
+    constexpr bool LAST = (P == PL::NP - 1);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const int w = t + T * g;                 // work item: lo = low S0 bits, hi = the rest
+        const int lo = w & ((1 << S0) - 1), hi = w >> S0;
+        const int base = (hi << (S0 + Q)) + lo;
+        double2 v[1 << Q];
+#pragma unroll
+        for (int r = 0; r < (1 << Q); ++r) v[r] = s[pad16(base + (r << S0))];
+        stages<Q>(v, tw, S0, lo);
+        if (LAST) {
+#pragma unroll
+            for (int r = 0; r < (1 << Q); ++r) {
+                double2 val = v[r];
+                if (base + (r << S0) == 0) val = make_double2(0.0, 0.0);  // reference: res[0] = 0
+                out[base + (r << S0)] = val;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < (1 << Q); ++r) s[pad16(base + (r << S0))] = v[r];
+        }
+    }
+}
+
+template <int LOGN>
+__global__ void __launch_bounds__(Plan64<LOGN>::T)
+fft_f64_fast_kernel(const double *__restrict__ samples, int n_samples, int64_t ld, const double2 *__restrict__ tw,
+                    double2 *__restrict__ spec, int center) {
+    using PL = Plan64<LOGN>;
+    constexpr int N = PL::N, T = PL::T;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double shd[64];
+    double2 *s = reinterpret_cast<double2 *>(smem_raw);
+    double *raw = reinterpret_cast<double *>(smem_raw);  // staging of the real samples (padded by i>>3), aliases s
+    const int t = threadIdx.x;
+    const int64_t win = blockIdx.x;
+    const double *x = samples + win * ld;
+
+    for (int i = t; i < N; i += T) raw[i + (i >> 3)] = i < n_samples ? x[i] : CUDART_INF;
+    __syncthreads();
+    // work item hi = t of pass 0 owns outputs idx = 16*t + r, i.e. inputs bitrev(idx) = bitrev4(r) * N/16 + bitrev(t)
+    const int tb = (int)(__brev((unsigned)t) >> (32 - (LOGN - 4)));
+    double val[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        const int src = ((int)(__brev((unsigned)r) >> 28) << (LOGN - 4)) + tb;
+        val[r] = raw[src + (src >> 3)];
+    }
+    __syncthreads();  // raw is dead from here on (s aliases it)
+    double med = 0.0;
+    if (center == APDA_CENTER_MEDIAN) med = select_median_f64<T>(val, n_samples, shd, t);
+    double2 v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = make_double2(val[r] < CUDART_INF ? sub_rn(val[r], med) : 0.0, 0.0);
+    stages<4>(v, tw, 0, 0);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) s[pad16(16 * t + r)] = v[r];
+    __syncthreads();
+
+    double2 *out = spec + win * (int64_t)N;
+    middle_or_last_pass<LOGN, 1, PL::q(1)>(s, tw, out, t);
+    if (PL::NP > 2) {
+        __syncthreads();
+        middle_or_last_pass<LOGN, 2 < PL::NP ? 2 : 1, PL::q(2 < PL::NP ? 2 : 1)>(s, tw, out, t);
+    }
+    if (PL::NP > 3) {
+        __syncthreads();
+        middle_or_last_pass<LOGN, 3 < PL::NP ? 3 : 1, PL::q(3 < PL::NP ? 3 : 1)>(s, tw, out, t);
+    }
+}
+
+template <int LOGN>
+int launch_n(apda_ctx *ctx, cudaStream_t st, const double *d_samples, int64_t n_samples, int64_t ld, int64_t batch,
+             int flags, const double2 *tw, double *d_spec) {
+    using PL = Plan64<LOGN>;
+    const size_t smem = (size_t)PL::SM_ELEMS * sizeof(double2);
+    APDA_CUDA(cudaFuncSetAttribute(fft_f64_fast_kernel<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fft_f64_fast_kernel<LOGN><<<(unsigned)batch, PL::T, smem, st>>>(d_samples, (int)n_samples, ld, tw,
+                                                                   reinterpret_cast<double2 *>(d_spec), flags);
+    ctx->launches++;
+    APDA_CUDA(cudaGetLastError());
+    return APDA_OK;
+}
+
+}  // namespace
+
+bool fft_f64_fast_supports(int64_t N) { return N == 1024 || N == 2048 || N == 4096 || N == 8192; }
+
+int launch_fft_f64_fast(apda_ctx *ctx, cudaStream_t st, const double *d_samples, int64_t n_samples, int64_t ld,
+                        int64_t batch, int64_t N, int flags, double *d_spec) {
+    TwiddleTables tw;
+    APDA_TRY(apda_get_twiddles(ctx, N, &tw));
+    switch (N) {
+        case 1024: return launch_n<10>(ctx, st, d_samples, n_samples, ld, batch, flags, tw.d64, d_spec);
+        case 2048: return launch_n<11>(ctx, st, d_samples, n_samples, ld, batch, flags, tw.d64, d_spec);
+        case 4096: return launch_n<12>(ctx, st, d_samples, n_samples, ld, batch, flags, tw.d64, d_spec);
+        case 8192: return launch_n<13>(ctx, st, d_samples, n_samples, ld, batch, flags, tw.d64, d_spec);
+    }
+    apda_set_error("fft_f64_fast: unsupported N=%lld", (long long)N);
+    return APDA_ERR_UNSUPPORTED;
+}

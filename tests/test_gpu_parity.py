@@ -378,3 +378,28 @@ def test_fft_large_f32_and_c2c(an):
     rng = np.random.default_rng(3)
     z = np.round(rng.standard_normal(1 << 15) + 1j * rng.standard_normal(1 << 15), 6)
     assert np.array_equal(an.fft_c2c(z)[0].view(np.float64), c_oracle.fft_c2c(z).view(np.float64))
+
+
+@pytest.mark.parametrize("n_fft", [1024, 2048, 4096, 8192])
+def test_f64_fast_kernel_bit_exact_incl_median_and_padding(n_fft, an):
+    """Register-blocked fp64 K1: bit-identical to the C oracle on skewed / tied / padded / odd-length windows."""
+    rng = np.random.default_rng(n_fft + 7)
+    for n_samples in (n_fft, n_fft - 1, n_fft - 2, (3 * n_fft) // 4 + 1, n_fft // 2 + 1, n_fft // 2 + 2):
+        rows = [np.round(np.exp(rng.standard_normal(n_samples)), 2),
+                np.round(rng.standard_normal(n_samples) * 0.3 + 5.0, 3),
+                (rng.random(n_samples) < 0.5).astype(np.float64),
+                np.round(np.sin(np.arange(n_samples) * 0.05) + 0.2 * rng.standard_normal(n_samples), 6),
+                np.zeros(n_samples), rng.standard_normal(n_samples)]
+        x = np.stack(rows)
+        got = an.fft(x, n_fft=n_fft)
+        want = c_oracle.start_fft_batch(x, n_fft=n_fft)
+        assert np.array_equal(got.view(np.float64), want.view(np.float64)), (n_fft, n_samples)
+    import apda_fft_b200.synth as synth
+    x = synth.fleet_windows(77, 64, n_fft)
+    fast = an.fft(x)
+    an.ctx.set_generic_only(True)
+    try:
+        slow = an.fft(x)
+    finally:
+        an.ctx.set_generic_only(False)
+    assert np.array_equal(fast.view(np.float64), slow.view(np.float64))
