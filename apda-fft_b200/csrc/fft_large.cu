@@ -16,6 +16,8 @@
 // K1, so the fp64 result is bit-identical to the reference for every N (the table is what makes N >= 2^16 match to
 // 1e-12: the reference's own twiddle drift reaches 3e-10 at N = 2^24).  fp32 runs the same passes on the rounded table.
 // The exact median of up to 2^30 samples is a multi-CTA radix select (histogram passes over HBM).
+#include <cuda.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -140,6 +142,123 @@ large_tail_kernel(typename vec2<T>::type *__restrict__ spec, int n, int s0, int 
         base[((int64_t)r << s0) + c] = val;
     }
     (void)rows;
+}
+
+// ---- tail pass, TMA staged -----------------------------------------------------------------------------------------
+// Same arithmetic as large_tail_kernel; the [2^q][C] tile is brought in by cp.async.bulk.tensor (one elected thread,
+// completion on an mbarrier) and written back in place by a bulk tensor store, so no thread spends registers or LSU
+// issue slots on the HBM traffic.  The tensor map views the spectra as [batch * n_hi][2^q][2^s0] complex values
+// (innermost dimension counted in scalars: 2 per complex value).
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+large_tail_tma_kernel(const __grid_constant__ CUtensorMap tmap, int n, int s0, int q, int C,
+                      const typename vec2<T>::type *__restrict__ tw, int zero_dc) {
+    using V2 = typename vec2<T>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bar;
+    // TMA wants a 128-byte aligned shared-memory destination; the dynamic segment only promises 16
+    V2 *tile = reinterpret_cast<V2 *>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+    const int tid = threadIdx.x;
+    const int64_t tiles_lo = ((int64_t)1 << s0) / C;
+    const int64_t n_hi = (int64_t)1 << (n - s0 - q);
+    const int64_t hi = blockIdx.x / tiles_lo;
+    const int64_t lo0 = (blockIdx.x % tiles_lo) * C;
+    const int rows = 1 << q;
+    const int box_rows = rows < 256 ? rows : 256;
+    const int c0 = (int)(2 * lo0), c2 = (int)((int64_t)blockIdx.y * n_hi + hi);
+    const uint32_t bar_a = smem_u32(&bar);
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = (uint32_t)((size_t)rows * C * sizeof(V2));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+        for (int r0 = 0; r0 < rows; r0 += box_rows) {
+            const uint32_t dst = smem_u32(tile + (size_t)r0 * C);
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(c0), "r"(r0), "r"(c2), "r"(bar_a)
+                : "memory");
+        }
+    }
+    {  // every thread waits for the tile (phase 0 of the barrier)
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(bar_a), "r"(0u)
+                : "memory");
+        }
+    }
+
+    for (int t = 1; t <= q; ++t) {
+        const int halfr = 1 << (t - 1);
+        const V2 *tab = tw + (((int64_t)1 << (s0 + t - 1)) - 1) + lo0;
+        for (int e = tid; e < (C << (q - 1)); e += kThreads) {
+            const int c = e % C, pb = e / C;
+            const int jr = pb & (halfr - 1);
+            const int ra = ((pb >> (t - 1)) << t) + jr;
+            V2 u = tile[ra * C + c], v = tile[(ra + halfr) * C + c];
+            butterfly<T>(u, v, __ldg(tab + ((int64_t)jr << s0) + c));
+            tile[ra * C + c] = u;
+            tile[(ra + halfr) * C + c] = v;
+        }
+        __syncthreads();
+    }
+    if (zero_dc && hi == 0 && lo0 == 0 && tid == 0) tile[0].x = tile[0].y = T(0);  // reference: res[0] = 0
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk store
+    __syncthreads();
+    if (tid == 0) {
+        for (int r0 = 0; r0 < rows; r0 += box_rows) {
+            const uint32_t src = smem_u32(tile + (size_t)r0 * C);
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(
+                             reinterpret_cast<uint64_t>(&tmap)),
+                         "r"(c0), "r"(r0), "r"(c2), "r"(src)
+                         : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+// tensor map of one tail pass; false if the driver entry point is missing or rejects the shape (caller falls back)
+template <typename T>
+static bool make_tail_tmap(CUtensorMap *tm, T *d_spec, int n, int s0, int q, int C, int64_t batch) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)2 << s0, (cuuint64_t)1 << q, (cuuint64_t)batch << (n - s0 - q)};
+    const cuuint64_t strides[2] = {((cuuint64_t)1 << s0) * 2 * sizeof(T), ((cuuint64_t)1 << (s0 + q)) * 2 * sizeof(T)};
+    const cuuint32_t box[3] = {(cuuint32_t)(2 * C), (cuuint32_t)std::min(1 << q, 256), 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    if (box[0] > 256 || dims[2] >= ((cuuint64_t)1 << 32)) return false;
+    return enc(tm, dt, 3, d_spec, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // ---- exact median of one long window: MSB-first 8-bit radix select with HBM histogram passes -----------------------
@@ -295,12 +414,19 @@ int launch_fft_large(apda_ctx *ctx, cudaStream_t st, const T *d_samples, int64_t
         const int q = plan.q[p];
         const int64_t cols = (int64_t)1 << s0;
         const int C = (int)std::min<int64_t>(std::min<int64_t>(max_tile >> q, 64), cols);
-        const size_t smem = (size_t)(C + 1) * (1u << q) * sizeof(V2);
-        APDA_CUDA(cudaFuncSetAttribute(large_tail_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int64_t tiles = (cols / C) * ((int64_t)1 << (n - s0 - q));
         dim3 grid((unsigned)tiles, (unsigned)batch);
         const int zero_dc = (!complex_input && p == plan.npass - 1) ? 1 : 0;
-        large_tail_kernel<T><<<grid, kThreads, smem, st>>>(reinterpret_cast<V2 *>(d_spec), n, s0, q, C, twp, zero_dc);
+        CUtensorMap tm;
+        if (!ctx->generic_only && make_tail_tmap<T>(&tm, d_spec, n, s0, q, C, batch)) {
+            const size_t smem = (size_t)C * (1u << q) * sizeof(V2) + 128;
+            APDA_CUDA(cudaFuncSetAttribute(large_tail_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            large_tail_tma_kernel<T><<<grid, kThreads, smem, st>>>(tm, n, s0, q, C, twp, zero_dc);
+        } else {
+            const size_t smem = (size_t)(C + 1) * (1u << q) * sizeof(V2);
+            APDA_CUDA(cudaFuncSetAttribute(large_tail_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            large_tail_kernel<T><<<grid, kThreads, smem, st>>>(reinterpret_cast<V2 *>(d_spec), n, s0, q, C, twp, zero_dc);
+        }
         ctx->launches++;
         APDA_CUDA(cudaGetLastError());
         s0 += q;

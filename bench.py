@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU work budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-variants", action="store_true")
     return ap.parse_args()
 
 
@@ -205,11 +206,13 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(kernel_key: str):
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if any."""
+def ncu_traffic(kernel_key: str, windows: int):
+    """DRAM bytes (read + write) of one launch of the dominant kernel, from the committed `ncu --set full` capture
+    (profiles/traffic.json holds bytes per window of that capture; scaled to this run's windows per launch)."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            return json.load(fh).get(kernel_key)
+            entry = json.load(fh)[kernel_key]
+        return entry["dram_bytes_per_window"] * windows
     except Exception:
         return None
 
@@ -252,15 +255,16 @@ def run_ours(args):
 
     k1_events = []
 
-    def step(record_k1: bool):
+    def step(record_k1: bool, center=center, flexible=flexible, events=k1_events):
         if record_k1:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
         an.fft_device(d_x.data_ptr(), b, n, n, args.dtype, d_spec.data_ptr(), center=center)
         if record_k1:
             e1.record(stream)
-            k1_events.append((e0, e1))
-        an.peaks_device(d_spec.data_ptr(), b, n, args.dtype, fs, d_rec.data_ptr(), flexible=flexible, k=k, rec_cap=5)
+            events.append((e0, e1))
+        an.peaks_device(d_spec.data_ptr(), b, n, args.dtype, fs, d_rec.data_ptr(), flexible=flexible,
+                        k=4 if flexible else 5, rec_cap=5)
         if world > 1:
             return gather_records(d_rec, b * world, dst=0)
         return d_rec
@@ -292,6 +296,37 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
     elapsed_ms, k1_ms = float(red[0]), float(red[1])
+
+    # secondary variants of the same workload (not the headline): the other centring mode and the other picker
+    def variant(v_center, v_flexible):
+        ev = []
+        for _ in range(3):
+            step(False, v_center, v_flexible, ev)
+        fence()
+        a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(args.steps):
+            step(True, v_center, v_flexible, ev)
+        z.record(stream)
+        fence()
+        vals = torch.tensor([a.elapsed_time(z), sum(p.elapsed_time(q) for p, q in ev) / max(len(ev), 1)],
+                            dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        ms = float(vals[0]) / args.steps
+        return {"value": b * world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "k1_ms_per_launch": float(vals[1]),
+                "pipeline_frac_of_peak": (4 * s_bytes * n + 128) * b / (ms * 1e-3) / 1e9 / measured_peak()[0]}
+
+    variants = {}
+    if args.dtype == "f32" and not args.no_variants:
+        other_center = _cabi.CENTER_MEAN if center == _cabi.CENTER_MEDIAN else _cabi.CENTER_MEDIAN
+        variants["centering_" + ("mean" if other_center == _cabi.CENTER_MEAN else "median")] = dict(
+            variant(other_center, flexible),
+            note="APDA_CENTER_MEAN is the documented opt-in, legal only when n_samples == N (bins >= 1 do not depend on "
+                 "the centring constant; bin 0 is zeroed)")
+        variants["picker_" + ("rigid" if flexible else "flexible")] = variant(center, not flexible)
+        step(False)            # leave the headline configuration's records in d_rec for the checks below
+        fence()
 
     # sanity of the result actually produced in the timed region (rank 0 sees the gathered table)
     summary = None
@@ -342,12 +377,14 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "K1 fft (samples -> N complex bins)", "achieved": k1_gbs,
                          "peak": peak, "unit": "GB/s", "frac": k1_gbs / peak, "peak_source": peak_src,
                          "bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms,
-                         "traffic": ncu_traffic(f"k1_{args.dtype}_n{n}")},
+                         "traffic": ncu_traffic(f"k1_{args.dtype}_n{n}", b),
+                         "traffic_source": "profiles/traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per window x windows per launch)"},
             "pipeline": {"b_alg_bytes_per_window": 4 * s_bytes * n + 128,
                          "achieved_gbs_per_gpu": b_alg / (step_ms * 1e-3) / 1e9,
                          "frac_of_peak": b_alg / (step_ms * 1e-3) / 1e9 / peak,
                          "k1_share_of_step": k1_ms / step_ms},
             "e2e": e2e, "gpu_launches": int(launches) * world, "clocks": clocks, "result_check": summary,
+            "variants": variants,
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
