@@ -89,6 +89,12 @@ bool fft_f64_fast_supports(int64_t N);
 int launch_fft_f64_fast(apda_ctx *ctx, cudaStream_t st, const double *d_samples, int64_t n_samples, int64_t ld,
                         int64_t batch, int64_t N, int flags, double *d_spec);
 bool peaks_f32_fast_supports(int64_t n, int k, int rec_cap);
+bool peaks_large_supports(int64_t n);
+template <typename T>
+size_t peaks_large_workspace_bytes(int64_t n);
+template <typename T>
+int launch_peaks_large(apda_ctx *ctx, cudaStream_t st, const T *d_spec, int64_t n, int64_t batch, double fs,
+                       const double *d_fs, int k, int rec_cap, int flexible, void *d_rec, void *ws);
 int launch_peaks_general_listed(apda_ctx *ctx, cudaStream_t st, const float *d_spec, int64_t n, int64_t batch, double fs,
                                 const double *d_fs, int k, int rec_cap, int flexible, void *d_rec, const int *list);
 int launch_peaks_f32_fast(apda_ctx *ctx, cudaStream_t st, const float *d_spec, int64_t n, int64_t batch, double fs,

@@ -325,29 +325,58 @@ __global__ void select_reset_kernel(SelectState *st, long long rank) {
     st->hist[threadIdx.x] = 0;
 }
 
+// upper middle order statistic from the lower one in a single pass: it equals the lower key when that key is
+// duplicated across the midpoint, else it is the smallest key above it
 template <typename T>
-__global__ void select_finish_kernel(const SelectState *st, T *med_out) {
+__global__ void __launch_bounds__(256) select_upper_kernel(const T *__restrict__ x, int64_t n, SelectState *st) {
     using K = typename KeyT<T>::type;
-    const T a = key_value((K)st->found[0], T(0)), b = key_value((K)st->found[1], T(0));
+    const K lo = (K)st->found[0];
+    unsigned long long le = 0, above = ~0ull;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const K k = ordered_key(x[i]);
+        le += (k <= lo);
+        if (k > lo && (unsigned long long)k < above) above = (unsigned long long)k;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        le += __shfl_xor_sync(0xffffffffu, le, o);
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, above, o);
+        above = other < above ? other : above;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&st->prefix, le);       // prefix / mask are free after the digit passes: reuse as count / min
+        atomicMin(&st->mask, above);
+    }
+}
+
+template <typename T>
+__global__ void select_finish_kernel(SelectState *st, int64_t n, T *med_out) {
+    using K = typename KeyT<T>::type;
+    const K lo = (K)st->found[0];
+    const K hi = ((long long)st->prefix >= (long long)(n / 2 + 1)) ? lo : (K)st->mask;
+    const T a = key_value(lo, T(0)), b = key_value(hi, T(0));
     *med_out = div_rn(add_rn(a, b), T(2));  // statistics.median: middle value, or (a + b) / 2 for even n
+}
+
+__global__ void select_prepare_upper_kernel(SelectState *st) {
+    st->prefix = 0;
+    st->mask = ~0ull;
 }
 
 template <typename T>
 int large_median(apda_ctx *ctx, cudaStream_t st, const T *d_x, int64_t n, SelectState *state, T *d_med) {
     const int bits = (int)sizeof(T) * 8;
     const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8);
-    const long long ranks[2] = {(long long)((n - 1) / 2), (long long)(n / 2)};
-    for (int which = 0; which < 2; ++which) {
-        select_reset_kernel<<<1, 256, 0, st>>>(state, ranks[which]);
-        for (int shift = bits - 8; shift >= 0; shift -= 8) {
-            select_hist_kernel<T><<<grid, 256, 0, st>>>(d_x, n, shift, state);
-            select_pick_kernel<<<1, 32, 0, st>>>(state, shift, which, shift == 0);
-            ctx->launches += 2;
-        }
-        ctx->launches += 1;
+    select_reset_kernel<<<1, 256, 0, st>>>(state, (long long)((n - 1) / 2));
+    for (int shift = bits - 8; shift >= 0; shift -= 8) {
+        select_hist_kernel<T><<<grid, 256, 0, st>>>(d_x, n, shift, state);
+        select_pick_kernel<<<1, 32, 0, st>>>(state, shift, 0, shift == 0);
+        ctx->launches += 2;
     }
-    select_finish_kernel<T><<<1, 1, 0, st>>>(state, d_med);
-    ctx->launches += 1;
+    select_prepare_upper_kernel<<<1, 1, 0, st>>>(state);
+    select_upper_kernel<T><<<grid, 256, 0, st>>>(d_x, n, state);
+    select_finish_kernel<T><<<1, 1, 0, st>>>(state, n, d_med);
+    ctx->launches += 4;
     APDA_CUDA(cudaGetLastError());
     return APDA_OK;
 }
@@ -379,7 +408,7 @@ int launch_fft_large(apda_ctx *ctx, cudaStream_t st, const T *d_samples, int64_t
     TwiddleTables tw;
     APDA_TRY(apda_get_twiddles(ctx, N, &tw));
     const V2 *twp = sizeof(T) == 8 ? reinterpret_cast<const V2 *>(tw.d64) : reinterpret_cast<const V2 *>(tw.d32);
-    const int max_tile = sizeof(T) == 8 ? 8192 : 16384;  // complex elements per 128 KB tile
+    const int max_tile = sizeof(T) == 8 ? 4096 : 8192;  // complex elements per 64 KB tile: 3 CTAs per SM overlap load, compute and store
     const PassPlan plan = make_plan(n, sizeof(T) == 8 ? 10 : 11);
 
     // centring constant per window

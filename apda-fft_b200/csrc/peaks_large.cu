@@ -1,0 +1,498 @@
+// K3 (large form) for power-of-two spectra with n >= 2^16 bins: the picker of one long window spread over the chip.
+//
+//   A  mags_kernel      one CTA per block of 1024 bins: magnitudes -> HBM, block max / min, double-double partial sums
+//   B  stats_kernel     one CTA: mean, sample sigma, threshold (same correctly rounded results as peaks.cu)
+//   C  hot_kernel       one CTA per block whose max exceeds the threshold: strict local maxima (flexible) or every
+//                       bin above the threshold (rigid) -> candidate list
+//   D  pick_*_kernel    one CTA of 32 warps: the reference's decision logic on the candidate list; prominence walks skip
+//                       whole 1024-bin blocks through the block max / min summaries (32 blocks per ballot)
+//
+// Decision semantics are those of peaks.cu (utils/get_peak_prominence.py:149-226, utils/get_peak_resolution.py:80-128).
+#include <algorithm>
+
+#include "common.cuh"
+#include "peaks_common.cuh"
+
+namespace {
+
+constexpr int SB = 1024;  // bins per summary block
+
+struct LargeState {
+    double mean, sd, thr;
+    int ncand, nfound, overflow, pad;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+mags_kernel(const typename vec2<T>::type *__restrict__ spec, T *__restrict__ mags, T *__restrict__ bmax,
+            T *__restrict__ bmin, dd *__restrict__ part) {
+    __shared__ dd red[16];
+    __shared__ T rmx[8], rmn[8];
+    const int tid = threadIdx.x;
+    const int64_t b0 = (int64_t)blockIdx.x * SB;
+    dd sx = {0.0, 0.0}, sxx = {0.0, 0.0};
+    T mx = T(0), mn = T(0);
+#pragma unroll
+    for (int u = 0; u < SB / 256; ++u) {
+        const int64_t i = b0 + tid + 256 * u;
+        const typename vec2<T>::type v = spec[i];
+        const T m = magnitude(v.x, v.y);
+        mags[i] = m;
+        mx = (u == 0 || m > mx) ? m : mx;
+        mn = (u == 0 || m < mn) ? m : mn;
+        const double d = (double)m;
+        if (sizeof(T) == 8) {
+            sx = dd_add_d(sx, d);
+            sxx = dd_add(sxx, two_prod(d, d));
+        } else {
+            sx.hi += d;
+            sxx.hi = __fma_rn(d, d, sxx.hi);
+        }
+    }
+    sx = warp_sum_dd(sx);
+    sxx = warp_sum_dd(sxx);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const T a = __shfl_xor_sync(0xffffffffu, mx, o), b = __shfl_xor_sync(0xffffffffu, mn, o);
+        mx = a > mx ? a : mx;
+        mn = b < mn ? b : mn;
+    }
+    if ((tid & 31) == 0) {
+        red[tid >> 5] = sx;
+        red[8 + (tid >> 5)] = sxx;
+        rmx[tid >> 5] = mx;
+        rmn[tid >> 5] = mn;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        dd a = red[0], b = red[8];
+        for (int w = 1; w < 8; ++w) {
+            a = dd_add(a, red[w]);
+            b = dd_add(b, red[8 + w]);
+            mx = rmx[w] > mx ? rmx[w] : mx;
+            mn = rmn[w] < mn ? rmn[w] : mn;
+        }
+        part[2 * blockIdx.x] = a;
+        part[2 * blockIdx.x + 1] = b;
+        bmax[blockIdx.x] = mx;
+        bmin[blockIdx.x] = mn;
+    }
+}
+
+__global__ void __launch_bounds__(256) stats_kernel(const dd *__restrict__ part, int nblk, int half, LargeState *st) {
+    __shared__ dd red[16];
+    const int tid = threadIdx.x;
+    dd a = {0.0, 0.0}, b = {0.0, 0.0};
+    for (int i = tid; i < nblk; i += 256) {
+        a = dd_add(a, part[2 * i]);
+        b = dd_add(b, part[2 * i + 1]);
+    }
+    a = warp_sum_dd(a);
+    b = warp_sum_dd(b);
+    if ((tid & 31) == 0) {
+        red[tid >> 5] = a;
+        red[8 + (tid >> 5)] = b;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        a = red[0];
+        b = red[8];
+        for (int w = 1; w < 8; ++w) {
+            a = dd_add(a, red[w]);
+            b = dd_add(b, red[8 + w]);
+        }
+        const double n = (double)half;
+        const dd mean = dd_div_d(a, n);
+        const dd ss = dd_add(b, dd_neg(dd_div_d(dd_mul(a, a), n)));
+        const dd var = dd_div_d(ss, n - 1.0);
+        st->mean = add_rn(mean.hi, mean.lo);
+        st->sd = dd_sqrt_to_double(var);
+        st->thr = add_rn(st->mean, mul_rn(2.0, st->sd));
+        st->ncand = 0;
+        st->nfound = 0;
+        st->overflow = 0;
+    }
+}
+
+template <typename T, bool FLEX>
+__global__ void __launch_bounds__(256)
+hot_kernel(const T *__restrict__ mags, const T *__restrict__ bmax, int half, LargeState *st, int *__restrict__ cand, int cap) {
+    const double thr = st->thr;
+    if (!((double)bmax[blockIdx.x] > thr)) return;
+    const int b0 = blockIdx.x * SB;
+    for (int u = 0; u < SB / 256; ++u) {
+        const int j = b0 + threadIdx.x + 256 * u;
+        const T m = mags[j];
+        if (!((double)m > thr)) continue;
+        bool take = true;
+        if (FLEX) take = j >= 1 && j <= half - 2 && m > mags[j - 1] && m > mags[j + 1];
+        if (take) {
+            const int pos = atomicAdd(&st->ncand, 1);
+            if (pos < cap) cand[pos] = j;
+            else st->overflow = 1;
+        }
+    }
+}
+
+// one direction of the prominence walk over bins [lo_b, hi_b] of the magnitude array (32 bins per step)
+template <typename T, int DIR>
+__device__ __forceinline__ bool scan_bins(const T *mags, int lo_b, int hi_b, T p, T &floor_lane, int lane) {
+    if (DIR < 0) {
+        for (int base = hi_b; base >= lo_b; base -= 32) {
+            const int i = base - lane;
+            const bool valid = i >= lo_b;
+            const T v = valid ? mags[i] : p;
+            const unsigned higher = __ballot_sync(0xffffffffu, valid && v > p);
+            const int stop = higher ? (__ffs(higher) - 1) : 32;
+            if (lane < stop && v < floor_lane) floor_lane = v;
+            if (higher) return true;
+        }
+    } else {
+        for (int base = lo_b; base <= hi_b; base += 32) {
+            const int i = base + lane;
+            const bool valid = i <= hi_b;
+            const T v = valid ? mags[i] : p;
+            const unsigned higher = __ballot_sync(0xffffffffu, valid && v > p);
+            const int stop = higher ? (__ffs(higher) - 1) : 32;
+            if (lane < stop && v < floor_lane) floor_lane = v;
+            if (higher) return true;
+        }
+    }
+    return false;
+}
+
+// utils/get_peak_prominence.py:32-54 with block summaries: whole 1024-bin blocks are skipped 32 at a time
+template <typename T>
+__device__ T summary_prominence(const T *mags, const T *bmax, const T *bmin, int half, int j, int lane) {
+    const T p = mags[j];
+    const int nblk = half / SB, bj = j / SB;
+    T fl = p, fr = p;
+    if (!scan_bins<T, -1>(mags, bj * SB, j - 1, p, fl, lane)) {
+        for (int base = bj - 1; base >= 0; base -= 32) {
+            const int b = base - lane;
+            const bool valid = b >= 0;
+            const unsigned higher = __ballot_sync(0xffffffffu, valid && bmax[b] > p);
+            const int stop = higher ? (__ffs(higher) - 1) : 32;
+            if (valid && lane < stop) {
+                const T m = bmin[b];
+                if (m < fl) fl = m;
+            }
+            if (higher) {
+                const int bs = base - stop;
+                scan_bins<T, -1>(mags, bs * SB, bs * SB + SB - 1, p, fl, lane);
+                break;
+            }
+        }
+    }
+    if (!scan_bins<T, +1>(mags, j + 1, bj * SB + SB - 1, p, fr, lane)) {
+        for (int base = bj + 1; base < nblk; base += 32) {
+            const int b = base + lane;
+            const bool valid = b < nblk;
+            const unsigned higher = __ballot_sync(0xffffffffu, valid && bmax[b] > p);
+            const int stop = higher ? (__ffs(higher) - 1) : 32;
+            if (valid && lane < stop) {
+                const T m = bmin[b];
+                if (m < fr) fr = m;
+            }
+            if (higher) {
+                const int bs = base + stop;
+                scan_bins<T, +1>(mags, bs * SB, bs * SB + SB - 1, p, fr, lane);
+                break;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const T a = __shfl_xor_sync(0xffffffffu, fl, o), b = __shfl_xor_sync(0xffffffffu, fr, o);
+        fl = a < fl ? a : fl;
+        fr = b < fr ? b : fr;
+    }
+    return sub_rn(p, fl > fr ? fl : fr);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024)
+pick_flexible_kernel(const T *__restrict__ mags, const T *__restrict__ bmax, const T *__restrict__ bmin, int64_t n,
+                     int half, double fs_all, const double *__restrict__ fs_ptr, int k, int rec_cap, LargeState *st, const int *__restrict__ cand,
+                     Found *__restrict__ found, int cap, unsigned char *__restrict__ rec) {
+    __shared__ int nfound_s;
+    __shared__ int acc_slot[APDA_MAX_REC_CAP];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ncand = min(st->ncand, cap);
+    const double fs = fs_ptr ? *fs_ptr : fs_all;
+    const double df = div_rn(fs, (double)n);
+    const double half_sd = mul_rn(0.5, st->sd);
+    if (tid == 0) nfound_s = 0;
+    __syncthreads();
+    for (int c = warp; c < ncand; c += 32) {
+        const int j = cand[c];
+        const T prom = summary_prominence<T>(mags, bmax, bmin, half, j, lane);
+        if (!((double)prom > half_sd)) continue;
+        const int bins = half_power_bins<T>(mags, half, prom, j);
+        const double width_hz = mul_rn((double)bins, df);
+        if (!(width_hz > 0.0)) continue;
+        const double fn = mul_rn((double)j, df);
+        const double q = div_rn(fn, width_hz);
+        const double damping = div_rn(1.0, mul_rn(2.0, q));
+        if (0.001 <= damping && damping <= 0.07 && lane == 0) {
+            const int pos = atomicAdd(&nfound_s, 1);
+            Found f;
+            f.rmag = round_dec4((double)mags[j]);
+            f.prom = (double)prom;
+            f.idx = j;
+            f.width = bins;
+            found[pos] = f;
+        }
+    }
+    __syncthreads();
+    // order by (rounded magnitude desc, idx asc) one element at a time; block-wide arg-max per step
+    __shared__ double bk[32];
+    __shared__ int bi[32], be[32];
+    __shared__ int sel_e, na_s;
+    __shared__ double prev_mag_s;
+    __shared__ int prev_idx_s;
+    if (tid == 0) {
+        na_s = 0;
+        prev_mag_s = CUDART_INF;
+        prev_idx_s = -1;
+    }
+    __syncthreads();
+    const int nfound = nfound_s;
+    while (true) {
+        const double prev_mag = prev_mag_s;
+        const int prev_idx = prev_idx_s;
+        double best = -1.0;
+        int best_idx = 0x7fffffff, best_e = -1;
+        for (int e = tid; e < nfound; e += 1024) {
+            const double r = found[e].rmag;
+            const int ix = found[e].idx;
+            const bool after_prev = r < prev_mag || (r == prev_mag && ix > prev_idx);
+            if (after_prev && (r > best || (r == best && ix < best_idx))) {
+                best = r;
+                best_idx = ix;
+                best_e = e;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double r = __shfl_xor_sync(0xffffffffu, best, o);
+            const int ix = __shfl_xor_sync(0xffffffffu, best_idx, o);
+            const int e = __shfl_xor_sync(0xffffffffu, best_e, o);
+            if (e >= 0 && (best_e < 0 || r > best || (r == best && ix < best_idx))) {
+                best = r;
+                best_idx = ix;
+                best_e = e;
+            }
+        }
+        if (lane == 0) {
+            bk[warp] = best;
+            bi[warp] = best_idx;
+            be[warp] = best_e;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < 32; ++w) {
+                if (be[w] >= 0 && (best_e < 0 || bk[w] > best || (bk[w] == best && bi[w] < best_idx))) {
+                    best = bk[w];
+                    best_idx = bi[w];
+                    best_e = be[w];
+                }
+            }
+            sel_e = best_e;
+            if (best_e >= 0) {
+                prev_mag_s = best;
+                prev_idx_s = best_idx;
+                const int na = na_s;
+                const double cf = round_dec4(mul_rn((double)best_idx, df));
+                bool hump = false;
+                for (int a = 0; a < na && !hump; ++a) {
+                    const double af = round_dec4(mul_rn((double)found[acc_slot[a]].idx, df));
+                    const double rel = div_rn(fabs(sub_rn(cf, af)), af);
+                    if (rel < 0.05 && div_rn(found[best_e].prom, best) < 0.10) hump = true;
+                }
+                if (!hump) {
+                    acc_slot[na] = best_e;
+                    na_s = na + 1;
+                }
+            }
+        }
+        __syncthreads();
+        if (sel_e < 0 || na_s >= k) break;
+    }
+    if (tid == 0) {
+        const int na = na_s;
+        write_rec_header(rec, na, st->overflow ? 1 : 0);
+        for (int a = 0; a < rec_cap; ++a) {
+            if (a < na) {
+                const Found f = found[acc_slot[a]];
+                write_rec_peak(rec, a, f.idx, f.width, (double)mags[f.idx], f.prom);
+            } else {
+                write_rec_peak(rec, a, -1, 0, 0.0, 0.0);
+            }
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024)
+pick_rigid_kernel(T *__restrict__ mags, int64_t n, int half, double fs_all, const double *__restrict__ fs_ptr, int k, int rec_cap, LargeState *st,
+                  const int *__restrict__ cand, int cap, unsigned char *__restrict__ rec) {
+    __shared__ double best_m[32];
+    __shared__ int best_j[32];
+    __shared__ int ctl[4];
+    __shared__ int acc_idx[APDA_MAX_REC_CAP];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nhot = min(st->ncand, cap);
+    const double thr = st->thr;
+    const double fs = fs_ptr ? *fs_ptr : fs_all;
+    const double df = div_rn(fs, (double)n);
+    const double distance = sub_rn(mul_rn(2.0, df), mul_rn(1.0, df));
+    if (tid == 0) ctl[3] = 0;
+    __syncthreads();
+    while (true) {
+        double bm = -1.0;
+        int bj = -1;
+        for (int e = tid; e < nhot; e += 1024) {
+            const int j = cand[e];
+            const T m = mags[j];
+            if (j >= 1 && j <= half - 2 && (double)m > thr && m > mags[j - 1] && m > mags[j + 1] &&
+                ((double)m > bm || ((double)m == bm && j < bj))) {
+                bm = (double)m;
+                bj = j;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double m2 = __shfl_xor_sync(0xffffffffu, bm, o);
+            const int j2 = __shfl_xor_sync(0xffffffffu, bj, o);
+            if (j2 >= 0 && (bj < 0 || m2 > bm || (m2 == bm && j2 < bj))) {
+                bm = m2;
+                bj = j2;
+            }
+        }
+        if (lane == 0) {
+            best_m[warp] = bm;
+            best_j[warp] = bj;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < 32; ++w) {
+                if (best_j[w] >= 0 && (bj < 0 || best_m[w] > bm || (best_m[w] == bm && best_j[w] < bj))) {
+                    bm = best_m[w];
+                    bj = best_j[w];
+                }
+            }
+            ctl[0] = bj;
+            if (bj >= 0) {
+                const int na = ctl[3];
+                const double f = mul_rn((double)bj, df);
+                const int w2 = half_height_bins<T>(mags, half, bj);
+                bool separated = true;
+                for (int a = 0; a < na && separated; ++a) {
+                    const int w1 = half_height_bins<T>(mags, half, acc_idx[a]);
+                    double rs = 0.0;
+                    if (w1 + w2 != 0) rs = div_rn(mul_rn(1.18, (double)abs(bj - acc_idx[a])), (double)(w1 + w2));
+                    if (!(rs >= 1.5)) separated = false;
+                }
+                if (separated) {
+                    acc_idx[na] = bj;
+                    write_rec_peak(rec, na, bj, w2, bm, 0.0);
+                    ctl[3] = na + 1;
+                }
+                double reach_d = rint(div_rn(mul_rn(f, 0.02), distance));
+                if (!(reach_d >= 0.0)) reach_d = 0.0;
+                if (reach_d > (double)half) reach_d = (double)half;
+                const int reach = (int)reach_d;
+                ctl[1] = max(0, bj - reach);
+                ctl[2] = min(half, bj + reach + 1);
+            }
+        }
+        __syncthreads();
+        if (ctl[0] < 0) break;
+        for (int j = ctl[1] + tid; j < ctl[2]; j += 1024) mags[j] = T(0);
+        const bool full = ctl[3] >= k;
+        __threadfence_block();
+        __syncthreads();
+        if (full) break;
+    }
+    if (tid == 0) {
+        const int na = ctl[3];
+        write_rec_header(rec, na, st->overflow ? 1 : 0);
+        for (int a = na; a < rec_cap; ++a) write_rec_peak(rec, a, -1, 0, 0.0, 0.0);
+    }
+}
+
+struct LargeLayout {
+    size_t mags, bmax, bmin, part, state, cand, found, bytes;
+    int cap, nblk;
+};
+template <typename T>
+LargeLayout large_layout(int64_t half) {
+    LargeLayout l;
+    l.nblk = (int)(half / SB);
+    l.cap = (int)std::min<int64_t>(half / 4 + 8, 1 << 20);
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        size_t at = o;
+        o += (bytes + 255) & ~(size_t)255;
+        return at;
+    };
+    l.mags = take((size_t)half * sizeof(T));
+    l.bmax = take((size_t)l.nblk * sizeof(T));
+    l.bmin = take((size_t)l.nblk * sizeof(T));
+    l.part = take((size_t)l.nblk * 2 * sizeof(dd));
+    l.state = take(sizeof(LargeState));
+    l.cand = take((size_t)l.cap * sizeof(int));
+    l.found = take((size_t)l.cap * sizeof(Found));
+    l.bytes = o;
+    return l;
+}
+
+}  // namespace
+
+bool peaks_large_supports(int64_t n) { return is_pow2_i64(n) && n >= (int64_t(1) << 16) && n <= (int64_t(1) << 31); }
+
+template <typename T>
+size_t peaks_large_workspace_bytes(int64_t n) {
+    return large_layout<T>(n / 2).bytes;
+}
+template size_t peaks_large_workspace_bytes<double>(int64_t);
+template size_t peaks_large_workspace_bytes<float>(int64_t);
+
+// windows are processed one after the other (long windows are few); ws holds one window's scratch
+template <typename T>
+int launch_peaks_large(apda_ctx *ctx, cudaStream_t st, const T *d_spec, int64_t n, int64_t batch, double fs,
+                       const double *d_fs, int k, int rec_cap, int flexible, void *d_rec, void *ws) {
+    using V2 = typename vec2<T>::type;
+    const int64_t half = n / 2;
+    const LargeLayout l = large_layout<T>(half);
+    char *base = reinterpret_cast<char *>(ws);
+    T *mags = reinterpret_cast<T *>(base + l.mags);
+    T *bmax = reinterpret_cast<T *>(base + l.bmax), *bmin = reinterpret_cast<T *>(base + l.bmin);
+    dd *part = reinterpret_cast<dd *>(base + l.part);
+    LargeState *state = reinterpret_cast<LargeState *>(base + l.state);
+    int *cand = reinterpret_cast<int *>(base + l.cand);
+    Found *found = reinterpret_cast<Found *>(base + l.found);
+    for (int64_t w = 0; w < batch; ++w) {
+        const V2 *spec = reinterpret_cast<const V2 *>(d_spec) + w * n;
+        unsigned char *rec = reinterpret_cast<unsigned char *>(d_rec) + w * APDA_REC_BYTES(rec_cap);
+        const double *fs_ptr = d_fs ? d_fs + w : nullptr;
+        mags_kernel<T><<<l.nblk, 256, 0, st>>>(spec, mags, bmax, bmin, part);
+        stats_kernel<<<1, 256, 0, st>>>(part, l.nblk, (int)half, state);
+        if (flexible) {
+            hot_kernel<T, true><<<l.nblk, 256, 0, st>>>(mags, bmax, (int)half, state, cand, l.cap);
+            pick_flexible_kernel<T><<<1, 1024, 0, st>>>(mags, bmax, bmin, n, (int)half, fs, fs_ptr, k, rec_cap, state, cand, found,
+                                                        l.cap, rec);
+        } else {
+            hot_kernel<T, false><<<l.nblk, 256, 0, st>>>(mags, bmax, (int)half, state, cand, l.cap);
+            pick_rigid_kernel<T><<<1, 1024, 0, st>>>(mags, n, (int)half, fs, fs_ptr, k, rec_cap, state, cand, l.cap, rec);
+        }
+        ctx->launches += 4;
+    }
+    APDA_CUDA(cudaGetLastError());
+    return APDA_OK;
+}
+template int launch_peaks_large<double>(apda_ctx *, cudaStream_t, const double *, int64_t, int64_t, double, const double *,
+                                        int, int, int, void *, void *);
+template int launch_peaks_large<float>(apda_ctx *, cudaStream_t, const float *, int64_t, int64_t, double, const double *, int,
+                                       int, int, void *, void *);

@@ -422,3 +422,28 @@ def test_fft_large_tma_equals_plain_tail_passes(an):
             else:
                 # generic_only also swaps the fp32 small-N kernels; at these sizes both runs use K2, so bits match too
                 assert np.array_equal(a.view(np.float32), b.view(np.float32)), log2n
+
+
+def test_peaks_large_multi_cta_vs_general_and_oracle(an):
+    """K3 large form (n >= 2^16, chip-wide): same records as the one-CTA general kernel, and as the oracle at 2^16."""
+    rng = np.random.default_rng(21)
+    for log2n in (16, 18):
+        n = 1 << log2n
+        i = np.arange(n, dtype=np.float64)
+        x = np.round(0.5 * np.sin(2 * np.pi * 1001.6 * i / n) + 0.3 * np.sin(2 * np.pi * 2520.4 * i / n + 0.3)
+                     + 0.2 * np.sin(2 * np.pi * 4980.0 * i / n + 1.1) + 0.01 * rng.uniform(-1, 1, n), 6)
+        spec = an.fft(x)
+        noise = an.fft(np.round(rng.standard_normal(n), 6))
+        for z in (spec, noise):
+            for flexible in (True, False):
+                for dt in (np.complex128, np.complex64):
+                    fast = an.peaks(z.astype(dt), 250.0, flexible=flexible)
+                    an.ctx.set_generic_only(True)
+                    try:
+                        slow = an.peaks(z.astype(dt), 250.0, flexible=flexible)
+                    finally:
+                        an.ctx.set_generic_only(False)
+                    assert fast.tobytes() == slow.tobytes(), (log2n, flexible, dt)
+        if log2n == 16:
+            assert _dicts(an.peaks(spec, 250.0, flexible=True)[0], 250.0, n, True) == c_oracle.peaks_prominence(spec[0], 250.0)
+            assert _dicts(an.peaks(spec, 250.0, flexible=False)[0], 250.0, n, False) == c_oracle.peaks_resolution(spec[0], 250.0)
