@@ -224,7 +224,7 @@ __device__ __forceinline__ void middle_or_last_pass(double2 *s, const double2 *_
 }
 
 template <int LOGN>
-__global__ void __launch_bounds__(Plan64<LOGN>::T)
+__global__ void __launch_bounds__(Plan64<LOGN>::T, (LOGN <= 12 ? 768 / Plan64<LOGN>::T : 1))
 fft_f64_fast_kernel(const double *__restrict__ samples, int n_samples, int64_t ld, const double2 *__restrict__ tw,
                     double2 *__restrict__ spec, int center) {
     using PL = Plan64<LOGN>;
