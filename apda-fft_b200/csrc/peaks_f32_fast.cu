@@ -412,10 +412,16 @@ peaks_f32_fast_kernel(const float2 *__restrict__ spec, int64_t batch, double df_
 #pragma unroll
             for (int a = 0; a < 5; ++a) {
                 if (a < na && separated) {
-                    const int w1 = half_height_bins_f<HALF>(mags, acc_idx[a]);
-                    double rs = 0.0;
-                    if (w1 + w2 != 0) rs = div_rn(mul_rn(1.18, (double)abs(bj - acc_idx[a])), (double)(w1 + w2));
-                    if (!(rs >= 1.5)) separated = false;
+                    // an accepted peak's own bin was zeroed when it was found, so its half-height width is 0 (the
+                    // reference's resolution() degenerates to 1.18*dist/w_candidate); walk only if that ever fails
+                    const int w1 = mags[P::addr(acc_idx[a])] == 0.f ? 0 : half_height_bins_f<HALF>(mags, acc_idx[a]);
+                    bool ok = false;
+                    if (w1 + w2 != 0) {
+                        const double num = mul_rn(1.18, (double)abs(bj - acc_idx[a])), den = 1.5 * (double)(w1 + w2);
+                        if (num >= den * (1.0 + 1e-12)) ok = true;                       // rs >= 1.5 by a clear margin
+                        else if (!(num < den * (1.0 - 1e-12))) ok = div_rn(num, (double)(w1 + w2)) >= 1.5;
+                    }
+                    if (!ok) separated = false;
                 }
             }
             if (separated) {
@@ -430,8 +436,18 @@ peaks_f32_fast_kernel(const float2 *__restrict__ spec, int64_t batch, double df_
                     if (a == na) acc_idx[a] = bj;
                 ++na;
             }
-            const double f = mul_rn((double)bj, df);
-            double reach_d = rint(div_rn(mul_rn(f, 0.02), distance));
+            // zeroing radius round((freq * 0.02) / (frequencies[2] - frequencies[1])): equals round-half-even(0.02 * idx)
+            // unless that product sits within 1e-6 of a tie; only then (or for a degenerate df) the exact expression runs
+            double reach_d;
+            {
+                const double x02 = 0.02 * (double)bj, fr = x02 - floor(x02);
+                if (df > 1e-300 && df < 1e300 && fabs(fr - 0.5) > 1e-6) {
+                    reach_d = rint(x02);
+                } else {
+                    const double f = mul_rn((double)bj, df);
+                    reach_d = rint(div_rn(mul_rn(f, 0.02), distance));
+                }
+            }
             if (!(reach_d >= 0.0)) reach_d = 0.0;
             if (reach_d > (double)HALF) reach_d = (double)HALF;
             const int reach = (int)reach_d;
