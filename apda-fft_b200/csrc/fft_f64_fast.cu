@@ -237,7 +237,8 @@ fft_f64_fast_kernel(const double *__restrict__ samples, int n_samples, int64_t l
     const int64_t win = blockIdx.x;
     const double *x = samples + win * ld;
 
-    for (int i = t; i < N; i += T) raw[i + (i >> 3)] = i < n_samples ? x[i] : CUDART_INF;
+    // streaming loads: keep L1 for the twiddle table (64 KB at N = 4096), which every window re-reads
+    for (int i = t; i < N; i += T) raw[i + (i >> 3)] = i < n_samples ? __ldcs(x + i) : CUDART_INF;
     __syncthreads();
     // work item hi = t of pass 0 owns outputs idx = 16*t + r, i.e. inputs bitrev(idx) = bitrev4(r) * N/16 + bitrev(t)
     const int tb = (int)(__brev((unsigned)t) >> (32 - (LOGN - 4)));
