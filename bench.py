@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--center", choices=["median", "mean"], default="median")
     ap.add_argument("--e2e-windows", type=int, default=131072, help="windows per GPU of the host-buffer (e2e) leg")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU work budget of the cpu_baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=60.0, help="CPU work budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
@@ -108,7 +108,7 @@ def run_reference_arm(args):
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     flexible = args.picker == "flexible"
-    per_core = 4
+    per_core = 16
     pool = mp.get_context("spawn").Pool(cores)
     try:
         for _ in range(args.warmup):
