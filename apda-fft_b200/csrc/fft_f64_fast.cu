@@ -237,8 +237,20 @@ fft_f64_fast_kernel(const double *__restrict__ samples, int n_samples, int64_t l
     const int64_t win = blockIdx.x;
     const double *x = samples + win * ld;
 
-    // streaming loads: keep L1 for the twiddle table (64 KB at N = 4096), which every window re-reads
-    for (int i = t; i < N; i += T) raw[i + (i >> 3)] = i < n_samples ? __ldcs(x + i) : CUDART_INF;
+    {   // streaming loads (L1 is kept for the twiddle table); all 16 loads of a thread are issued before the first store,
+        // so one HBM latency is exposed instead of sixteen
+        double ld_v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int i = t + T * u;
+            ld_v[u] = i < n_samples ? __ldcs(x + i) : CUDART_INF;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int i = t + T * u;
+            raw[i + (i >> 3)] = ld_v[u];
+        }
+    }
     __syncthreads();
     // work item hi = t of pass 0 owns outputs idx = 16*t + r, i.e. inputs bitrev(idx) = bitrev4(r) * N/16 + bitrev(t)
     const int tb = (int)(__brev((unsigned)t) >> (32 - (LOGN - 4)));
