@@ -20,7 +20,17 @@ namespace {
 
 template <typename T>
 __device__ void load_magnitudes(const typename vec2<T>::type *spec, T *mags, int half) {
-    for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    // four independent loads in flight per thread before the (long) magnitude arithmetic consumes them
+    const int step = blockDim.x;
+    int i = threadIdx.x;
+    for (; i + 3 * step < half; i += 4 * step) {
+        typename vec2<T>::type v0 = spec[i], v1 = spec[i + step], v2 = spec[i + 2 * step], v3 = spec[i + 3 * step];
+        mags[i] = magnitude(v0.x, v0.y);
+        mags[i + step] = magnitude(v1.x, v1.y);
+        mags[i + 2 * step] = magnitude(v2.x, v2.y);
+        mags[i + 3 * step] = magnitude(v3.x, v3.y);
+    }
+    for (; i < half; i += step) {
         typename vec2<T>::type v = spec[i];
         mags[i] = magnitude(v.x, v.y);
     }
