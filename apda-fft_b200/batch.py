@@ -84,6 +84,25 @@ class Analyzer:
                       fs_scalar, _p(fs_arr.ctypes.data if fs_arr is not None else 0), k, cap, _p(recs.ctypes.data))
         return recs
 
+    def analyze_fused(self, samples: np.ndarray, fs, flexible: bool = True, k: int | None = None,
+                      center: int = _cabi.CENTER_MEDIAN) -> np.ndarray:
+        """[B, N] float32, N in {1024, 2048, 4096, 8192} -> records[B] through the fused window->record kernel."""
+        x = np.ascontiguousarray(np.atleast_2d(samples), dtype=np.float32)
+        b, ns = x.shape
+        n = next_pow2(ns)
+        k = (4 if flexible else 5) if k is None else int(k)
+        recs = np.zeros(b, dtype=record_dtype(5))
+        fs_scalar, fs_arr = self._fs(fs, b)
+        self.ctx.call("apda_analyze_fused_f32_host", _p(x.ctypes.data), ns, ns, b, n, center, int(bool(flexible)), fs_scalar,
+                      _p(fs_arr.ctypes.data if fs_arr is not None else 0), k, 5, _p(recs.ctypes.data))
+        return recs
+
+    def analyze_fused_device(self, d_samples: int, batch: int, n_samples: int, n_fft: int, fs: float, d_rec: int,
+                             flexible: bool = True, k: int = 4, center: int = _cabi.CENTER_MEDIAN, d_fs: int = 0,
+                             ld: int | None = None) -> None:
+        self.ctx.call("apda_analyze_fused_f32_dev", _p(d_samples), n_samples, ld or n_samples, batch, n_fft, center,
+                      int(bool(flexible)), float(fs), _p(d_fs), k, 5, _p(d_rec))
+
     def analyze_host_ptr(self, h_ptr: int, batch: int, n_samples: int, n_fft: int, dtype: str, fs: float,
                          h_rec_ptr: int, flexible: bool = True, k: int = 4, rec_cap: int = 5,
                          center: int = _cabi.CENTER_MEDIAN) -> None:

@@ -357,7 +357,7 @@ extern "C" int apda_analyze_f32_dev(apda_ctx *ctx, const float *d_samples, int64
 // ---------------------------------------------------------------------------------------------------------------
 // host-pointer entry points: chunked two-stream pipeline (H2D of chunk c+1 overlaps the kernels / D2H of chunk c)
 // ---------------------------------------------------------------------------------------------------------------
-enum HostMode { kFftOnly, kPeaksOnly, kAnalyze };
+enum HostMode { kFftOnly, kPeaksOnly, kAnalyze, kFused };
 
 template <typename T>
 static int host_pipeline(apda_ctx *ctx, HostMode mode, const T *h_in, int64_t n_samples, int64_t ld, int64_t batch,
@@ -370,15 +370,15 @@ static int host_pipeline(apda_ctx *ctx, HostMode mode, const T *h_in, int64_t n_
     const size_t in_ld = mode == kPeaksOnly ? (size_t)N * 2 : (complex_in ? (size_t)N * 2 : (size_t)ld);
     const size_t spec_elems = (size_t)N * 2;
     // chunk: ~96 MB of spectrum per stream, at least one window
-    int64_t chunk = std::max<int64_t>(1, (int64_t)((96u << 20) / (spec_elems * sizeof(T))));
+    int64_t chunk = std::max<int64_t>(1, (int64_t)((96u << 20) / ((mode == kFused ? in_elems : spec_elems) * sizeof(T))));
     chunk = std::min<int64_t>(chunk, batch);
     if (batch > chunk && batch < 2 * chunk) chunk = (batch + 1) / 2;
 
     const size_t in_bytes = align256(chunk * in_elems * sizeof(T));
-    const size_t spec_bytes = mode == kPeaksOnly ? 0 : align256(chunk * spec_elems * sizeof(T));
+    const size_t spec_bytes = (mode == kPeaksOnly || mode == kFused) ? 0 : align256(chunk * spec_elems * sizeof(T));
     const size_t recs_bytes = mode == kFftOnly ? 0 : align256(chunk * rec_bytes);
     const size_t fs_bytes = (h_fs && mode != kFftOnly) ? align256(chunk * sizeof(double)) : 0;
-    const size_t mag_bytes = mode == kFftOnly ? 0 : align256(peaks_mag_workspace_bytes<T>(ctx, N, chunk));
+    const size_t mag_bytes = (mode == kFftOnly || mode == kFused) ? 0 : align256(peaks_mag_workspace_bytes<T>(ctx, N, chunk));
     const size_t total = in_bytes + spec_bytes + recs_bytes + fs_bytes + mag_bytes;
     for (int s = 0; s < 2; ++s) {
         if (total > ctx->ws_pipe_bytes[s]) {
@@ -412,6 +412,15 @@ static int host_pipeline(apda_ctx *ctx, HostMode mode, const T *h_in, int64_t n_
         if (d_fs) APDA_CUDA(cudaMemcpyAsync(d_fs, h_fs + done, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
 
         const T *spec_for_peaks = d_in;
+        if (mode == kFused) {
+            status = launch_fused_f32(ctx, st, reinterpret_cast<const float *>(d_in), n_samples, (int64_t)in_elems, cnt, N,
+                                      flags, flexible, fs, d_fs, k, d_rec);
+            if (status == APDA_OK)
+                APDA_CUDA(cudaMemcpyAsync((char *)h_rec_out + (size_t)done * rec_bytes, d_rec, cnt * rec_bytes,
+                                          cudaMemcpyDeviceToHost, st));
+            done += cnt;
+            continue;
+        }
         if (mode != kPeaksOnly) {
             status = fft_dispatch<T>(ctx, st, d_in, n_samples, (int64_t)in_elems, cnt, N, flags, d_spec, complex_in);
             spec_for_peaks = d_spec;
@@ -492,6 +501,39 @@ extern "C" int apda_analyze_f32_host(apda_ctx *ctx, const float *h_samples, int6
     APDA_TRY(check_peaks_args(ctx, h_samples, N, batch, k, rec_cap, h_rec));
     return host_pipeline<float>(ctx, kAnalyze, h_samples, n_samples, ld, batch, N, flags, flexible, fs, h_fs, k, rec_cap,
                                 false, nullptr, h_rec);
+}
+
+static int check_fused_args(int64_t N, int flags, int k, int rec_cap) {
+    if (!fft_f32_fast_supports(N) || rec_cap != 5 || k < 1 || k > 5) {
+        apda_set_error("analyze_fused_f32: needs N in {1024, 2048, 4096, 8192}, 1 <= k <= 5 and 128-byte records (rec_cap 5)");
+        return APDA_ERR_UNSUPPORTED;
+    }
+    if (flags == APDA_CENTER_NONE) {
+        apda_set_error("analyze_fused_f32: APDA_CENTER_NONE is not offered by the fused kernel");
+        return APDA_ERR_UNSUPPORTED;
+    }
+    return APDA_OK;
+}
+
+extern "C" int apda_analyze_fused_f32_dev(apda_ctx *ctx, const float *d_samples, int64_t n_samples, int64_t ld,
+                                          int64_t batch, int64_t N, int flags, int flexible, double fs,
+                                          const double *d_fs, int k, int rec_cap, void *d_rec) {
+    APDA_TRY(check_fft_args(ctx, d_samples, n_samples, ld, batch, N, flags, d_rec));
+    APDA_TRY(check_peaks_args(ctx, d_samples, N, batch, k, rec_cap, d_rec));
+    APDA_TRY(check_fused_args(N, flags, k, rec_cap));
+    APDA_CUDA(cudaSetDevice(ctx->device));
+    if (batch == 0) return APDA_OK;
+    return launch_fused_f32(ctx, ctx->stream, d_samples, n_samples, ld, batch, N, flags, flexible, fs, d_fs, k, d_rec);
+}
+
+extern "C" int apda_analyze_fused_f32_host(apda_ctx *ctx, const float *h_samples, int64_t n_samples, int64_t ld,
+                                           int64_t batch, int64_t N, int flags, int flexible, double fs,
+                                           const double *h_fs, int k, int rec_cap, void *h_rec) {
+    APDA_TRY(check_fft_args(ctx, h_samples, n_samples, ld, batch, N, flags, h_rec));
+    APDA_TRY(check_peaks_args(ctx, h_samples, N, batch, k, rec_cap, h_rec));
+    APDA_TRY(check_fused_args(N, flags, k, rec_cap));
+    return host_pipeline<float>(ctx, kFused, h_samples, n_samples, ld, batch, N, flags, flexible, fs, h_fs, k, rec_cap, false,
+                                nullptr, h_rec);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -1,0 +1,486 @@
+// K3 (fp32 fast form) for n = 1024 / 2048 / 4096 / 8192 bins per window, k <= 5, 128-byte records: the headline picker.
+//
+// One WARP per window, four windows per CTA, no block-level barrier.
+//   phase 1  32 lanes stream the half spectrum with coalesced 128-bit loads (8 in flight per lane), take magnitudes,
+//            accumulate sum / sum of squares in registers and stage the magnitudes in shared memory;
+//   phase 2  every lane re-reads one CONTIGUOUS chunk of HALF/32 bins (conflict-free 128-bit LDS thanks to a 4-word
+//            pad per chunk), keeps the chunk's max and min in registers and appends the few bins above
+//            mean + 2 sigma ("hot" bins, < 20 % of the bins by Cantelli's inequality, typically ~10) to a slot list;
+//   flexible picker: for every hot strict local maximum the prominence walk runs on the chunk summaries - whole
+//            chunks are skipped with one ballot over the lanes' chunk maxima, only the two boundary chunks are
+//            scanned (warp-cooperatively, 32 bins per step); the scalar epilogue (half-power width, damping gate,
+//            decimal rounding) runs lane-parallel, one candidate per lane; a warp arg-max extracts the order
+//            "descending round(mag, 4), ascending idx" for the greedy hump exclusion;
+//   rigid picker: the iterative arg-max / resolution test / +-2 % zeroing loop works on the hot list only (zeroing
+//            can only create new maxima among bins that were already above the threshold).
+// The record (128 B) is assembled in shared memory and written with one coalesced 128-byte store.
+//
+// Decision semantics are those of peaks.cu (the general kernel), which documents the reference line by line:
+//   utils/get_peak_prominence.py:149-226, utils/get_peak_resolution.py:80-128.
+#pragma once
+#include "common.cuh"
+
+namespace {
+
+constexpr int kWPC = 2;  // windows (warps) per CTA
+
+struct Slot {
+    uint16_t idx;
+    uint16_t width;  // flexible: half-power bins if the candidate passed every gate, else 0
+    float prom;
+};
+
+template <int HALF>
+struct K3 {
+    static constexpr int C = HALF / 32;                // bins per lane chunk
+    static constexpr int MAGW = HALF + 4 * 32;         // magnitude words incl. 4-word pad per chunk
+    static constexpr int SLOTS = 96;                   // candidates / hot bins kept on chip; more -> repair list (general kernel)
+    static constexpr int REC_OFF = MAGW * 4 + SLOTS * 8;
+    static constexpr int BYTES = (REC_OFF + 128 + 15) & ~15;
+    __device__ static __forceinline__ int addr(int b) { return b + 4 * (b / C); }
+    // word offset of the 64-bin row R (R = r0 + u with r0 a multiple of 8: row_off is additive in that split)
+    __device__ static __forceinline__ int row_off(int R) { return 64 * R + (C <= 64 ? 4 * (64 / C) * R : 4 * (R / (C / 64))); }
+};
+
+__device__ __forceinline__ double round_dec4_d(double x) {  // exact emulation of Python round(x, 4); see peaks.cu
+    const double p = 1e4;
+    double hi = mul_rn(x, p);
+    double lo = __fma_rn(x, p, -hi);
+    double n = rint(hi);
+    double d = sub_rn(hi, n);
+    if (d == 0.5 && lo > 0.0) n += 1.0;
+    if (d == -0.5 && lo < 0.0) n -= 1.0;
+    return div_rn(n, p);
+}
+
+__device__ __forceinline__ float sqrt_fast(float x) {  // MUFU.SQRT: <= 1 ulp, far inside the fp32 path's 1e-5 contract
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// div_rn(x, y) < c, decided by one multiplication unless the quotient is within a few ulps of c (then by the division)
+__device__ __forceinline__ bool ratio_lt(double x, double y, double c) {
+    const double t = c * y;
+    if (y > 0.0 && x < t * (1.0 - 0x1p-48)) return true;
+    if (y > 0.0 && x > t * (1.0 + 0x1p-48)) return false;
+    return div_rn(x, y) < c;
+}
+
+// integer n with round(x, 4) == n / 1e4 (see round_dec4_d); ordering by n == ordering by the rounded value
+__device__ __forceinline__ double round_dec4_units(double x) {
+    const double p = 1e4;
+    double hi = mul_rn(x, p);
+    double lo = __fma_rn(x, p, -hi);
+    double n = rint(hi);
+    double d = sub_rn(hi, n);
+    if (d == 0.5 && lo > 0.0) n += 1.0;
+    if (d == -0.5 && lo < 0.0) n -= 1.0;
+    return n;
+}
+
+__device__ __forceinline__ float4 ldg_stream(const float4 *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// one direction of the prominence walk inside [lo_b, hi_b] (a piece of one chunk), 32 bins per step.
+// DIR = -1: from hi_b downwards, +1: from lo_b upwards.  Returns true when a bin strictly higher than p stopped it.
+template <int HALF, int DIR>
+__device__ __forceinline__ bool scan_piece(const float *mags, int lo_b, int hi_b, float p, float &floor_lane, int lane) {
+    if (DIR < 0) {
+        for (int base = hi_b; base >= lo_b; base -= 32) {
+            const int i = base - lane;
+            const bool valid = i >= lo_b;
+            const float v = valid ? mags[K3<HALF>::addr(i)] : p;
+            const unsigned higher = __ballot_sync(0xffffffffu, valid && v > p);
+            const int stop = higher ? (__ffs(higher) - 1) : 32;
+            if (lane < stop && v < floor_lane) floor_lane = v;
+            if (higher) return true;
+        }
+    } else {
+        for (int base = lo_b; base <= hi_b; base += 32) {
+            const int i = base + lane;
+            const bool valid = i <= hi_b;
+            const float v = valid ? mags[K3<HALF>::addr(i)] : p;
+            const unsigned higher = __ballot_sync(0xffffffffu, valid && v > p);
+            const int stop = higher ? (__ffs(higher) - 1) : 32;
+            if (lane < stop && v < floor_lane) floor_lane = v;
+            if (higher) return true;
+        }
+    }
+    return false;
+}
+
+// utils/get_peak_prominence.py:32-54 on the chunk summaries (cmax/cmin: this lane's chunk maximum / minimum)
+template <int HALF>
+__device__ float coop_prominence(const float *mags, int j, float cmax, float cmin, int lane) {
+    constexpr int C = K3<HALF>::C;
+    const float p = mags[K3<HALF>::addr(j)];
+    const int cj = j / C;
+    const unsigned above = __ballot_sync(0xffffffffu, cmax > p);
+    float fl = p, fr = p;
+    if (!scan_piece<HALF, -1>(mags, C * cj, j - 1, p, fl, lane)) {
+        const unsigned hl = above & ((1u << cj) - 1u);
+        const int L = hl ? 31 - __clz(hl) : -1;
+        if (lane > L && lane < cj && cmin < fl) fl = cmin;
+        if (L >= 0) scan_piece<HALF, -1>(mags, C * L, C * (L + 1) - 1, p, fl, lane);
+    }
+    if (!scan_piece<HALF, +1>(mags, j + 1, C * (cj + 1) - 1, p, fr, lane)) {
+        const unsigned hr = above & ~((2u << cj) - 1u);
+        const int R = hr ? __ffs(hr) - 1 : 32;
+        if (lane > cj && lane < R && cmin < fr) fr = cmin;
+        if (R < 32) scan_piece<HALF, +1>(mags, C * R, C * (R + 1) - 1, p, fr, lane);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        fl = fminf(fl, __shfl_xor_sync(0xffffffffu, fl, o));
+        fr = fminf(fr, __shfl_xor_sync(0xffffffffu, fr, o));
+    }
+    return __fsub_rn(p, fmaxf(fl, fr));
+}
+
+template <int HALF>
+__device__ __forceinline__ int half_power_bins_f(const float *mags, float prom, int j) {
+    const float top = mags[K3<HALF>::addr(j)];
+    const float level = __fadd_rn(__fsub_rn(top, prom), __fmul_rn(prom, 0.707f));
+    int lo = j;
+    while (lo > 0 && mags[K3<HALF>::addr(lo)] > level) {
+        if (mags[K3<HALF>::addr(lo)] > top) break;
+        --lo;
+    }
+    int hi = j;
+    while (hi < HALF - 1 && mags[K3<HALF>::addr(hi)] > level) {
+        if (mags[K3<HALF>::addr(hi)] > top) break;
+        ++hi;
+    }
+    const int w = hi - lo;
+    return w > 1 ? w : 1;
+}
+
+template <int HALF>
+__device__ __forceinline__ int half_height_bins_f(const float *mags, int j) {
+    const float level = __fmul_rn(0.707f, mags[K3<HALF>::addr(j)]);
+    int lo = j;
+    while (lo > 0 && mags[K3<HALF>::addr(lo)] > level) --lo;
+    int hi = j;
+    while (hi < HALF && mags[K3<HALF>::addr(hi)] > level) ++hi;
+    return hi - lo;
+}
+
+// The reference sorts the gated candidates by round(mag, 4) descending (stable: ties keep ascending idx) and walks that
+// order with the greedy "hump" exclusion.  Each lane owns PER slots; a slot's place in the order is its rank (number of
+// passing slots that precede it), computed once with shuffles.  Accepted peaks go straight into the record.
+template <int HALF, int PER>
+__device__ __forceinline__ int order_and_exclude(const Slot *slots, int nslot, const float *mags, unsigned char *rec_s,
+                                                 double df, int k, int lane) {
+    using P = K3<HALF>;
+    double key[PER];
+    int sidx[PER], srank[PER];
+    unsigned passm[PER];
+    int npass = 0;
+#pragma unroll
+    for (int r = 0; r < PER; ++r) {
+        const int e = lane + 32 * r;
+        const bool ok = e < nslot && slots[e].width != 0;
+        sidx[r] = ok ? (int)slots[e].idx : 0x7fffffff;
+        key[r] = -1.0;
+        if (ok) key[r] = round_dec4_units((double)mags[P::addr(sidx[r])]);
+        passm[r] = __ballot_sync(0xffffffffu, ok);
+        npass += __popc(passm[r]);
+        srank[r] = 0;
+    }
+#pragma unroll
+    for (int r2 = 0; r2 < PER; ++r2) {
+        for (unsigned m = passm[r2]; m; m &= m - 1) {
+            const int src = __ffs(m) - 1;
+            const double ko = __shfl_sync(0xffffffffu, key[r2], src);
+            const int io = __shfl_sync(0xffffffffu, sidx[r2], src);
+#pragma unroll
+            for (int r = 0; r < PER; ++r) srank[r] += (ko > key[r]) || (ko == key[r] && io < sidx[r]);
+        }
+    }
+    int na = 0;
+    for (int pos = 0; pos < npass && na < k; ++pos) {
+        int e_sel = -1;
+#pragma unroll
+        for (int r = 0; r < PER; ++r) {
+            const unsigned hit = __ballot_sync(0xffffffffu, (passm[r] >> lane & 1u) && srank[r] == pos);
+            if (hit) e_sel = (__ffs(hit) - 1) + 32 * r;
+        }
+        const int c_idx = slots[e_sel].idx;
+        const float cprom = slots[e_sel].prom;
+        const float cmag = mags[P::addr(c_idx)];
+        bool hump = false;
+        for (int a = 0; a < na && !hump; ++a) {
+            const int ja = reinterpret_cast<const int *>(rec_s + 8 + 24 * a)[0];
+            const double fc = mul_rn((double)c_idx, df), fa = mul_rn((double)ja, df);
+            // |round4(fc) - round4(fa)| >= |fc - fa| - 1e-4 and round4(fa) <= fa + 5e-5: most pairs are provably > 5 % apart
+            if (fabs(fc - fa) - 1.0e-4 > 0.05 * (fa + 5.0e-5) * (1.0 + 1e-9)) continue;
+            const double cf = round_dec4_d(fc), af = round_dec4_d(fa);
+            if (div_rn(fabs(sub_rn(cf, af)), af) < 0.05 &&
+                div_rn((double)cprom, div_rn(round_dec4_units((double)cmag), 1e4)) < 0.10)
+                hump = true;
+        }
+        if (!hump) {
+            if (lane == 0) {
+                unsigned char *pk = rec_s + 8 + 24 * na;
+                reinterpret_cast<int *>(pk)[0] = c_idx;
+                reinterpret_cast<int *>(pk)[1] = slots[e_sel].width;
+                reinterpret_cast<double *>(pk + 8)[0] = (double)cmag;
+                reinterpret_cast<double *>(pk + 8)[1] = (double)cprom;
+            }
+            ++na;
+            __syncwarp();
+        }
+    }
+    return na;
+}
+
+// Same order / exclusion for any number of slots (only reached with > 96 gated candidates, i.e. noise-like windows in
+// the fused kernel, whose slot list lives in the free FFT buffer): extract the order one element at a time.
+template <int HALF>
+__device__ int order_and_exclude_any(const Slot *slots, int nslot, const float *mags, unsigned char *rec_s, double df,
+                                     int k, int lane) {
+    using P = K3<HALF>;
+    double prev_key = CUDART_INF;
+    int prev_idx = -1, na = 0;
+    while (na < k) {
+        double best = -1.0;
+        int best_idx = 0x7fffffff, best_e = -1;
+        for (int e = lane; e < nslot; e += 32) {
+            if (slots[e].width == 0) continue;
+            const int ix = slots[e].idx;
+            const double r = round_dec4_units((double)mags[P::addr(ix)]);
+            const bool after_prev = r < prev_key || (r == prev_key && ix > prev_idx);
+            if (after_prev && (r > best || (r == best && ix < best_idx))) {
+                best = r;
+                best_idx = ix;
+                best_e = e;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double r = __shfl_xor_sync(0xffffffffu, best, o);
+            const int ix = __shfl_xor_sync(0xffffffffu, best_idx, o);
+            const int e = __shfl_xor_sync(0xffffffffu, best_e, o);
+            if (e >= 0 && (best_e < 0 || r > best || (r == best && ix < best_idx))) {
+                best = r;
+                best_idx = ix;
+                best_e = e;
+            }
+        }
+        if (best_e < 0) break;
+        prev_key = best;
+        prev_idx = best_idx;
+        const float cprom = slots[best_e].prom;
+        const float cmag = mags[P::addr(best_idx)];
+        bool hump = false;
+        for (int a = 0; a < na && !hump; ++a) {
+            const int ja = reinterpret_cast<const int *>(rec_s + 8 + 24 * a)[0];
+            const double cf = round_dec4_d(mul_rn((double)best_idx, df)), af = round_dec4_d(mul_rn((double)ja, df));
+            if (div_rn(fabs(sub_rn(cf, af)), af) < 0.05 && div_rn((double)cprom, div_rn(best, 1e4)) < 0.10) hump = true;
+        }
+        if (!hump) {
+            if (lane == 0) {
+                unsigned char *pk = rec_s + 8 + 24 * na;
+                reinterpret_cast<int *>(pk)[0] = best_idx;
+                reinterpret_cast<int *>(pk)[1] = slots[best_e].width;
+                reinterpret_cast<double *>(pk + 8)[0] = (double)cmag;
+                reinterpret_cast<double *>(pk + 8)[1] = (double)cprom;
+            }
+            ++na;
+            __syncwarp();
+        }
+    }
+    return na;
+}
+
+// Everything after the magnitudes are in shared memory: hot-bin list, picker, record.  Shared by the pipeline kernel
+// (peaks_f32_fast.cu) and the fused window->record kernel (fused_f32.cu).  Runs on ONE warp.
+template <int HALF, bool FLEX>
+__device__ __forceinline__ void k3_tail(float *mags, Slot *slots, const int slot_cap, unsigned char *rec_s,
+                                        int *nslot_ptr, const double sd,
+                                        const float thr_f, const double df, const int k, const int lane,
+                                        const int64_t win, unsigned char *__restrict__ recs, int *__restrict__ repair) {
+    using P = K3<HALF>;
+    constexpr int C = P::C;
+    // ---- phase 2: contiguous chunk per lane: chunk max/min, hot bins -> slot list -------------------------------------
+    float cmax = -CUDART_INF_F, cmin = CUDART_INF_F;
+    {
+        const float4 *ch = reinterpret_cast<const float4 *>(mags + P::addr(C * lane));
+        unsigned hotq = 0;  // bit q: the q-th float4 of this chunk holds a bin above the threshold (C/4 <= 32 groups)
+#pragma unroll
+        for (int q = 0; q < C / 4; ++q) {
+            const float4 v = ch[q];
+            const float m4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+            cmax = fmaxf(cmax, m4);
+            cmin = fminf(cmin, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
+            if (m4 > thr_f) hotq |= 1u << q;
+        }
+        while (hotq) {  // rare: a handful of bins per window
+            const int q = __ffs(hotq) - 1;
+            hotq &= hotq - 1;
+            const float4 v = ch[q];
+            const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (e[u] > thr_f) {
+                    const int j = C * lane + 4 * q + u;
+                    bool take = true;
+                    if (FLEX)  // strict local maximum, candidates j in [1, HALF-2]
+                        take = j >= 1 && j <= HALF - 2 && e[u] > mags[P::addr(j - 1)] && e[u] > mags[P::addr(j + 1)];
+                    if (take) {
+                        const int pos = atomicAdd(&(*nslot_ptr), 1);
+                        if (pos < slot_cap) slots[pos].idx = (uint16_t)j;
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    const int nslot_raw = (*nslot_ptr);
+    if (nslot_raw > slot_cap) {  // more candidates than the on-chip list holds: hand the window to the general kernel
+        if (lane == 0) repair[1 + atomicAdd(&repair[0], 1)] = (int)win;
+        return;
+    }
+    const int nslot = nslot_raw;
+    const int status = 0;
+
+    int na = 0;
+    if (FLEX) {
+        // ---- A: cooperative prominence per candidate -----------------------------------------------------------------
+        for (int c = 0; c < nslot; ++c) {
+            const int j = slots[c].idx;
+            const float prom = coop_prominence<HALF>(mags, j, cmax, cmin, lane);
+            if (lane == 0) slots[c].prom = prom;
+        }
+        __syncwarp();
+        // ---- B: lane-parallel gates (one candidate per lane) ---------------------------------------------------------
+        const double half_sd = mul_rn(0.5, sd);
+        for (int c = lane; c < nslot; c += 32) {
+            const int j = slots[c].idx;
+            const float prom = slots[c].prom;
+            int width = 0;
+            if ((double)prom > half_sd) {
+                const int bins = half_power_bins_f<HALF>(mags, prom, j);
+                const double width_hz = mul_rn((double)bins, df);
+                if (width_hz > 0.0) {
+                    const double fn = mul_rn((double)j, df);
+                    // 0.001 <= 1/(2*(fn/width_hz)) <= 0.07, decided by products unless within 1e-12 of a bound
+                    const double lo_b = 0.002 * fn, hi_b = 0.14 * fn;
+                    if (width_hz >= lo_b * (1.0 + 1e-12) && width_hz <= hi_b * (1.0 - 1e-12)) {
+                        width = bins;
+                    } else if (!(width_hz < lo_b * (1.0 - 1e-12) || width_hz > hi_b * (1.0 + 1e-12))) {
+                        const double q = div_rn(fn, width_hz);
+                        const double damping = div_rn(1.0, mul_rn(2.0, q));
+                        if (0.001 <= damping && damping <= 0.07) width = bins;
+                    }
+                }
+            }
+            slots[c].width = (uint16_t)width;
+        }
+        __syncwarp();
+        // ---- C: order "descending round(mag,4), ascending idx" (stable sort of the reference), greedy hump exclusion ------
+        na = nslot <= 32   ? order_and_exclude<HALF, 1>(slots, nslot, mags, rec_s, df, k, lane)
+             : nslot <= 96 ? order_and_exclude<HALF, 3>(slots, nslot, mags, rec_s, df, k, lane)
+                           : order_and_exclude_any<HALF>(slots, nslot, mags, rec_s, df, k, lane);
+        if (lane == 0) {
+            reinterpret_cast<int *>(rec_s)[0] = na;
+            reinterpret_cast<int *>(rec_s)[1] = status;
+        }
+    } else {
+        // ---- rigid picker on the hot list ---------------------------------------------------------------------------------
+        const double distance = sub_rn(mul_rn(2.0, df), mul_rn(1.0, df));
+        int acc_idx[5];
+#pragma unroll
+        for (int a = 0; a < 5; ++a) acc_idx[a] = -1;
+        __syncwarp();
+        while (na < k) {
+            float bm = -1.f;
+            int bj = -1;
+            for (int e = lane; e < nslot; e += 32) {
+                const int j = slots[e].idx;
+                const float m = mags[P::addr(j)];
+                if (j >= 1 && j <= HALF - 2 && m > thr_f && m > mags[P::addr(j - 1)] && m > mags[P::addr(j + 1)] &&
+                    (m > bm || (m == bm && j < bj))) {
+                    bm = m;
+                    bj = j;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float m2 = __shfl_xor_sync(0xffffffffu, bm, o);
+                const int j2 = __shfl_xor_sync(0xffffffffu, bj, o);
+                if (j2 >= 0 && (bj < 0 || m2 > bm || (m2 == bm && j2 < bj))) {
+                    bm = m2;
+                    bj = j2;
+                }
+            }
+            if (bj < 0) break;
+            const int w2 = half_height_bins_f<HALF>(mags, bj);
+            bool separated = true;
+#pragma unroll
+            for (int a = 0; a < 5; ++a) {
+                if (a < na && separated) {
+                    // an accepted peak's own bin was zeroed when it was found, so its half-height width is 0 (the
+                    // reference's resolution() degenerates to 1.18*dist/w_candidate); walk only if that ever fails
+                    const int w1 = mags[P::addr(acc_idx[a])] == 0.f ? 0 : half_height_bins_f<HALF>(mags, acc_idx[a]);
+                    bool ok = false;
+                    if (w1 + w2 != 0) {
+                        const double num = mul_rn(1.18, (double)abs(bj - acc_idx[a])), den = 1.5 * (double)(w1 + w2);
+                        if (num >= den * (1.0 + 1e-12)) ok = true;                       // rs >= 1.5 by a clear margin
+                        else if (!(num < den * (1.0 - 1e-12))) ok = div_rn(num, (double)(w1 + w2)) >= 1.5;
+                    }
+                    if (!ok) separated = false;
+                }
+            }
+            if (separated) {
+                if (lane == 0) {
+                    unsigned char *pk = rec_s + 8 + 24 * na;
+                    reinterpret_cast<int *>(pk)[0] = bj;
+                    reinterpret_cast<int *>(pk)[1] = w2;
+                    reinterpret_cast<double *>(pk + 8)[0] = (double)bm;
+                }
+#pragma unroll
+                for (int a = 0; a < 5; ++a)
+                    if (a == na) acc_idx[a] = bj;
+                ++na;
+            }
+            // zeroing radius round((freq * 0.02) / (frequencies[2] - frequencies[1])): equals round-half-even(0.02 * idx)
+            // unless that product sits within 1e-6 of a tie; only then (or for a degenerate df) the exact expression runs
+            double reach_d;
+            {
+                const double x02 = 0.02 * (double)bj, fr = x02 - floor(x02);
+                if (df > 1e-300 && df < 1e300 && fabs(fr - 0.5) > 1e-6) {
+                    reach_d = rint(x02);
+                } else {
+                    const double f = mul_rn((double)bj, df);
+                    reach_d = rint(div_rn(mul_rn(f, 0.02), distance));
+                }
+            }
+            if (!(reach_d >= 0.0)) reach_d = 0.0;
+            if (reach_d > (double)HALF) reach_d = (double)HALF;
+            const int reach = (int)reach_d;
+            const int z0 = max(0, bj - reach), z1 = min(HALF, bj + reach + 1);
+            __syncwarp();
+            for (int b = z0 + lane; b < z1; b += 32) mags[P::addr(b)] = 0.f;
+            __syncwarp();
+        }
+        if (lane == 0) {
+            reinterpret_cast<int *>(rec_s)[0] = na;
+            reinterpret_cast<int *>(rec_s)[1] = status;
+        }
+    }
+    __syncwarp();
+    if (lane < 16) {
+        const double2 *s2 = reinterpret_cast<const double2 *>(rec_s);
+        (void)s2;
+        reinterpret_cast<uint64_t *>(recs + win * 128)[lane] = reinterpret_cast<const uint64_t *>(rec_s)[lane];
+    }
+}
+
+}  // namespace

@@ -325,6 +325,33 @@ def run_ours(args):
             note="APDA_CENTER_MEAN is the documented opt-in, legal only when n_samples == N (bins >= 1 do not depend on "
                  "the centring constant; bin 0 is zeroed)")
         variants["picker_" + ("rigid" if flexible else "flexible")] = variant(center, not flexible)
+
+        # leaner variant (SURVEY 8d "never mix"): fused window->record kernel, its own byte accounting B_min = s*N + 128
+        def fused_variant(v_center):
+            def run():
+                an.analyze_fused_device(d_x.data_ptr(), b, n, n, fs, d_rec.data_ptr(), flexible=flexible,
+                                        k=4 if flexible else 5, center=v_center)
+                return gather_records(d_rec, b * world, dst=0) if world > 1 else d_rec
+            for _ in range(3):
+                run()
+            fence()
+            a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(args.steps):
+                run()
+            z.record(stream)
+            fence()
+            vals = torch.tensor([a.elapsed_time(z)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+            ms = float(vals[0]) / args.steps
+            b_min = s_bytes * n + 128
+            return {"value": b * world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "bytes_per_window": b_min,
+                    "achieved_gbs_per_gpu": b_min * b / (ms * 1e-3) / 1e9,
+                    "note": "spectrum never written to HBM; compute-bound, so the HBM fraction is not its yardstick"}
+        if n in (1024, 2048, 4096, 8192):
+            variants["fused_kernel_median"] = fused_variant(_cabi.CENTER_MEDIAN)
+            variants["fused_kernel_mean"] = fused_variant(_cabi.CENTER_MEAN)
         step(False)            # leave the headline configuration's records in d_rec for the checks below
         fence()
 

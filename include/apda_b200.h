@@ -132,6 +132,17 @@ int apda_analyze_f32_host(apda_ctx *ctx, const float *h_samples, int64_t n_sampl
                           int64_t N, int flags, int flexible, double fs, const double *h_fs, int k, int rec_cap,
                           void *h_rec);
 
+/* Fused window -> record kernel (fp32, N in {1024, 2048, 4096, 8192}, k <= 5, rec_cap == 5): same records as
+ * apda_analyze_f32_*, but the spectrum never exists in memory (HBM traffic s*N + 128 bytes per window instead of
+ * 4*s*N + 128).  A throughput variant for fleets that only need the peak tables; the drop-in
+ * start_fft contract stays with the pipeline entry points above. */
+int apda_analyze_fused_f32_dev(apda_ctx *ctx, const float *d_samples, int64_t n_samples, int64_t ld, int64_t batch,
+                               int64_t N, int flags, int flexible, double fs, const double *d_fs, int k, int rec_cap,
+                               void *d_rec);
+int apda_analyze_fused_f32_host(apda_ctx *ctx, const float *h_samples, int64_t n_samples, int64_t ld, int64_t batch,
+                                int64_t N, int flags, int flexible, double fs, const double *h_fs, int k, int rec_cap,
+                                void *h_rec);
+
 /* ---- picker helpers on a magnitude array (module-public functions of the reference) --------------------------
  * utils/get_peak_prominence.py:32-54 calculate_prominence(magnitudes, peak_idx) */
 int apda_prominence_f64_host(apda_ctx *ctx, const double *h_mags, int64_t n, int64_t idx, double *out);

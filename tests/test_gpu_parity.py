@@ -447,3 +447,30 @@ def test_peaks_large_multi_cta_vs_general_and_oracle(an):
         if log2n == 16:
             assert _dicts(an.peaks(spec, 250.0, flexible=True)[0], 250.0, n, True) == c_oracle.peaks_prominence(spec[0], 250.0)
             assert _dicts(an.peaks(spec, 250.0, flexible=False)[0], 250.0, n, False) == c_oracle.peaks_resolution(spec[0], 250.0)
+
+
+@pytest.mark.parametrize("n", [1024, 2048, 4096, 8192])
+def test_fused_kernel_matches_pipeline_and_oracle(n, an):
+    """Fused window->record kernel (no spectrum in memory) vs the two-kernel pipeline and the oracle."""
+    import apda_fft_b200
+    import apda_fft_b200.synth as synth
+    tones = synth.fleet_windows(1200, 96, n, dtype=np.float32)
+    noise = np.stack([synth.noise_window(w, n) for w in range(32)]).astype(np.float32)
+    padded = synth.fleet_windows(5, 16, n, dtype=np.float32)[:, : (3 * n) // 4 + 3]
+    for x, min_same in ((tones, 1.0), (padded, 1.0), (noise, 0.9)):
+        for flexible in (True, False):
+            for center in (apda_fft_b200._cabi.CENTER_MEDIAN, apda_fft_b200._cabi.CENTER_MEAN):
+                if center == apda_fft_b200._cabi.CENTER_MEAN and x.shape[1] != n:
+                    continue
+                fused = an.analyze_fused(x, 125.0, flexible=flexible, center=center)
+                pipe = an.analyze(x, 125.0, flexible=flexible, center=center)
+                assert (fused["status"] == 0).all()
+                same = [(fused[w]["count"] == pipe[w]["count"]) and (fused[w]["pk"]["idx"] == pipe[w]["pk"]["idx"]).all()
+                        for w in range(x.shape[0])]
+                assert np.mean(same) >= min_same, (n, flexible, center, np.mean(same))
+                live = (pipe["pk"]["idx"] >= 0) & (fused["pk"]["idx"] == pipe["pk"]["idx"])
+                assert np.allclose(fused["pk"]["mag"][live], pipe["pk"]["mag"][live], rtol=2e-6)
+    want = c_oracle.start_fft_batch(tones[:8].astype(np.float64))
+    got = an.analyze_fused(tones[:8], 125.0, flexible=True)
+    for w in range(8):
+        assert [p["idx"] for p in _dicts(got[w], 125.0, n, True)] == [p["idx"] for p in c_oracle.peaks_prominence(want[w], 125.0)]
