@@ -103,6 +103,36 @@ class Analyzer:
         self.ctx.call("apda_analyze_fused_f32_dev", _p(d_samples), n_samples, ld or n_samples, batch, n_fft, center,
                       int(bool(flexible)), float(fs), _p(d_fs), k, 5, _p(d_rec))
 
+    # ---- wire-format ingest (16-bit samples, high byte first) ----------------------------------------------------------
+    def decode_wire16(self, payload: np.ndarray, first_value) -> tuple[np.ndarray, np.ndarray]:
+        """uint8[B, 2*n] payload rows + baseline per window -> (float64[B, n] compacted samples, int32[B] counts)."""
+        pay = np.ascontiguousarray(np.atleast_2d(payload), dtype=np.uint8)
+        b, nb = pay.shape
+        n = nb // 2
+        fv = np.ascontiguousarray(np.broadcast_to(np.asarray(first_value, dtype=np.float64), (b,)))
+        out = np.zeros((b, n), dtype=np.float64)
+        nv = np.zeros(b, dtype=np.int32)
+        self.ctx.call("apda_decode_wire16_f64_host", _p(pay.ctypes.data), n, nb, b, _p(fv.ctypes.data), _p(out.ctypes.data),
+                      _p(nv.ctypes.data))
+        return out, nv
+
+    def analyze_wire16(self, payload: np.ndarray, first_value, fs, n_fft: int | None = None, dtype: str = "f64",
+                       flexible: bool = True, k: int | None = None) -> np.ndarray:
+        """uint8[B, 2*n] payload rows -> records[B] (decode, drop non-finite, centre, FFT, pick; all on the device)."""
+        pay = np.ascontiguousarray(np.atleast_2d(payload), dtype=np.uint8)
+        b, nb = pay.shape
+        n = nb // 2
+        nfft = next_pow2(n) if n_fft is None else int(n_fft)
+        fv = np.ascontiguousarray(np.broadcast_to(np.asarray(first_value, dtype=np.float64), (b,)))
+        k = (4 if flexible else 5) if k is None else int(k)
+        cap = max(5, k)
+        recs = np.zeros(b, dtype=record_dtype(cap))
+        fs_scalar, fs_arr = self._fs(fs, b)
+        self.ctx.call(f"apda_analyze_wire16_{dtype}_host", _p(pay.ctypes.data), n, nb, b, _p(fv.ctypes.data), nfft,
+                      _cabi.CENTER_MEDIAN, int(bool(flexible)), fs_scalar,
+                      _p(fs_arr.ctypes.data if fs_arr is not None else 0), k, cap, _p(recs.ctypes.data))
+        return recs
+
     def analyze_host_ptr(self, h_ptr: int, batch: int, n_samples: int, n_fft: int, dtype: str, fs: float,
                          h_rec_ptr: int, flexible: bool = True, k: int = 4, rec_cap: int = 5,
                          center: int = _cabi.CENTER_MEDIAN) -> None:

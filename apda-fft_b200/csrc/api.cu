@@ -102,6 +102,7 @@ extern "C" int apda_ctx_destroy(apda_ctx *ctx) {
     cudaFree(ctx->ws);
     cudaFree(ctx->ws_small);
     cudaFree(ctx->repair);
+    cudaFree(ctx->ragged);
     for (auto &kv : ctx->stream_scratch) cudaFree(kv.second.first);
     for (int i = 0; i < 2; ++i) {
         cudaFree(ctx->ws_pipe[i]);
@@ -275,6 +276,99 @@ static int peaks_dispatch(apda_ctx *ctx, cudaStream_t st, const T *d_spec, int64
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 // ---------------------------------------------------------------------------------------------------------------
+// ragged batches: per-window sample counts (windows that lost samples to inf/nan filtering, text logs of different
+// lengths).  Windows with the common length n_max run on the specialised kernels; the others are listed on the device
+// and go through the general kernel with their own length.  No host synchronisation anywhere.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void ragged_list_kernel(const int *__restrict__ nv, int64_t batch, int n_max, int *__restrict__ list) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < batch && nv[w] != n_max) list[1 + atomicAdd(&list[0], 1)] = (int)w;
+}
+
+// record status of ragged windows: bit 2 = the window's own padded length differs from the batch N (the reference would
+// transform at that other length), bit 3 = empty window (the reference's pickers raise StatisticsError on start_fft([]))
+__global__ void ragged_status_kernel(const int *__restrict__ list, const int *__restrict__ nv, int64_t N,
+                                     unsigned char *__restrict__ recs, int64_t rec_bytes) {
+    for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < list[0]; it += gridDim.x * blockDim.x) {
+        const int w = list[1 + it];
+        const int n = nv[w];
+        int64_t p = 1;
+        while (p < n) p <<= 1;
+        int *hdr = reinterpret_cast<int *>(recs + (int64_t)w * rec_bytes);
+        if (n <= 0) {
+            hdr[0] = 0;
+            hdr[1] |= 8;
+        } else if (p != N) {
+            hdr[1] |= 4;
+        }
+    }
+}
+
+static int reserve_ragged(apda_ctx *ctx, cudaStream_t st, int64_t batch) {
+    const size_t need = ((size_t)batch + 1) * sizeof(int);
+    if (need > ctx->ragged_bytes) {
+        APDA_CUDA(cudaStreamSynchronize(st));
+        APDA_TRY(apda_reserve((void **)&ctx->ragged, &ctx->ragged_bytes, need));
+    }
+    return APDA_OK;
+}
+
+template <typename T>
+static int fft_dispatch_ragged(apda_ctx *ctx, cudaStream_t st, const T *d_samples, const int *d_nv, int64_t n_max,
+                               int64_t ld, int64_t batch, int64_t N, int flags, T *d_spec) {
+    if (batch == 0) return APDA_OK;
+    if (N > fft_smem_max_n<T>(ctx)) {
+        apda_set_error("ragged batches are offered for N <= %lld", (long long)fft_smem_max_n<T>(ctx));
+        return APDA_ERR_UNSUPPORTED;
+    }
+    if (flags == APDA_CENTER_MEAN) {
+        apda_set_error("ragged batches need the exact median (padding): APDA_CENTER_MEAN is not legal");
+        return APDA_ERR_INVALID;
+    }
+    const bool fast32 = sizeof(T) == 4 && !ctx->generic_only && fft_f32_fast_supports(N);
+    const bool fast64 = sizeof(T) == 8 && !ctx->generic_only && fft_f64_fast_supports(N);
+    if (!fast32 && !fast64)
+        return launch_fft_smem<T>(ctx, st, d_samples, n_max, ld, batch, N, flags, d_spec, false, d_nv, nullptr);
+    APDA_TRY(reserve_ragged(ctx, st, batch));
+    APDA_CUDA(cudaMemsetAsync(ctx->ragged, 0, sizeof(int), st));
+    ragged_list_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, st>>>(d_nv, batch, (int)n_max, ctx->ragged);
+    ctx->launches++;
+    if (fast32)
+        APDA_TRY(launch_fft_f32_fast(ctx, st, reinterpret_cast<const float *>(d_samples), n_max, ld, batch, N, flags,
+                                     reinterpret_cast<float *>(d_spec), d_nv));
+    else
+        APDA_TRY(launch_fft_f64_fast(ctx, st, reinterpret_cast<const double *>(d_samples), n_max, ld, batch, N, flags,
+                                     reinterpret_cast<double *>(d_spec), d_nv));
+    return launch_fft_smem<T>(ctx, st, d_samples, n_max, ld, batch, N, flags, d_spec, false, d_nv, ctx->ragged);
+}
+
+static int check_ragged_args(apda_ctx *ctx, const void *in, const void *nv, int64_t n_max, int64_t ld, int64_t batch,
+                             int64_t N, int flags, const void *out) {
+    if (!nv) {
+        apda_set_error("ragged: n_valid array is NULL");
+        return APDA_ERR_INVALID;
+    }
+    return check_fft_args(ctx, in, n_max, ld, batch, N, flags, out);
+}
+
+template <typename T>
+static int analyze_ragged_dev(apda_ctx *ctx, cudaStream_t st, const T *d_samples, const int *d_nv, int64_t n_max, int64_t ld,
+                              int64_t batch, int64_t N, int flags, int flexible, double fs, const double *d_fs, int k,
+                              int rec_cap, T *d_spec, void *d_rec, void **ws, size_t *ws_bytes, size_t ws_off) {
+    APDA_TRY(fft_dispatch_ragged<T>(ctx, st, d_samples, d_nv, n_max, ld, batch, N, flags, d_spec));
+    APDA_TRY(peaks_dispatch<T>(ctx, st, d_spec, N, batch, fs, d_fs, k, rec_cap, flexible, d_rec, ws, ws_bytes, ws_off));
+    if (batch > 0 && ctx->ragged && ((sizeof(T) == 4 && !ctx->generic_only && fft_f32_fast_supports(N)) ||
+                                     (sizeof(T) == 8 && !ctx->generic_only && fft_f64_fast_supports(N)))) {
+        ragged_status_kernel<<<64, 256, 0, st>>>(ctx->ragged, d_nv, N, reinterpret_cast<unsigned char *>(d_rec),
+                                                 APDA_REC_BYTES(rec_cap));
+        ctx->launches++;
+        APDA_CUDA(cudaGetLastError());
+    }
+    return APDA_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
 // device-pointer entry points
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T>
@@ -352,6 +446,52 @@ extern "C" int apda_analyze_f32_dev(apda_ctx *ctx, const float *d_samples, int64
                                     int rec_cap, float *d_spec_ws, void *d_rec) {
     return analyze_dev<float>(ctx, d_samples, n_samples, ld, batch, N, flags, flexible, fs, d_fs, k, rec_cap, d_spec_ws,
                               d_rec);
+}
+
+template <typename T>
+static int fft_ragged_dev(apda_ctx *ctx, const T *d_samples, const int32_t *d_nv, int64_t n_max, int64_t ld, int64_t batch,
+                          int64_t N, int flags, T *d_spec) {
+    APDA_TRY(check_ragged_args(ctx, d_samples, d_nv, n_max, ld, batch, N, flags, d_spec));
+    APDA_CUDA(cudaSetDevice(ctx->device));
+    return fft_dispatch_ragged<T>(ctx, ctx->stream, d_samples, d_nv, n_max, ld, batch, N, flags, d_spec);
+}
+extern "C" int apda_fft_ragged_f64_dev(apda_ctx *ctx, const double *d_samples, const int32_t *d_n_valid, int64_t n_max,
+                                       int64_t ld, int64_t batch, int64_t N, int flags, double *d_spec) {
+    return fft_ragged_dev<double>(ctx, d_samples, d_n_valid, n_max, ld, batch, N, flags, d_spec);
+}
+extern "C" int apda_fft_ragged_f32_dev(apda_ctx *ctx, const float *d_samples, const int32_t *d_n_valid, int64_t n_max,
+                                       int64_t ld, int64_t batch, int64_t N, int flags, float *d_spec) {
+    return fft_ragged_dev<float>(ctx, d_samples, d_n_valid, n_max, ld, batch, N, flags, d_spec);
+}
+
+template <typename T>
+static int analyze_ragged_entry(apda_ctx *ctx, const T *d_samples, const int32_t *d_nv, int64_t n_max, int64_t ld,
+                                int64_t batch, int64_t N, int flags, int flexible, double fs, const double *d_fs, int k,
+                                int rec_cap, T *d_spec_ws, void *d_rec) {
+    APDA_TRY(check_ragged_args(ctx, d_samples, d_nv, n_max, ld, batch, N, flags, d_rec));
+    APDA_TRY(check_peaks_args(ctx, d_samples, N, batch, k, rec_cap, d_rec));
+    APDA_CUDA(cudaSetDevice(ctx->device));
+    const size_t spec_bytes = d_spec_ws ? 0 : align256((size_t)batch * (size_t)N * 2 * sizeof(T));
+    const size_t mag_bytes = peaks_mag_workspace_bytes<T>(ctx, N, batch);
+    if (spec_bytes + mag_bytes > ctx->ws_bytes) {
+        APDA_CUDA(cudaStreamSynchronize(ctx->stream));
+        APDA_TRY(apda_reserve(&ctx->ws, &ctx->ws_bytes, spec_bytes + mag_bytes));
+    }
+    T *spec = d_spec_ws ? d_spec_ws : reinterpret_cast<T *>(ctx->ws);
+    return analyze_ragged_dev<T>(ctx, ctx->stream, d_samples, d_nv, n_max, ld, batch, N, flags, flexible, fs, d_fs, k, rec_cap,
+                                 spec, d_rec, &ctx->ws, &ctx->ws_bytes, spec_bytes);
+}
+extern "C" int apda_analyze_ragged_f64_dev(apda_ctx *ctx, const double *d_samples, const int32_t *d_n_valid, int64_t n_max,
+                                           int64_t ld, int64_t batch, int64_t N, int flags, int flexible, double fs,
+                                           const double *d_fs, int k, int rec_cap, double *d_spec_ws, void *d_rec) {
+    return analyze_ragged_entry<double>(ctx, d_samples, d_n_valid, n_max, ld, batch, N, flags, flexible, fs, d_fs, k, rec_cap,
+                                        d_spec_ws, d_rec);
+}
+extern "C" int apda_analyze_ragged_f32_dev(apda_ctx *ctx, const float *d_samples, const int32_t *d_n_valid, int64_t n_max,
+                                           int64_t ld, int64_t batch, int64_t N, int flags, int flexible, double fs,
+                                           const double *d_fs, int k, int rec_cap, float *d_spec_ws, void *d_rec) {
+    return analyze_ragged_entry<float>(ctx, d_samples, d_n_valid, n_max, ld, batch, N, flags, flexible, fs, d_fs, k, rec_cap,
+                                       d_spec_ws, d_rec);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -534,6 +674,148 @@ extern "C" int apda_analyze_fused_f32_host(apda_ctx *ctx, const float *h_samples
     APDA_TRY(check_fused_args(N, flags, k, rec_cap));
     return host_pipeline<float>(ctx, kFused, h_samples, n_samples, ld, batch, N, flags, flexible, fs, h_fs, k, rec_cap, false,
                                 nullptr, h_rec);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// wire-format ingest: 2 bytes per sample over PCIe instead of 4/8
+// ---------------------------------------------------------------------------------------------------------------
+static int check_wire_args(apda_ctx *ctx, const void *payload, const void *fv, int64_t n_max, int64_t ld_bytes,
+                           int64_t batch, const void *out) {
+    if (!ctx || !payload || !fv || !out || n_max < 1 || n_max > (int64_t(1) << 24) || ld_bytes < 2 * n_max || batch < 0 ||
+        batch > 0x7fffffff) {
+        apda_set_error("wire16: bad arguments (need payload, first_value, out, 1 <= n_max, ld_bytes >= 2*n_max)");
+        return APDA_ERR_INVALID;
+    }
+    return APDA_OK;
+}
+
+template <typename T>
+static int decode_wire16_dev(apda_ctx *ctx, const uint8_t *d_payload, int64_t n_max, int64_t ld_bytes, int64_t batch,
+                             const double *d_first_value, T *d_samples, int64_t ld_out, int32_t *d_n_valid) {
+    APDA_TRY(check_wire_args(ctx, d_payload, d_first_value, n_max, ld_bytes, batch, d_samples));
+    if (!d_n_valid || ld_out < n_max) {
+        apda_set_error("wire16: n_valid is NULL or ld_out < n_max");
+        return APDA_ERR_INVALID;
+    }
+    APDA_CUDA(cudaSetDevice(ctx->device));
+    return launch_decode_wire16<T>(ctx, ctx->stream, d_payload, n_max, ld_bytes, batch, d_first_value, d_samples, ld_out,
+                                   d_n_valid);
+}
+extern "C" int apda_decode_wire16_f64_dev(apda_ctx *ctx, const uint8_t *d_payload, int64_t n_max, int64_t ld_bytes,
+                                          int64_t batch, const double *d_first_value, double *d_samples, int64_t ld_out,
+                                          int32_t *d_n_valid) {
+    return decode_wire16_dev<double>(ctx, d_payload, n_max, ld_bytes, batch, d_first_value, d_samples, ld_out, d_n_valid);
+}
+extern "C" int apda_decode_wire16_f32_dev(apda_ctx *ctx, const uint8_t *d_payload, int64_t n_max, int64_t ld_bytes,
+                                          int64_t batch, const double *d_first_value, float *d_samples, int64_t ld_out,
+                                          int32_t *d_n_valid) {
+    return decode_wire16_dev<float>(ctx, d_payload, n_max, ld_bytes, batch, d_first_value, d_samples, ld_out, d_n_valid);
+}
+
+// host payload -> (optionally) host samples and/or host records; chunked over the two pipeline streams
+template <typename T>
+static int wire16_host(apda_ctx *ctx, const uint8_t *h_payload, int64_t n_max, int64_t ld_bytes, int64_t batch,
+                       const double *h_first_value, T *h_samples_out, int32_t *h_n_valid_out, bool analyze, int64_t N,
+                       int flags, int flexible, double fs, const double *h_fs, int k, int rec_cap, void *h_rec) {
+    APDA_CUDA(cudaSetDevice(ctx->device));
+    if (batch == 0) return APDA_OK;
+    const size_t rec_bytes = (size_t)APDA_REC_BYTES(rec_cap);
+    const size_t per_window = analyze ? (size_t)N * 2 * sizeof(T) : (size_t)n_max * sizeof(T);
+    int64_t chunk = std::max<int64_t>(1, (int64_t)((96u << 20) / per_window));
+    chunk = std::min<int64_t>(chunk, batch);
+    if (batch > chunk && batch < 2 * chunk) chunk = (batch + 1) / 2;
+    const size_t pay_b = align256(chunk * (size_t)n_max * 2), fv_b = align256(chunk * sizeof(double));
+    const size_t smp_b = align256(chunk * (size_t)n_max * sizeof(T)), nv_b = align256(chunk * sizeof(int));
+    const size_t spec_b = analyze ? align256(chunk * (size_t)N * 2 * sizeof(T)) : 0;
+    const size_t recs_b = analyze ? align256(chunk * rec_bytes) : 0;
+    const size_t fs_b = (analyze && h_fs) ? align256(chunk * sizeof(double)) : 0;
+    const size_t mag_b = analyze ? align256(peaks_mag_workspace_bytes<T>(ctx, N, chunk)) : 0;
+    const size_t total = pay_b + fv_b + smp_b + nv_b + spec_b + recs_b + fs_b + mag_b;
+    for (int s = 0; s < 2; ++s) {
+        if (total > ctx->ws_pipe_bytes[s]) {
+            APDA_CUDA(cudaStreamSynchronize(ctx->pipe[s]));
+            APDA_TRY(apda_reserve(&ctx->ws_pipe[s], &ctx->ws_pipe_bytes[s], total));
+        }
+        if (batch <= chunk) break;
+    }
+    int status = APDA_OK;
+    int64_t done = 0;
+    for (int c = 0; done < batch && status == APDA_OK; ++c) {
+        const int s = c & 1;
+        cudaStream_t st = ctx->pipe[s];
+        const int64_t cnt = std::min<int64_t>(chunk, batch - done);
+        char *base = (char *)ctx->ws_pipe[s];
+        unsigned char *d_pay = (unsigned char *)base;
+        double *d_fv = (double *)(base + pay_b);
+        T *d_smp = (T *)(base + pay_b + fv_b);
+        int *d_nv = (int *)(base + pay_b + fv_b + smp_b);
+        T *d_spec = (T *)(base + pay_b + fv_b + smp_b + nv_b);
+        void *d_rec = base + pay_b + fv_b + smp_b + nv_b + spec_b;
+        double *d_fs = fs_b ? (double *)(base + pay_b + fv_b + smp_b + nv_b + spec_b + recs_b) : nullptr;
+        void *mag_ws = mag_b ? base + pay_b + fv_b + smp_b + nv_b + spec_b + recs_b + fs_b : nullptr;
+        size_t mag_have = mag_b;
+        if (ld_bytes == 2 * n_max)
+            APDA_CUDA(cudaMemcpyAsync(d_pay, h_payload + (size_t)done * ld_bytes, cnt * (size_t)n_max * 2,
+                                      cudaMemcpyHostToDevice, st));
+        else
+            APDA_CUDA(cudaMemcpy2DAsync(d_pay, (size_t)n_max * 2, h_payload + (size_t)done * ld_bytes, ld_bytes,
+                                        (size_t)n_max * 2, cnt, cudaMemcpyHostToDevice, st));
+        APDA_CUDA(cudaMemcpyAsync(d_fv, h_first_value + done, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+        if (d_fs) APDA_CUDA(cudaMemcpyAsync(d_fs, h_fs + done, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+        status = launch_decode_wire16<T>(ctx, st, d_pay, n_max, (int64_t)n_max * 2, cnt, d_fv, d_smp, n_max, d_nv);
+        if (status != APDA_OK) break;
+        if (h_samples_out)
+            APDA_CUDA(cudaMemcpyAsync(h_samples_out + (size_t)done * n_max, d_smp, cnt * (size_t)n_max * sizeof(T),
+                                      cudaMemcpyDeviceToHost, st));
+        if (h_n_valid_out)
+            APDA_CUDA(cudaMemcpyAsync(h_n_valid_out + done, d_nv, cnt * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (analyze) {
+            status = analyze_ragged_dev<T>(ctx, st, d_smp, d_nv, n_max, n_max, cnt, N, flags, flexible, fs, d_fs, k, rec_cap,
+                                           d_spec, d_rec, &mag_ws, &mag_have, 0);
+            if (status == APDA_OK)
+                APDA_CUDA(cudaMemcpyAsync((char *)h_rec + (size_t)done * rec_bytes, d_rec, cnt * rec_bytes,
+                                          cudaMemcpyDeviceToHost, st));
+        }
+        done += cnt;
+    }
+    cudaError_t e0 = cudaStreamSynchronize(ctx->pipe[0]);
+    cudaError_t e1 = cudaStreamSynchronize(ctx->pipe[1]);
+    if (status != APDA_OK) return status;
+    if (e0 != cudaSuccess) return apda_cuda_fail(e0, "wire16 pipeline (stream 0)");
+    if (e1 != cudaSuccess) return apda_cuda_fail(e1, "wire16 pipeline (stream 1)");
+    return APDA_OK;
+}
+
+extern "C" int apda_decode_wire16_f64_host(apda_ctx *ctx, const uint8_t *h_payload, int64_t n_max, int64_t ld_bytes,
+                                           int64_t batch, const double *h_first_value, double *h_samples,
+                                           int32_t *h_n_valid) {
+    APDA_TRY(check_wire_args(ctx, h_payload, h_first_value, n_max, ld_bytes, batch, h_samples));
+    return wire16_host<double>(ctx, h_payload, n_max, ld_bytes, batch, h_first_value, h_samples, h_n_valid, false, 0, 0, 0,
+                               0.0, nullptr, 1, 5, nullptr);
+}
+template <typename T>
+static int analyze_wire16_host(apda_ctx *ctx, const uint8_t *h_payload, int64_t n_max, int64_t ld_bytes, int64_t batch,
+                               const double *h_first_value, int64_t N, int flags, int flexible, double fs,
+                               const double *h_fs, int k, int rec_cap, void *h_rec) {
+    APDA_TRY(check_wire_args(ctx, h_payload, h_first_value, n_max, ld_bytes, batch, h_rec));
+    APDA_TRY(check_fft_args(ctx, h_payload, n_max, n_max, batch, N, flags, h_rec));
+    APDA_TRY(check_peaks_args(ctx, h_payload, N, batch, k, rec_cap, h_rec));
+    return wire16_host<T>(ctx, h_payload, n_max, ld_bytes, batch, h_first_value, nullptr, nullptr, true, N, flags, flexible, fs,
+                          h_fs, k, rec_cap, h_rec);
+}
+extern "C" int apda_analyze_wire16_f64_host(apda_ctx *ctx, const uint8_t *h_payload, int64_t n_max, int64_t ld_bytes,
+                                            int64_t batch, const double *h_first_value, int64_t N, int flags,
+                                            int flexible, double fs, const double *h_fs, int k, int rec_cap,
+                                            void *h_rec) {
+    return analyze_wire16_host<double>(ctx, h_payload, n_max, ld_bytes, batch, h_first_value, N, flags, flexible, fs, h_fs, k,
+                                       rec_cap, h_rec);
+}
+extern "C" int apda_analyze_wire16_f32_host(apda_ctx *ctx, const uint8_t *h_payload, int64_t n_max, int64_t ld_bytes,
+                                            int64_t batch, const double *h_first_value, int64_t N, int flags,
+                                            int flexible, double fs, const double *h_fs, int k, int rec_cap,
+                                            void *h_rec) {
+    return analyze_wire16_host<float>(ctx, h_payload, n_max, ld_bytes, batch, h_first_value, N, flags, flexible, fs, h_fs, k,
+                                      rec_cap, h_rec);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

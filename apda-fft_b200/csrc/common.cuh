@@ -36,6 +36,8 @@ struct apda_ctx {
     size_t ws_small_bytes = 0;
     int64_t launches = 0;
     std::map<cudaStream_t, std::pair<void *, size_t>> stream_scratch;  // K2 median state, one per stream
+    int *ragged = nullptr;  // ragged batches: windows whose length differs from the batch's common length
+    size_t ragged_bytes = 0;
     int *repair = nullptr;  // K3 fast path: windows handed over to the general kernel
     size_t repair_bytes = 0;
     int generic_only = 0;  // debug/test switch: bypass the specialised fp32 kernels
@@ -67,7 +69,8 @@ static inline bool is_pow2_i64(int64_t v) { return v > 0 && (v & (v - 1)) == 0; 
 // launchers implemented in the kernel translation units
 template <typename T>
 int launch_fft_smem(apda_ctx *ctx, cudaStream_t st, const T *d_samples, int64_t n_samples, int64_t ld, int64_t batch,
-                    int64_t N, int flags, T *d_spec, bool complex_input);
+                    int64_t N, int flags, T *d_spec, bool complex_input, const int *d_nv = nullptr,
+                    const int *d_list = nullptr);
 template <typename T>
 int launch_fft_large(apda_ctx *ctx, cudaStream_t st, const T *d_samples, int64_t n_samples, int64_t ld, int64_t batch,
                      int64_t N, int flags, T *d_spec, bool complex_input);
@@ -83,13 +86,16 @@ template <typename T>
 int64_t fft_smem_max_n(apda_ctx *ctx);
 bool fft_f32_fast_supports(int64_t N);
 int launch_fft_f32_fast(apda_ctx *ctx, cudaStream_t st, const float *d_samples, int64_t n_samples, int64_t ld,
-                        int64_t batch, int64_t N, int flags, float *d_spec);
+                        int64_t batch, int64_t N, int flags, float *d_spec, const int *d_nv = nullptr);
 void fft_f32_fast_release(apda_ctx *ctx);
 int launch_fused_f32(apda_ctx *ctx, cudaStream_t st, const float *d_samples, int64_t n_samples, int64_t ld, int64_t batch,
                      int64_t N, int flags, int flexible, double fs, const double *d_fs, int k, void *d_rec);
+template <typename T>
+int launch_decode_wire16(apda_ctx *ctx, cudaStream_t st, const unsigned char *d_payload, int64_t n_max, int64_t ld_bytes,
+                         int64_t batch, const double *d_first_value, T *d_samples, int64_t ld_out, int *d_n_valid);
 bool fft_f64_fast_supports(int64_t N);
 int launch_fft_f64_fast(apda_ctx *ctx, cudaStream_t st, const double *d_samples, int64_t n_samples, int64_t ld,
-                        int64_t batch, int64_t N, int flags, double *d_spec);
+                        int64_t batch, int64_t N, int flags, double *d_spec, const int *d_nv = nullptr);
 bool peaks_f32_fast_supports(int64_t n, int k, int rec_cap);
 bool peaks_large_supports(int64_t n);
 template <typename T>

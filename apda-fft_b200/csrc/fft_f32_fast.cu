@@ -8,7 +8,7 @@ __global__ void __launch_bounds__(Plan<N>::WPB *(N / 32))
 fft_f32_fast_kernel(const float *__restrict__ samples, int n_samples, int64_t ld, int64_t batch,
                     const float2 *__restrict__ tw1,  // [R1][S1]: W_M^{c*k1}
                     const float2 *__restrict__ twu,  // [M]: -i/2 * W_N^k
-                    float2 *__restrict__ spec) {
+                    float2 *__restrict__ spec, const int *__restrict__ nv) {
     constexpr int center = CENTER;
     using P = Plan<N>;
     constexpr int M = N / 2, R1 = P::R1, R2 = P::R2, R3 = P::R3, T = M / 16, WPB = P::WPB;
@@ -24,6 +24,7 @@ fft_f32_fast_kernel(const float *__restrict__ samples, int n_samples, int64_t ld
     const int t = threadIdx.x % T;
     const int64_t win = (int64_t)blockIdx.x * WPB + wslot;
     if (win >= batch) return;  // windows synchronise on their own named barrier, so a dead slot can leave
+    if (nv && nv[win] != n_samples) return;  // ragged batch: windows of another length go to the general kernel
     const int64_t winc = win;
     float2 *s = sm[wslot];
 
@@ -109,7 +110,7 @@ static int fast_tables(apda_ctx *ctx, FastTables *out) {
 
 template <int N>
 static int launch_fast_n(apda_ctx *ctx, cudaStream_t st, const float *d_samples, int64_t n_samples, int64_t ld,
-                         int64_t batch, int flags, float *d_spec) {
+                         int64_t batch, int flags, float *d_spec, const int *d_nv) {
     using P = Plan<N>;
     FastTables ft;
     APDA_TRY(fast_tables<N>(ctx, &ft));
@@ -122,7 +123,7 @@ static int launch_fast_n(apda_ctx *ctx, cudaStream_t st, const float *d_samples,
                     ? (full ? fft_f32_fast_kernel<N, APDA_CENTER_MEAN, true> : fft_f32_fast_kernel<N, APDA_CENTER_MEAN, false>)
                     : (full ? fft_f32_fast_kernel<N, APDA_CENTER_NONE, true> : fft_f32_fast_kernel<N, APDA_CENTER_NONE, false>);
     kern<<<(unsigned)blocks, threads, 0, st>>>(d_samples, (int)n_samples, ld, batch, ft.tw1, ft.twu,
-                                               reinterpret_cast<float2 *>(d_spec));
+                                               reinterpret_cast<float2 *>(d_spec), d_nv);
     ctx->launches++;
     APDA_CUDA(cudaGetLastError());
     return APDA_OK;
@@ -146,12 +147,12 @@ int fft_f32_fast_get_tables(apda_ctx *ctx, int64_t N, const float2 **tw1, const 
 bool fft_f32_fast_supports(int64_t N) { return N == 1024 || N == 2048 || N == 4096 || N == 8192; }
 
 int launch_fft_f32_fast(apda_ctx *ctx, cudaStream_t st, const float *d_samples, int64_t n_samples, int64_t ld,
-                        int64_t batch, int64_t N, int flags, float *d_spec) {
+                        int64_t batch, int64_t N, int flags, float *d_spec, const int *d_nv) {
     switch (N) {
-        case 1024: return launch_fast_n<1024>(ctx, st, d_samples, n_samples, ld, batch, flags, d_spec);
-        case 2048: return launch_fast_n<2048>(ctx, st, d_samples, n_samples, ld, batch, flags, d_spec);
-        case 4096: return launch_fast_n<4096>(ctx, st, d_samples, n_samples, ld, batch, flags, d_spec);
-        case 8192: return launch_fast_n<8192>(ctx, st, d_samples, n_samples, ld, batch, flags, d_spec);
+        case 1024: return launch_fast_n<1024>(ctx, st, d_samples, n_samples, ld, batch, flags, d_spec, d_nv);
+        case 2048: return launch_fast_n<2048>(ctx, st, d_samples, n_samples, ld, batch, flags, d_spec, d_nv);
+        case 4096: return launch_fast_n<4096>(ctx, st, d_samples, n_samples, ld, batch, flags, d_spec, d_nv);
+        case 8192: return launch_fast_n<8192>(ctx, st, d_samples, n_samples, ld, batch, flags, d_spec, d_nv);
     }
     apda_set_error("fft_f32_fast: unsupported N=%lld", (long long)N);
     return APDA_ERR_UNSUPPORTED;

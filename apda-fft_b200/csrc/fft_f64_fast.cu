@@ -226,7 +226,7 @@ __device__ __forceinline__ void middle_or_last_pass(double2 *s, const double2 *_
 template <int LOGN>
 __global__ void __launch_bounds__(Plan64<LOGN>::T, (LOGN <= 12 ? 768 / Plan64<LOGN>::T : 1))
 fft_f64_fast_kernel(const double *__restrict__ samples, int n_samples, int64_t ld, const double2 *__restrict__ tw,
-                    double2 *__restrict__ spec, int center) {
+                    double2 *__restrict__ spec, int center, const int *__restrict__ nv) {
     using PL = Plan64<LOGN>;
     constexpr int N = PL::N, T = PL::T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -235,6 +235,7 @@ fft_f64_fast_kernel(const double *__restrict__ samples, int n_samples, int64_t l
     double *raw = reinterpret_cast<double *>(smem_raw);  // staging of the real samples (padded by i>>3), aliases s
     const int t = threadIdx.x;
     const int64_t win = blockIdx.x;
+    if (nv && nv[win] != n_samples) return;  // ragged batch: windows of another length go to the general kernel
     const double *x = samples + win * ld;
 
     {   // streaming loads (L1 is kept for the twiddle table); all 16 loads of a thread are issued before the first store,
@@ -285,12 +286,12 @@ fft_f64_fast_kernel(const double *__restrict__ samples, int n_samples, int64_t l
 
 template <int LOGN>
 int launch_n(apda_ctx *ctx, cudaStream_t st, const double *d_samples, int64_t n_samples, int64_t ld, int64_t batch,
-             int flags, const double2 *tw, double *d_spec) {
+             int flags, const double2 *tw, double *d_spec, const int *d_nv) {
     using PL = Plan64<LOGN>;
     const size_t smem = (size_t)PL::SM_ELEMS * sizeof(double2);
     APDA_CUDA(cudaFuncSetAttribute(fft_f64_fast_kernel<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fft_f64_fast_kernel<LOGN><<<(unsigned)batch, PL::T, smem, st>>>(d_samples, (int)n_samples, ld, tw,
-                                                                   reinterpret_cast<double2 *>(d_spec), flags);
+                                                                   reinterpret_cast<double2 *>(d_spec), flags, d_nv);
     ctx->launches++;
     APDA_CUDA(cudaGetLastError());
     return APDA_OK;
@@ -301,14 +302,14 @@ int launch_n(apda_ctx *ctx, cudaStream_t st, const double *d_samples, int64_t n_
 bool fft_f64_fast_supports(int64_t N) { return N == 1024 || N == 2048 || N == 4096 || N == 8192; }
 
 int launch_fft_f64_fast(apda_ctx *ctx, cudaStream_t st, const double *d_samples, int64_t n_samples, int64_t ld,
-                        int64_t batch, int64_t N, int flags, double *d_spec) {
+                        int64_t batch, int64_t N, int flags, double *d_spec, const int *d_nv) {
     TwiddleTables tw;
     APDA_TRY(apda_get_twiddles(ctx, N, &tw));
     switch (N) {
-        case 1024: return launch_n<10>(ctx, st, d_samples, n_samples, ld, batch, flags, tw.d64, d_spec);
-        case 2048: return launch_n<11>(ctx, st, d_samples, n_samples, ld, batch, flags, tw.d64, d_spec);
-        case 4096: return launch_n<12>(ctx, st, d_samples, n_samples, ld, batch, flags, tw.d64, d_spec);
-        case 8192: return launch_n<13>(ctx, st, d_samples, n_samples, ld, batch, flags, tw.d64, d_spec);
+        case 1024: return launch_n<10>(ctx, st, d_samples, n_samples, ld, batch, flags, tw.d64, d_spec, d_nv);
+        case 2048: return launch_n<11>(ctx, st, d_samples, n_samples, ld, batch, flags, tw.d64, d_spec, d_nv);
+        case 4096: return launch_n<12>(ctx, st, d_samples, n_samples, ld, batch, flags, tw.d64, d_spec, d_nv);
+        case 8192: return launch_n<13>(ctx, st, d_samples, n_samples, ld, batch, flags, tw.d64, d_spec, d_nv);
     }
     apda_set_error("fft_f64_fast: unsupported N=%lld", (long long)N);
     return APDA_ERR_UNSUPPORTED;

@@ -11,6 +11,8 @@
 // the specialised fp32 kernels (fft_f32_fast.cu) do not cover.
 #include <math_constants.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -118,9 +120,9 @@ struct KeyOf<float> {
 // ---- K1 general kernel -------------------------------------------------------------------------------------------
 // dynamic shared memory: N complex<T> (transform; doubles as the select-key buffer) followed by N T (raw samples)
 template <typename T, bool FAITHFUL, bool COMPLEX_IN>
-__global__ void __launch_bounds__(kThreads)
-fft_smem_kernel(const T *__restrict__ samples, int n_samples, int64_t ld, int N, int logN,
-                const typename vec2<T>::type *__restrict__ tw, typename vec2<T>::type *__restrict__ spec, int center) {
+__device__ void fft_smem_window(const int64_t win, const T *__restrict__ samples, int n_samples, int64_t ld, int N, int logN,
+                                const typename vec2<T>::type *__restrict__ tw,
+                                typename vec2<T>::type *__restrict__ spec, int center) {
     using V2 = typename vec2<T>::type;
     using K = typename KeyOf<T>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -129,7 +131,6 @@ fft_smem_kernel(const T *__restrict__ samples, int n_samples, int64_t ld, int N,
     __shared__ double red[kThreads / 32];
     V2 *y = reinterpret_cast<V2 *>(smem_raw);
     const int tid = threadIdx.x;
-    const int64_t win = blockIdx.x;
 
     if (COMPLEX_IN) {
         const V2 *x = reinterpret_cast<const V2 *>(samples) + win * (int64_t)N;
@@ -141,7 +142,9 @@ fft_smem_kernel(const T *__restrict__ samples, int n_samples, int64_t ld, int N,
         for (int i = tid; i < n_samples; i += kThreads) raw[i] = x[i];
         __syncthreads();
         T med = T(0);
-        if (center == APDA_CENTER_MEDIAN) {
+        if (n_samples == 0) {
+            // ragged batches only: an empty window (the reference returns [0]; flagged in the record status)
+        } else if (center == APDA_CENTER_MEDIAN) {
             med = block_median<T, K>(raw, keys, n_samples, hist, bcast);
         } else if (center == APDA_CENTER_MEAN) {
             double s = 0.0;
@@ -198,6 +201,25 @@ fft_smem_kernel(const T *__restrict__ samples, int n_samples, int64_t ld, int N,
     }
 }
 
+// One CTA per window.  nv (optional): per-window sample counts of a ragged batch; list (optional): list[0] = count,
+// list[1..] = the windows to process (grid-stride), used for the ragged windows the specialised kernels skip.
+template <typename T, bool FAITHFUL, bool COMPLEX_IN>
+__global__ void __launch_bounds__(kThreads)
+fft_smem_kernel(const T *__restrict__ samples, int n_samples, int64_t ld, int N, int logN,
+                const typename vec2<T>::type *__restrict__ tw, typename vec2<T>::type *__restrict__ spec, int center,
+                const int *__restrict__ nv, const int *__restrict__ list) {
+    if (!list) {
+        const int64_t win = blockIdx.x;
+        fft_smem_window<T, FAITHFUL, COMPLEX_IN>(win, samples, nv ? nv[win] : n_samples, ld, N, logN, tw, spec, center);
+        return;
+    }
+    for (int it = blockIdx.x; it < list[0]; it += gridDim.x) {
+        const int64_t win = list[1 + it];
+        fft_smem_window<T, FAITHFUL, COMPLEX_IN>(win, samples, nv[win], ld, N, logN, tw, spec, center);
+        __syncthreads();
+    }
+}
+
 // remove_dc_component on one list (metrics/fft_iterativa.py:5-11): out[i] = in[i] - median(in)
 __global__ void __launch_bounds__(kThreads) center_kernel(const double *__restrict__ in, int n, double *__restrict__ out,
                                                           uint64_t *keys) {
@@ -226,7 +248,7 @@ template int64_t fft_smem_max_n<float>(apda_ctx *);
 
 template <typename T>
 int launch_fft_smem(apda_ctx *ctx, cudaStream_t st, const T *d_samples, int64_t n_samples, int64_t ld, int64_t batch,
-                    int64_t N, int flags, T *d_spec, bool complex_input) {
+                    int64_t N, int flags, T *d_spec, bool complex_input, const int *d_nv, const int *d_list) {
     using V2 = typename vec2<T>::type;
     TwiddleTables tw;
     APDA_TRY(apda_get_twiddles(ctx, N, &tw));
@@ -241,16 +263,17 @@ int launch_fft_smem(apda_ctx *ctx, cudaStream_t st, const T *d_samples, int64_t 
     APDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int logN = ilog2_i64(N);
     // grid.x is limited to 2^31-1 windows per launch, far above any batch that fits HBM
-    kern<<<(unsigned)batch, kThreads, smem, st>>>(d_samples, (int)n_samples, ld, (int)N, logN, twp,
-                                                  reinterpret_cast<V2 *>(d_spec), flags);
+    const unsigned grid = d_list ? (unsigned)std::min<int64_t>(batch, 2 * (int64_t)ctx->sm_count) : (unsigned)batch;
+    kern<<<grid, kThreads, smem, st>>>(d_samples, (int)n_samples, ld, (int)N, logN, twp, reinterpret_cast<V2 *>(d_spec),
+                                       flags, d_nv, d_list);
     ctx->launches++;
     APDA_CUDA(cudaGetLastError());
     return APDA_OK;
 }
 template int launch_fft_smem<double>(apda_ctx *, cudaStream_t, const double *, int64_t, int64_t, int64_t, int64_t, int,
-                                     double *, bool);
+                                     double *, bool, const int *, const int *);
 template int launch_fft_smem<float>(apda_ctx *, cudaStream_t, const float *, int64_t, int64_t, int64_t, int64_t, int,
-                                    float *, bool);
+                                    float *, bool, const int *, const int *);
 
 int launch_center_f64(apda_ctx *ctx, cudaStream_t st, const double *d_in, int64_t n, double *d_out) {
     // keys live in global scratch right behind the output (caller reserves 2*n doubles at d_out)

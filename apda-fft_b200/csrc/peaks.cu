@@ -282,7 +282,7 @@ __device__ void peaks_resolution_window(const int64_t win, const typename vec2<T
 // One CTA per window; with a repair list (list[0] = count, list[1..] = window ids, written by the fp32 fast kernel) the
 // CTAs stride over the listed windows instead.
 template <typename T, bool SMEM, bool FLEX>
-__global__ void peaks_kernel(const typename vec2<T>::type *__restrict__ spec, int64_t n, int half, int64_t batch,
+__global__ void __launch_bounds__(SMEM ? 256 : 1024) peaks_kernel(const typename vec2<T>::type *__restrict__ spec, int64_t n, int half, int64_t batch,
                              double fs_all, const double *__restrict__ d_fs, int k, int rec_cap,
                              unsigned char *__restrict__ recs, unsigned char *__restrict__ ws,
                              const int *__restrict__ list) {

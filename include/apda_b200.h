@@ -132,6 +132,41 @@ int apda_analyze_f32_host(apda_ctx *ctx, const float *h_samples, int64_t n_sampl
                           int64_t N, int flags, int flexible, double fs, const double *h_fs, int k, int rec_cap,
                           void *h_rec);
 
+/* Ragged batches: window b holds d_n_valid[b] <= n_max <= N samples (rows of ld reals); everything stays on the device
+ * and nothing synchronises.  Windows of the common length n_max run on the specialised kernels, the others on the
+ * general kernel with their own length.  Record status bit 2 (4): the window's own padded length differs from N (the
+ * reference would transform it at that length); bit 3 (8): empty window.  Used by the ingest paths (wire decode, text
+ * logs), where non-finite samples are dropped per window as utils/load_data.py:72-80 does. */
+int apda_fft_ragged_f64_dev(apda_ctx *ctx, const double *d_samples, const int32_t *d_n_valid, int64_t n_max, int64_t ld,
+                            int64_t batch, int64_t N, int flags, double *d_spec);
+int apda_fft_ragged_f32_dev(apda_ctx *ctx, const float *d_samples, const int32_t *d_n_valid, int64_t n_max, int64_t ld,
+                            int64_t batch, int64_t N, int flags, float *d_spec);
+int apda_analyze_ragged_f64_dev(apda_ctx *ctx, const double *d_samples, const int32_t *d_n_valid, int64_t n_max,
+                                int64_t ld, int64_t batch, int64_t N, int flags, int flexible, double fs,
+                                const double *d_fs, int k, int rec_cap, double *d_spec_ws, void *d_rec);
+int apda_analyze_ragged_f32_dev(apda_ctx *ctx, const float *d_samples, const int32_t *d_n_valid, int64_t n_max, int64_t ld,
+                                int64_t batch, int64_t N, int flags, int flexible, double fs, const double *d_fs, int k,
+                                int rec_cap, float *d_spec_ws, void *d_rec);
+
+/* ---- wire-format ingest ------------------------------------------------------------------
+ * replaces protocol_decoder.py:116-175 (decode_float_v2 / decode_samples: 16-bit samples, high byte first, + the axis
+ * baseline first_value, formatted "%8.6f") together with the float() read-back of utils/load_data.py:67-80 (non-finite
+ * tokens dropped): payload row b (n_max samples, 2 bytes each, rows ld_bytes apart) -> the samples the reference's FFT
+ * would have loaded, compacted, with their count in n_valid[b].  fp64 results are bit-identical to the reference chain.
+ * apda_analyze_wire16_* continues into the ragged pipeline (records as apda_analyze_*; 2 bytes per sample over PCIe). */
+int apda_decode_wire16_f64_dev(apda_ctx *ctx, const uint8_t *d_payload, int64_t n_max, int64_t ld_bytes, int64_t batch,
+                               const double *d_first_value, double *d_samples, int64_t ld_out, int32_t *d_n_valid);
+int apda_decode_wire16_f32_dev(apda_ctx *ctx, const uint8_t *d_payload, int64_t n_max, int64_t ld_bytes, int64_t batch,
+                               const double *d_first_value, float *d_samples, int64_t ld_out, int32_t *d_n_valid);
+int apda_decode_wire16_f64_host(apda_ctx *ctx, const uint8_t *h_payload, int64_t n_max, int64_t ld_bytes, int64_t batch,
+                                const double *h_first_value, double *h_samples, int32_t *h_n_valid);
+int apda_analyze_wire16_f64_host(apda_ctx *ctx, const uint8_t *h_payload, int64_t n_max, int64_t ld_bytes, int64_t batch,
+                                 const double *h_first_value, int64_t N, int flags, int flexible, double fs,
+                                 const double *h_fs, int k, int rec_cap, void *h_rec);
+int apda_analyze_wire16_f32_host(apda_ctx *ctx, const uint8_t *h_payload, int64_t n_max, int64_t ld_bytes, int64_t batch,
+                                 const double *h_first_value, int64_t N, int flags, int flexible, double fs,
+                                 const double *h_fs, int k, int rec_cap, void *h_rec);
+
 /* Fused window -> record kernel (fp32, N in {1024, 2048, 4096, 8192}, k <= 5, rec_cap == 5): same records as
  * apda_analyze_f32_*, but the spectrum never exists in memory (HBM traffic s*N + 128 bytes per window instead of
  * 4*s*N + 128).  A throughput variant for fleets that only need the peak tables; the drop-in

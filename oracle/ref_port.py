@@ -256,3 +256,44 @@ def top_peaks_resolution(spectrum, fs, k=5):
         for j in range(max(0, best_j - reach), min(half, best_j + reach + 1)):
             mags[j] = 0
     return peaks
+
+
+# ----------------------------------------------------------------------------
+# Wire-format samples  (reference: protocol_decoder.py, utils/load_data.py)
+# ----------------------------------------------------------------------------
+
+
+def decode_wire_float16(high_byte, low_byte):
+    """protocol_decoder.py:116-144 - the sensors' 16-bit sample: 1 sign, 5 exponent, 10 mantissa bits.
+
+    Exponent 31 -> inf (mantissa 0, always positive) or nan; exponent 0 -> sign * 0.00006103515 * (m/1024)
+    (a non-IEEE subnormal scale; +0.0 when the mantissa is 0); otherwise sign * 2^(e-15) * (1 + m/1024).
+    """
+    word = (high_byte << 8) | low_byte
+    expo = (word & 0x7C00) >> 10
+    sign = -1 if word & 0x8000 else 1
+    frac = (word & 0x03FF) / 1024.0
+    if expo == 31:
+        return float("nan") if frac != 0 else float("inf")
+    if expo == 0:
+        return sign * 0.00006103515 * frac if frac != 0 else 0.0
+    return sign * (pow(2, expo - 15) * (1.0 + frac))
+
+
+def decode_wire_samples_text(raw_payload, first_value=0.0):
+    """protocol_decoder.py:146-175 - byte pairs -> '%8.6f' strings of value + first_value (a trailing odd byte is ignored)."""
+    out = []
+    for i in range(0, len(raw_payload) - 1, 2):
+        out.append("%8.6f" % (decode_wire_float16(raw_payload[i], raw_payload[i + 1]) + first_value))
+    return out
+
+
+def wire_samples_as_loaded(raw_payload, first_value=0.0):
+    """What the FFT finally sees: the text above parsed back by utils/load_data.py:67-80 (float(); non-finite dropped)."""
+    import math
+    vals = []
+    for tok in decode_wire_samples_text(raw_payload, first_value):
+        v = float(tok)
+        if math.isfinite(v):
+            vals.append(v)
+    return vals

@@ -160,6 +160,40 @@ SPECTRA = [
         [1018, [100.0, 690.0, 100.0]], [1025, [100.0, 680.0, 100.0]], [30, [100.0, 500.0, 100.0]]]},
 ]
 
+def wire_payload(seed: int, n: int, specials: bool = True) -> np.ndarray:
+    """uint8[2*n]: n random 16-bit wire samples (high byte first); with `specials` a few inf/nan/subnormal/zero words."""
+    s = (seed * 2654435761 + 12345) & ((1 << 64) - 1)
+    words = np.empty(n, dtype=np.uint16)
+    for i in range(n):
+        s = (s * 6364136223846793005 + 1442695040888963407) & ((1 << 64) - 1)
+        w = (s >> 33) & 0xFFFF
+        if ((w >> 10) & 31) == 31 and not (specials and i % 97 == 0):
+            w &= 0xBFFF                       # keep ordinary words finite
+        words[i] = w
+    if specials and n >= 64:
+        words[3] = 0x7C00      # +inf
+        words[5] = 0xFC00      # "-inf" decodes to +inf
+        words[9] = 0x7E01      # nan
+        words[11] = 0x0000     # +0
+        words[12] = 0x8000     # sign bit, zero mantissa -> +0.0
+        words[13] = 0x0001     # smallest subnormal
+        words[14] = 0x83FF     # largest negative subnormal
+        words[15] = 0x3C00     # 1.0
+        words[16] = 0xBC00     # -1.0
+    out = np.empty(2 * n, dtype=np.uint8)
+    out[0::2] = words >> 8
+    out[1::2] = words & 0xFF
+    return out
+
+
+WIRE_CASES = [
+    {"id": "wire_1024_base0", "seed": 1, "n": 1024, "first_value": 0.0},
+    {"id": "wire_4096_basez", "seed": 2, "n": 4096, "first_value": 0.9981234},
+    {"id": "wire_4096_neg", "seed": 3, "n": 4096, "first_value": -0.5000005},
+    {"id": "wire_777_tiny", "seed": 4, "n": 777, "first_value": 1e-07},
+    {"id": "wire_4096_clean", "seed": 5, "n": 4096, "first_value": 0.0123456, "specials": False},
+]
+
 # cases too small for the pickers (statistics errors) are listed with the expected exception text
 K_VARIANTS = [("six_tones", 2), ("six_tones", 6), ("noise4096", 10), ("noise1024", 1), ("katB", 3)]
 

@@ -474,3 +474,35 @@ def test_fused_kernel_matches_pipeline_and_oracle(n, an):
     got = an.analyze_fused(tones[:8], 125.0, flexible=True)
     for w in range(8):
         assert [p["idx"] for p in _dicts(got[w], 125.0, n, True)] == [p["idx"] for p in c_oracle.peaks_prominence(want[w], 125.0)]
+
+
+def test_wire16_decode_bit_exact_and_pipeline(golden, an):
+    """Wire ingest: device decode == reference decode_samples + '%8.6f' + float() (fp64 bits), and the ragged pipeline
+    on the decoded windows == the oracle on the same samples."""
+    rows, firsts = [], []
+    for wc in cases.WIRE_CASES:
+        g = golden["wire"][wc["id"]]
+        pay = cases.wire_payload(wc["seed"], wc["n"], wc.get("specials", True))
+        samples, nv = an.decode_wire16(pay[None, :], wc["first_value"])
+        assert int(nv[0]) == g["n_valid"]
+        assert cases.sha16(samples[0, : nv[0]]) == g["sha"], wc["id"]
+        if wc["n"] == 4096:
+            rows.append(pay)
+            firsts.append(wc["first_value"])
+    # a ragged batch: three 4096-sample payloads (two of them lose samples to inf/nan), fp64 and fp32
+    pay = np.stack(rows)
+    fv = np.asarray(firsts)
+    samples, nv = an.decode_wire16(pay, fv)
+    for dtype, tol in (("f64", TOL64), ("f32", TOL32)):
+        for flexible in (True, False):
+            recs = an.analyze_wire16(pay, fv, 125.0, dtype=dtype, flexible=flexible)
+            for w in range(pay.shape[0]):
+                x = samples[w, : nv[w]]
+                spec = c_oracle.start_fft_batch(x, n_fft=4096)[0]
+                want = c_oracle.peaks_prominence(spec, 125.0) if flexible else c_oracle.peaks_resolution(spec, 125.0)
+                got = _dicts(recs[w], 125.0, 4096, flexible)
+                if dtype == "f64":
+                    assert_peaks_close(got, want, tol, (w, flexible))
+                else:
+                    assert [p["idx"] for p in got][:2] == [p["idx"] for p in want][:2] or len(want) == 0
+                assert recs[w]["status"] == 0

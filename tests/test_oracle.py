@@ -113,3 +113,13 @@ def test_golden_file_still_matches_live_reference():
     rc = subprocess.call([sys.executable, os.path.join(ROOT, "tests", "golden", "make_golden.py"), "--check"],
                          stdout=subprocess.DEVNULL)
     assert rc == 0
+
+
+def test_wire_decode_port_matches_golden(golden):
+    for wc in cases.WIRE_CASES:
+        g = golden["wire"][wc["id"]]
+        pay = cases.wire_payload(wc["seed"], wc["n"], wc.get("specials", True))
+        loaded = ref_port.wire_samples_as_loaded(pay.tolist(), wc["first_value"])
+        assert len(loaded) == g["n_valid"] and cases.sha16(np.asarray(loaded)) == g["sha"]
+        assert loaded[:6] == g["head"]
+        assert ref_port.decode_wire_samples_text(pay.tolist(), wc["first_value"])[:6] == g["text_head"]
