@@ -390,6 +390,40 @@ def run_ours(args):
                "windows_per_gpu_per_step": eb, "records_equal_device_path": same,
                "api": f"apda_analyze_{args.dtype}_host (pinned host buffers, chunked 2-stream H2D/compute/D2H)"}
 
+    # ---- e2e from the sensors' 16-bit wire samples (2 bytes per sample over PCIe) --------------------
+    e2e_wire = None
+    if not args.no_e2e and args.dtype == "f32":
+        eb = min(args.e2e_windows, b)
+        rng = np.random.default_rng(1234 + rank)
+        # synthetic payload: finite 16-bit words (exponent 31 cleared), random baseline per window
+        words = rng.integers(0, 1 << 16, size=(eb, n), dtype=np.uint16) & np.uint16(0xBFFF)
+        pay = np.empty((eb, 2 * n), dtype=np.uint8)
+        pay[:, 0::2] = (words >> 8).astype(np.uint8)
+        pay[:, 1::2] = (words & 0xFF).astype(np.uint8)
+        h_pay = torch.from_numpy(pay).pin_memory()
+        h_fv = torch.from_numpy(rng.uniform(-1, 1, eb)).pin_memory()
+        h_rec2 = torch.zeros((eb, 128), dtype=torch.uint8).pin_memory()
+        import ctypes
+
+        def wire_step():
+            an.ctx.call("apda_analyze_wire16_f32_host", ctypes.c_void_p(h_pay.data_ptr()), n, 2 * n, eb,
+                        ctypes.c_void_p(h_fv.data_ptr()), n, _cabi.CENTER_MEDIAN, int(flexible), fs, ctypes.c_void_p(0),
+                        4 if flexible else 5, 5, ctypes.c_void_p(h_rec2.data_ptr()))
+
+        wire_step()
+        fence()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            wire_step()
+        torch.cuda.synchronize()
+        t_w = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_w, op=dist.ReduceOp.MAX)
+        e2e_wire = {"value": eb * world * args.e2e_steps / float(t_w[0]), "unit": UNIT,
+                    "h2d_bytes_per_step": eb * (2 * n + 8), "d2h_bytes_per_step": eb * 128,
+                    "api": "apda_analyze_wire16_f32_host (raw 16-bit sensor samples + baseline; decode, centre, FFT, pick on device)",
+                    "data": "random finite 16-bit words (throughput only; parity is covered by tests/golden wire cases)"}
+
     if rank == 0:
         peak, peak_src = measured_peak()
         k1_bytes = 3 * s_bytes * n * b
@@ -411,7 +445,7 @@ def run_ours(args):
                          "frac_of_peak": b_alg / (step_ms * 1e-3) / 1e9 / peak,
                          "k1_share_of_step": k1_ms / step_ms},
             "e2e": e2e, "gpu_launches": int(launches) * world, "clocks": clocks, "result_check": summary,
-            "variants": variants,
+            "variants": variants, "e2e_wire16": e2e_wire,
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

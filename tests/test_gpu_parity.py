@@ -506,3 +506,40 @@ def test_wire16_decode_bit_exact_and_pipeline(golden, an):
                 else:
                     assert [p["idx"] for p in got][:2] == [p["idx"] for p in want][:2] or len(want) == 0
                 assert recs[w]["status"] == 0
+
+
+def test_ragged_batch_device_api(an):
+    """apda_analyze_ragged_*_dev: per-window sample counts, including an empty window and one whose own padded length
+    differs from the batch N (status bits 3 and 2)."""
+    import ctypes
+    import torch
+    import apda_fft_b200.synth as synth
+    from apda_fft_b200.records import record_dtype
+    n = 4096
+    counts = [4096, 4095, 3000, 2049, 4096, 0, 1500, 4096]
+    full = synth.fleet_windows(60, len(counts), n)
+    dev = torch.device("cuda:0")
+    an.use_stream(torch.cuda.current_stream(dev).cuda_stream)
+    try:
+        for name, tdt, tol in (("f64", torch.float64, TOL64), ("f32", torch.float32, TOL32)):
+            d_x = torch.as_tensor(full, device=dev).to(tdt).contiguous()
+            d_nv = torch.tensor(counts, dtype=torch.int32, device=dev)
+            d_rec = torch.zeros((len(counts), 128), dtype=torch.uint8, device=dev)
+            an.ctx.call(f"apda_analyze_ragged_{name}_dev", ctypes.c_void_p(d_x.data_ptr()), ctypes.c_void_p(d_nv.data_ptr()),
+                        n, n, len(counts), n, 0, 1, 125.0, ctypes.c_void_p(0), 4, 5, ctypes.c_void_p(0),
+                        ctypes.c_void_p(d_rec.data_ptr()))
+            torch.cuda.synchronize()
+            recs = d_rec.cpu().numpy().view(record_dtype(5)).reshape(-1)
+            for w, cnt in enumerate(counts):
+                if cnt == 0:
+                    assert recs[w]["status"] & 8 and recs[w]["count"] == 0
+                    continue
+                assert bool(recs[w]["status"] & 4) == (c_oracle.padded_len(cnt) != n), (w, cnt)
+                want = c_oracle.peaks_prominence(c_oracle.start_fft_batch(full[w, :cnt], n_fft=n)[0], 125.0)
+                got = _dicts(recs[w], 125.0, n, True)
+                if name == "f64":
+                    assert_peaks_close(got, want, tol, (w, cnt))
+                else:
+                    assert [p["idx"] for p in got] == [p["idx"] for p in want], (w, cnt)
+    finally:
+        an.use_stream(None)
