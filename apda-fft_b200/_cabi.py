@@ -59,6 +59,9 @@ SIGNATURES = {
     "apda_decode_wire16_f64_host": (_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p]),
     "apda_analyze_wire16_f64_host": (_int, [_p, _p, _i64, _i64, _i64, _p, _i64, _int, _int, _dbl, _p, _int, _int, _p]),
     "apda_analyze_wire16_f32_host": (_int, [_p, _p, _i64, _i64, _i64, _p, _i64, _int, _int, _dbl, _p, _int, _int, _p]),
+    "apda_parse_samples_f64_host": (_int, [_p, _p, _p, _i64, _i64, _p, _p, _p]),
+    "apda_analyze_text_f64_host": (_int, [_p, _p, _p, _i64, _i64, _i64, _int, _int, _dbl, _p, _int, _int, _p, _p, _p]),
+    "apda_analyze_text_f32_host": (_int, [_p, _p, _p, _i64, _i64, _i64, _int, _int, _dbl, _p, _int, _int, _p, _p, _p]),
     "apda_analyze_fused_f32_dev": (_int, [_p, _p, _i64, _i64, _i64, _i64, _int, _int, _dbl, _p, _int, _int, _p]),
     "apda_analyze_fused_f32_host": (_int, [_p, _p, _i64, _i64, _i64, _i64, _int, _int, _dbl, _p, _int, _int, _p]),
     "apda_prominence_f64_host": (_int, [_p, _p, _i64, _i64, _c.POINTER(_dbl)]),

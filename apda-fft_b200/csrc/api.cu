@@ -819,6 +819,123 @@ extern "C" int apda_analyze_wire16_f32_host(apda_ctx *ctx, const uint8_t *h_payl
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// text ingest: the sample lines of many sensor logs -> samples (-> records) on the device
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+static int text_host(apda_ctx *ctx, const char *h_text, const int64_t *h_offsets, int64_t batch, int64_t n_max,
+                     T *h_samples_out, int32_t *h_n_valid, int32_t *h_flags, bool analyze, int64_t N, int flags,
+                     int flexible, double fs, const double *h_fs, int k, int rec_cap, void *h_rec) {
+    if (!ctx || !h_text || !h_offsets || !h_n_valid || !h_flags || batch < 0 || batch > 0x7fffffff || n_max < 1) {
+        apda_set_error("text ingest: bad arguments");
+        return APDA_ERR_INVALID;
+    }
+    APDA_CUDA(cudaSetDevice(ctx->device));
+    if (batch == 0) return APDA_OK;
+    const size_t rec_bytes = (size_t)APDA_REC_BYTES(rec_cap);
+    const size_t per_window = analyze ? (size_t)N * 2 * sizeof(T) : (size_t)n_max * sizeof(T);
+    int64_t chunk = std::max<int64_t>(1, (int64_t)((96u << 20) / per_window));
+    chunk = std::min<int64_t>(chunk, batch);
+    if (batch > chunk && batch < 2 * chunk) chunk = (batch + 1) / 2;
+    size_t max_text = 0;  // largest text span of a chunk
+    for (int64_t d = 0; d < batch; d += chunk)
+        max_text = std::max<size_t>(max_text, (size_t)(h_offsets[std::min(batch, d + chunk)] - h_offsets[d]));
+    const size_t txt_b = align256(max_text + 16), off_b = align256((chunk + 1) * sizeof(int64_t));
+    const size_t smp_b = align256(chunk * (size_t)n_max * sizeof(T)), nv_b = align256(chunk * sizeof(int));
+    const size_t fl_b = align256(chunk * sizeof(int));
+    const size_t spec_b = analyze ? align256(chunk * (size_t)N * 2 * sizeof(T)) : 0;
+    const size_t recs_b = analyze ? align256(chunk * rec_bytes) : 0;
+    const size_t fs_b = (analyze && h_fs) ? align256(chunk * sizeof(double)) : 0;
+    const size_t mag_b = analyze ? align256(peaks_mag_workspace_bytes<T>(ctx, N, chunk)) : 0;
+    const size_t total = txt_b + off_b + smp_b + nv_b + fl_b + spec_b + recs_b + fs_b + mag_b;
+    for (int s = 0; s < 2; ++s) {
+        if (total > ctx->ws_pipe_bytes[s]) {
+            APDA_CUDA(cudaStreamSynchronize(ctx->pipe[s]));
+            APDA_TRY(apda_reserve(&ctx->ws_pipe[s], &ctx->ws_pipe_bytes[s], total));
+        }
+        if (batch <= chunk) break;
+    }
+    std::vector<int64_t> rel[2];
+    int status = APDA_OK;
+    int64_t done = 0;
+    for (int c = 0; done < batch && status == APDA_OK; ++c) {
+        const int s = c & 1;
+        cudaStream_t st = ctx->pipe[s];
+        const int64_t cnt = std::min<int64_t>(chunk, batch - done);
+        char *base = (char *)ctx->ws_pipe[s];
+        char *d_txt = base;
+        int64_t *d_off = (int64_t *)(base + txt_b);
+        T *d_smp = (T *)(base + txt_b + off_b);
+        int *d_nv = (int *)(base + txt_b + off_b + smp_b);
+        int *d_fl = (int *)(base + txt_b + off_b + smp_b + nv_b);
+        T *d_spec = (T *)(base + txt_b + off_b + smp_b + nv_b + fl_b);
+        void *d_rec = base + txt_b + off_b + smp_b + nv_b + fl_b + spec_b;
+        double *d_fs = fs_b ? (double *)(base + txt_b + off_b + smp_b + nv_b + fl_b + spec_b + recs_b) : nullptr;
+        void *mag_ws = mag_b ? base + txt_b + off_b + smp_b + nv_b + fl_b + spec_b + recs_b + fs_b : nullptr;
+        size_t mag_have = mag_b;
+        APDA_CUDA(cudaStreamSynchronize(st));  // rel[s] is reused: the previous chunk on this stream must have consumed it
+        rel[s].resize((size_t)cnt + 1);
+        for (int64_t i = 0; i <= cnt; ++i) rel[s][(size_t)i] = h_offsets[done + i] - h_offsets[done];
+        APDA_CUDA(cudaMemcpyAsync(d_txt, h_text + h_offsets[done], (size_t)rel[s][(size_t)cnt], cudaMemcpyHostToDevice, st));
+        APDA_CUDA(cudaMemcpyAsync(d_off, rel[s].data(), (size_t)(cnt + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        if (d_fs) APDA_CUDA(cudaMemcpyAsync(d_fs, h_fs + done, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+        status = launch_parse_samples<T>(ctx, st, d_txt, d_off, cnt, n_max, d_smp, d_nv, d_fl);
+        if (status != APDA_OK) break;
+        if (h_samples_out)
+            APDA_CUDA(cudaMemcpyAsync(h_samples_out + (size_t)done * n_max, d_smp, cnt * (size_t)n_max * sizeof(T),
+                                      cudaMemcpyDeviceToHost, st));
+        APDA_CUDA(cudaMemcpyAsync(h_n_valid + done, d_nv, cnt * sizeof(int), cudaMemcpyDeviceToHost, st));
+        APDA_CUDA(cudaMemcpyAsync(h_flags + done, d_fl, cnt * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (analyze) {
+            status = analyze_ragged_dev<T>(ctx, st, d_smp, d_nv, n_max, n_max, cnt, N, flags, flexible, fs, d_fs, k, rec_cap,
+                                           d_spec, d_rec, &mag_ws, &mag_have, 0);
+            if (status == APDA_OK)
+                APDA_CUDA(cudaMemcpyAsync((char *)h_rec + (size_t)done * rec_bytes, d_rec, cnt * rec_bytes,
+                                          cudaMemcpyDeviceToHost, st));
+        }
+        done += cnt;
+    }
+    cudaError_t e0 = cudaStreamSynchronize(ctx->pipe[0]);
+    cudaError_t e1 = cudaStreamSynchronize(ctx->pipe[1]);
+    if (status != APDA_OK) return status;
+    if (e0 != cudaSuccess) return apda_cuda_fail(e0, "text pipeline (stream 0)");
+    if (e1 != cudaSuccess) return apda_cuda_fail(e1, "text pipeline (stream 1)");
+    return APDA_OK;
+}
+
+extern "C" int apda_parse_samples_f64_host(apda_ctx *ctx, const char *h_text, const int64_t *h_offsets, int64_t batch,
+                                           int64_t n_max, double *h_samples, int32_t *h_n_valid, int32_t *h_flags) {
+    if (!h_samples) {
+        apda_set_error("parse_samples: output is NULL");
+        return APDA_ERR_INVALID;
+    }
+    return text_host<double>(ctx, h_text, h_offsets, batch, n_max, h_samples, h_n_valid, h_flags, false, 0, 0, 0, 0.0, nullptr,
+                             1, 5, nullptr);
+}
+template <typename T>
+static int analyze_text_host(apda_ctx *ctx, const char *h_text, const int64_t *h_offsets, int64_t batch, int64_t n_max,
+                             int64_t N, int flags, int flexible, double fs, const double *h_fs, int k, int rec_cap,
+                             void *h_rec, int32_t *h_n_valid, int32_t *h_flags) {
+    APDA_TRY(check_fft_args(ctx, h_text, n_max, n_max, batch, N, flags, h_rec));
+    APDA_TRY(check_peaks_args(ctx, h_text, N, batch, k, rec_cap, h_rec));
+    return text_host<T>(ctx, h_text, h_offsets, batch, n_max, nullptr, h_n_valid, h_flags, true, N, flags, flexible, fs, h_fs, k,
+                        rec_cap, h_rec);
+}
+extern "C" int apda_analyze_text_f64_host(apda_ctx *ctx, const char *h_text, const int64_t *h_offsets, int64_t batch,
+                                          int64_t n_max, int64_t N, int flags, int flexible, double fs,
+                                          const double *h_fs, int k, int rec_cap, void *h_rec, int32_t *h_n_valid,
+                                          int32_t *h_flags) {
+    return analyze_text_host<double>(ctx, h_text, h_offsets, batch, n_max, N, flags, flexible, fs, h_fs, k, rec_cap, h_rec,
+                                     h_n_valid, h_flags);
+}
+extern "C" int apda_analyze_text_f32_host(apda_ctx *ctx, const char *h_text, const int64_t *h_offsets, int64_t batch,
+                                          int64_t n_max, int64_t N, int flags, int flexible, double fs,
+                                          const double *h_fs, int k, int rec_cap, void *h_rec, int32_t *h_n_valid,
+                                          int32_t *h_flags) {
+    return analyze_text_host<float>(ctx, h_text, h_offsets, batch, n_max, N, flags, flexible, fs, h_fs, k, rec_cap, h_rec,
+                                    h_n_valid, h_flags);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // small helpers on host lists
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" int apda_center_f64_host(apda_ctx *ctx, const double *h_in, int64_t n, double *h_out) {

@@ -93,6 +93,9 @@ int launch_fused_f32(apda_ctx *ctx, cudaStream_t st, const float *d_samples, int
 template <typename T>
 int launch_decode_wire16(apda_ctx *ctx, cudaStream_t st, const unsigned char *d_payload, int64_t n_max, int64_t ld_bytes,
                          int64_t batch, const double *d_first_value, T *d_samples, int64_t ld_out, int *d_n_valid);
+template <typename T>
+int launch_parse_samples(apda_ctx *ctx, cudaStream_t st, const char *d_text, const int64_t *d_offsets, int64_t batch,
+                         int64_t ld, T *d_samples, int *d_n_valid, int *d_flags);
 bool fft_f64_fast_supports(int64_t N);
 int launch_fft_f64_fast(apda_ctx *ctx, cudaStream_t st, const double *d_samples, int64_t n_samples, int64_t ld,
                         int64_t batch, int64_t N, int flags, double *d_spec, const int *d_nv = nullptr);

@@ -167,6 +167,22 @@ int apda_analyze_wire16_f32_host(apda_ctx *ctx, const uint8_t *h_payload, int64_
                                  const double *h_first_value, int64_t N, int flags, int flexible, double fs,
                                  const double *h_fs, int k, int rec_cap, void *h_rec);
 
+/* ---- text ingest ---------------------------------------------------------------------------
+ * replaces the sample loop of utils/load_data.py:67-80 for many sensor logs at once.  h_text holds the logs' sample
+ * regions (everything after the four header lines) back to back; log b is h_text[h_offsets[b] .. h_offsets[b+1]).
+ * Pieces between ';' / newlines are parsed like float() and non-finite / unparsable ones dropped; log b yields
+ * h_n_valid[b] <= n_max samples.  h_flags[b] bit 0: the log holds a piece in a float() syntax the kernel does not
+ * decide (exponent, '_', > 15 significant digits, non-ASCII): re-parse that log on the host; bit 1: more than n_max
+ * samples (truncated).  apda_analyze_text_* continues into the ragged pipeline without moving the samples to the host. */
+int apda_parse_samples_f64_host(apda_ctx *ctx, const char *h_text, const int64_t *h_offsets, int64_t batch, int64_t n_max,
+                                double *h_samples, int32_t *h_n_valid, int32_t *h_flags);
+int apda_analyze_text_f64_host(apda_ctx *ctx, const char *h_text, const int64_t *h_offsets, int64_t batch, int64_t n_max,
+                               int64_t N, int flags, int flexible, double fs, const double *h_fs, int k, int rec_cap,
+                               void *h_rec, int32_t *h_n_valid, int32_t *h_flags);
+int apda_analyze_text_f32_host(apda_ctx *ctx, const char *h_text, const int64_t *h_offsets, int64_t batch, int64_t n_max,
+                               int64_t N, int flags, int flexible, double fs, const double *h_fs, int k, int rec_cap,
+                               void *h_rec, int32_t *h_n_valid, int32_t *h_flags);
+
 /* Fused window -> record kernel (fp32, N in {1024, 2048, 4096, 8192}, k <= 5, rec_cap == 5): same records as
  * apda_analyze_f32_*, but the spectrum never exists in memory (HBM traffic s*N + 128 bytes per window instead of
  * 4*s*N + 128).  A throughput variant for fleets that only need the peak tables; the drop-in

@@ -297,3 +297,25 @@ def wire_samples_as_loaded(raw_payload, first_value=0.0):
         if math.isfinite(v):
             vals.append(v)
     return vals
+
+
+# ----------------------------------------------------------------------------
+# Sensor log sample lines  (reference: utils/load_data.py)
+# ----------------------------------------------------------------------------
+
+
+def parse_log_sample_lines(lines):
+    """utils/load_data.py:67-80 - lines[4:] of a sensor log: ';'-separated pieces, float(), finite values only."""
+    import math
+    out = []
+    for line in lines:
+        for piece in line.strip().split(";"):
+            if not piece:
+                continue
+            try:
+                val = float(piece)
+            except ValueError:
+                continue
+            if math.isfinite(val):
+                out.append(val)
+    return out

@@ -186,6 +186,34 @@ def wire_payload(seed: int, n: int, specials: bool = True) -> np.ndarray:
     return out
 
 
+LOG_HEADER = "2_11_22_18_20_32;2 g;125.0 Hz;X axis;\nSynced;\n25.010;-0.0222;0.0110;0.9981;85.0;\n0.268262;-0.5;1.0;\n"
+
+NASTY_PIECES = ["+1.5", ".5", "5.", "-0.000000", "00012.500", "1e3", "1E-2", "1_0", "nan", "inf", "-inf", "Infinity", "abc",
+                "* MISSING PACKETS 3-4 *", " ", "1.2.3", "--1", "1-", "0.1234567890123456789", "123456789012345678",
+                "0.0000000000000000000001", "\u0661\u0662", " 7.25 ", "+", ".", "-.", "9007199254740993", "1e400", "-1e-400",
+                "0x10", "1,5", "\t-3.125\t"]
+
+
+def log_text(seed: int, n: int, nasty: bool, newline: str = "\n", per_line: int = 60) -> str:
+    """Text of one sensor .log: 4 header lines + n '%8.6f' samples (optionally sprinkled with nasty pieces)."""
+    vals = np.round(np.sin(np.arange(n) * 0.37 + seed) * 1.7 + 0.3 * (2 * _lcg_uniform(seed + 77, n) - 1), 6)
+    pieces = ["%8.6f" % v for v in vals]
+    if nasty:
+        for i, tok in enumerate(NASTY_PIECES):
+            pieces.insert(min(len(pieces), 5 + 13 * i), tok)
+    rows = [";".join(pieces[i:i + per_line]) + ";" for i in range(0, len(pieces), per_line)]
+    return LOG_HEADER.replace("\n", newline) + newline.join(rows) + newline
+
+
+LOG_CASES = [
+    {"id": "log_clean_4096", "seed": 1, "n": 4096, "nasty": False},
+    {"id": "log_nasty_1000", "seed": 2, "n": 1000, "nasty": True},
+    {"id": "log_crlf_2048", "seed": 3, "n": 2048, "nasty": False, "newline": "\r\n", "per_line": 7},
+    {"id": "log_short_0", "seed": 4, "n": 0, "nasty": False},
+    {"id": "log_oneline_300", "seed": 5, "n": 300, "nasty": True, "per_line": 100000},
+]
+
+
 WIRE_CASES = [
     {"id": "wire_1024_base0", "seed": 1, "n": 1024, "first_value": 0.0},
     {"id": "wire_4096_basez", "seed": 2, "n": 4096, "first_value": 0.9981234},

@@ -543,3 +543,41 @@ def test_ragged_batch_device_api(an):
                     assert [p["idx"] for p in got] == [p["idx"] for p in want], (w, cnt)
     finally:
         an.use_stream(None)
+
+
+def test_text_ingest_matches_load_sensor(golden, tmp_path, an):
+    """Batched GPU log parser == the reference's load_sensor on clean, CRLF, one-line and nasty logs."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "apda-fft_b200"))
+    from utils.load_data import load_sensor, load_sensors
+    paths = []
+    for lc in cases.LOG_CASES:
+        text = cases.log_text(lc["seed"], lc["n"], lc["nasty"], lc.get("newline", "\n"), lc.get("per_line", 60))
+        path = tmp_path / (lc["id"] + ".log")
+        path.write_bytes(text.encode("utf-8"))
+        paths.append(str(path))
+    short = tmp_path / "short.log"
+    short.write_text("a;b;1 Hz;X axis;\nNo;\n")
+    paths.append(str(short))
+    batch = load_sensors(paths)
+    assert batch[-1] is None
+    for lc, got in zip(cases.LOG_CASES, batch):
+        g = golden["logs"][lc["id"]]
+        want = load_sensor(paths[cases.LOG_CASES.index(lc)])
+        if want is None:
+            assert got is None
+            continue
+        assert got["metadata"] == want["metadata"] and got["summary"] == want["summary"]
+        assert len(got["samples"]) == g["n_samples"] and cases.sha16(np.asarray(got["samples"])) == g["sha"], lc["id"]
+    # the device parser alone (no host fallback): every piece it decides must equal float(); undecided ones raise the flag
+    import ctypes
+    pieces = ["0.5", "-1.25", "+3", ".125", "7.", "000.500", "-0.000000", "123456789.012345", "0.000001", "nan", "x1", "", " "]
+    text = (";".join(pieces) + ";\n").encode()
+    off = np.array([0, len(text)], dtype=np.int64)
+    out = np.zeros((1, 64)); nv = np.zeros(1, dtype=np.int32); fl = np.zeros(1, dtype=np.int32)
+    buf = np.frombuffer(text, dtype=np.uint8)
+    p = ctypes.c_void_p
+    an.ctx.call("apda_parse_samples_f64_host", p(buf.ctypes.data), p(off.ctypes.data), 1, 64, p(out.ctypes.data),
+                p(nv.ctypes.data), p(fl.ctypes.data))
+    assert fl[0] == 0 and out[0, : nv[0]].tolist() == [0.5, -1.25, 3.0, 0.125, 7.0, 0.5, -0.0, 123456789.012345, 1e-06]
+    assert np.signbit(out[0, 6])

@@ -123,3 +123,26 @@ def test_wire_decode_port_matches_golden(golden):
         assert len(loaded) == g["n_valid"] and cases.sha16(np.asarray(loaded)) == g["sha"]
         assert loaded[:6] == g["head"]
         assert ref_port.decode_wire_samples_text(pay.tolist(), wc["first_value"])[:6] == g["text_head"]
+
+
+def test_log_parsing_port_and_split(golden, tmp_path):
+    import io
+    sys.path.insert(0, os.path.join(ROOT, "apda-fft_b200"))
+    from utils.load_data import load_sensor, split_log
+    for lc in cases.LOG_CASES:
+        g = golden["logs"][lc["id"]]
+        text = cases.log_text(lc["seed"], lc["n"], lc["nasty"], lc.get("newline", "\n"), lc.get("per_line", 60))
+        lines = io.StringIO(text, newline=None).readlines()
+        got = ref_port.parse_log_sample_lines(lines[4:])
+        assert len(got) == g["n_samples"] and cases.sha16(np.asarray(got)) == g["sha"] and got[-4:] == g["tail"]
+        path = tmp_path / (lc["id"] + ".log")
+        path.write_bytes(text.encode("utf-8"))
+        mine = load_sensor(str(path))
+        assert mine["samples"] == got and mine["metadata"]["fs"] == g["fs"] and mine["metadata"]["axis"] == g["axis"]
+        parts = split_log(text.encode("utf-8"))
+        if lc["n"] == 0:
+            assert parts is None or ref_port.parse_log_sample_lines(
+                io.StringIO(parts[1].decode(), newline=None).readlines()) == []
+        else:
+            rows = io.StringIO(parts[1].decode("utf-8"), newline=None).readlines()
+            assert parts[0] == lines[:4] and ref_port.parse_log_sample_lines(rows) == got
