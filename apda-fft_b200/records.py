@@ -37,3 +37,30 @@ def resolution_dicts(rec, fs: float, n: int) -> list[dict]:
     df = fs / n
     return [{"freq": int(pk["idx"]) * df, "mag": float(pk["mag"]), "idx": int(pk["idx"])}
             for pk in rec["pk"][: int(rec["count"])]]
+
+
+def gateway_entry(peaks: list[dict]) -> dict:
+    """The per-axis ``fft_dict`` entry the reference's caller builds from a picker result (GT_FFT_v5.py:644-659):
+    ``peak_freq`` / ``max_mag`` of the first peak (-1 when there is none) plus ``peak_freq_i`` / ``max_mag_i`` for
+    every returned peak.  (The timing fields the caller adds afterwards are its own business.)"""
+    entry = {"peak_freq": -1, "max_mag": -1}
+    if peaks:
+        entry["peak_freq"] = peaks[0]["freq"]
+        entry["max_mag"] = peaks[0]["mag"]
+        for i, pk in enumerate(peaks):
+            entry[f"peak_freq_{i + 1}"] = pk["freq"]
+            entry[f"max_mag_{i + 1}"] = pk["mag"]
+    return entry
+
+
+def fleet_table(recs, fs, n: int, flexible: bool = True, k: int = 4):
+    """Columnar view of a record batch for bulk consumers: (count[B], idx[B,k], freq[B,k], mag[B,k]).
+    freq/mag are the raw doubles (idx * fs / n and |X|); apply prominence_dicts per window where the reference's
+    decimal rounding is needed."""
+    import numpy as np
+    recs = np.asarray(recs)
+    idx = recs["pk"]["idx"][:, :k].astype(np.int64)
+    fs_col = np.broadcast_to(np.asarray(fs, dtype=np.float64), (recs.shape[0],))[:, None]
+    freq = np.where(idx >= 0, idx * (fs_col / n), np.nan)
+    mag = np.where(idx >= 0, recs["pk"]["mag"][:, :k], np.nan)
+    return recs["count"].astype(np.int64), idx, freq, mag

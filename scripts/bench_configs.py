@@ -161,6 +161,43 @@ def main():
     r, _, _ = batch_config(an, dev, 1_000_000, 4096, "f32", False)
     out["cfg5_rigid_median"] = r
 
+    # ingest rows: text logs and 16-bit wire samples -> records, host buffers in, records out
+    import ctypes
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases
+    nlog, ns = 4096, 4096
+    one = cases.log_text(1, ns, False).encode()
+    region = one[one.index(b"\n", one.index(b"\n", one.index(b"\n", one.index(b"\n") + 1) + 1) + 1) + 1:]
+    text = np.frombuffer(region * nlog, dtype=np.uint8)
+    off = (np.arange(nlog + 1, dtype=np.int64) * len(region))
+    recs = np.zeros(nlog, dtype=record_dtype(5)); nv = np.zeros(nlog, dtype=np.int32); fl = np.zeros(nlog, dtype=np.int32)
+    p = ctypes.c_void_p
+
+    def text_step(dtype):
+        an.ctx.call(f"apda_analyze_text_{dtype}_host", p(text.ctypes.data), p(off.ctypes.data), nlog, ns, ns, 0, 1, 125.0, p(0),
+                    4, 5, p(recs.ctypes.data), p(nv.ctypes.data), p(fl.ctypes.data))
+    ingest = {}
+    for dtype in ("f32", "f64"):
+        text_step(dtype)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            text_step(dtype)
+        dt = (time.perf_counter() - t0) / 3
+        ingest[f"text_logs_{dtype}"] = {"logs": nlog, "samples_per_log": ns, "text_bytes_per_log": len(region),
+                                        "logs_per_s": nlog / dt, "text_gbs": nlog * len(region) / dt / 1e9,
+                                        "all_valid": bool((nv == ns).all() and (fl == 0).all())}
+    # host baseline: the reference loop (split + float()) on one core
+    rows = region.decode().splitlines()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        cnt = 0
+        for row in rows:
+            for tok in row.strip().split(";"):
+                if tok:
+                    float(tok); cnt += 1
+    ingest["python_float_parse_logs_per_s_per_core"] = 3 / (time.perf_counter() - t0)
+    out["ingest"] = ingest
+
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as fh:
         json.dump(out, fh, indent=1)

@@ -166,3 +166,19 @@ def test_synth_device_twin_constants():
     block = synth.fleet_windows(123, 3, 256, on_bin=True, dtype=np.float32)
     for r in range(3):
         assert np.array_equal(block[r], synth.fleet_window(123 + r, 256, on_bin=True).astype(np.float32))
+
+
+def test_gateway_entry_and_fleet_table(golden):
+    from apda_fft_b200.records import fleet_table, gateway_entry, record_dtype
+    peaks = golden["cases"]["katA"]["prominence"]["ok"]
+    entry = gateway_entry(peaks)
+    assert entry["peak_freq"] == 3.0518 and entry["max_mag"] == 195.833 and entry["peak_freq_3"] == 15.1367
+    assert gateway_entry([]) == {"peak_freq": -1, "max_mag": -1}
+    recs = np.zeros(2, dtype=record_dtype(5))
+    recs["pk"]["idx"] = -1
+    recs[0]["count"] = 2
+    recs[0]["pk"][0] = (25, 2, 195.8, 195.7)
+    recs[0]["pk"][1] = (63, 2, 149.3, 149.1)
+    count, idx, freq, mag = fleet_table(recs, 125.0, 1024)
+    assert count.tolist() == [2, 0] and idx[0, :2].tolist() == [25, 63] and freq[0, 0] == 25 * (125.0 / 1024)
+    assert np.isnan(freq[1]).all() and mag[0, 1] == 149.3
