@@ -227,14 +227,14 @@ __device__ float select_median(const float2 (&v2)[16], int n_valid, uint32_t *sh
         int cnt = 0;
 #pragma unroll
         for (int i = 0; i < 32; ++i) cnt += (VAL(i) < pivot);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        if (lane == 0) sh[warp] = (uint32_t)cnt;
+        cnt = __reduce_add_sync(0xffffffffu, cnt);  // REDUX: one instruction instead of a shuffle tree
+        // one barrier per round: the per-warp partial counts alternate between two banks of slots
+        uint32_t *cslot = sh + 40 + 8 * (round & 1);
+        if (lane == 0) cslot[warp] = (uint32_t)cnt;
         group_sync<T>(slot);
         int tot = 0;
 #pragma unroll
-        for (int w = 0; w < NW; ++w) tot += (int)sh[w];
-        group_sync<T>(slot);
+        for (int w = 0; w < NW; ++w) tot += (int)cslot[w];
         if (tot <= r_lo) {  // both middle order statistics are >= pivot
             lo = pivot;
             c_lo = tot;

@@ -102,14 +102,13 @@ __device__ double select_median_f64(const double (&val)[16], int n_valid, double
         int cnt = 0;
 #pragma unroll
         for (int i = 0; i < 16; ++i) cnt += (val[i] < pivot);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        if (lane == 0) shu[warp] = (unsigned)cnt;
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        unsigned *cslot = shu + 16 * (round & 1);  // alternating banks: one barrier per round
+        if (lane == 0) cslot[warp] = (unsigned)cnt;
         __syncthreads();
         int tot = 0;
 #pragma unroll
-        for (int w = 0; w < NW; ++w) tot += (int)shu[w];
-        __syncthreads();
+        for (int w = 0; w < NW; ++w) tot += (int)cslot[w];
         if (tot <= r_lo) {
             lo = pivot;
             c_lo = tot;
@@ -142,17 +141,18 @@ __device__ double select_median_f64(const double (&val)[16], int n_valid, double
             return div_rn(add_rn(below, above), 2.0);
         }
     }
-    if (tid == 0) shu[16] = 0;
+    unsigned *gather_cnt = reinterpret_cast<unsigned *>(shd + 41);
+    if (tid == 0) *gather_cnt = 0;
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         if (val[i] >= lo && val[i] < hi) {
-            const unsigned pos = atomicAdd(&shu[16], 1u);
+            const unsigned pos = atomicAdd(gather_cnt, 1u);
             if (pos < 32u) shd[2 + pos] = val[i];
         }
     }
     __syncthreads();
-    const int cnt = (int)shu[16];
+    const int cnt = (int)*gather_cnt;
     if (warp == 0) {
         double med;
         if (cnt > 32) {
