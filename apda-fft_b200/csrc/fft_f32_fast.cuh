@@ -224,9 +224,17 @@ __device__ float select_median(const float2 (&v2)[16], int n_valid, uint32_t *sh
             if (!(pivot > lo)) pivot = lo_next;       // also catches NaN
             if (!(pivot < hi)) pivot = lo_next;
         }
-        int cnt = 0;
+        // count(v < pivot): the sign bit of v - pivot is exact (x - x = +0, differences of floats never round across 0),
+        // so one packed subtraction per value pair and one funnel shift per value collect 32 sign bits into a word
+        unsigned signs = 0;
+        const float2 pv = make_float2(pivot, pivot);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) cnt += (VAL(i) < pivot);
+        for (int i = 0; i < 16; ++i) {
+            const float2 d = csub(v2[i], pv);
+            signs = __funnelshift_l(__float_as_uint(d.x), signs, 1);
+            signs = __funnelshift_l(__float_as_uint(d.y), signs, 1);
+        }
+        int cnt = __popc(signs);
         cnt = __reduce_add_sync(0xffffffffu, cnt);  // REDUX: one instruction instead of a shuffle tree
         // one barrier per round: the per-warp partial counts alternate between two banks of slots
         uint32_t *cslot = sh + 40 + 8 * (round & 1);
