@@ -163,8 +163,9 @@ __device__ __forceinline__ float next_above(float v) {  // smallest float strict
 // the key space, which bounds the worst case).  When at most 32 values remain in the bracket one warp ranks them.
 // Exact for any input; the estimates only steer the pivots.  Padding slots (index >= n_valid) must hold +inf.
 // Returns statistics.median: the middle value (odd n) or the mean of the two middle values (even n).
-template <int T, bool FULL>
-__device__ float select_median(const float2 (&v2)[16], int n_valid, uint32_t *sh /* 64 words */, int t, int slot) {
+template <int T, bool FULL, typename Reload>
+__device__ float select_median(const float2 (&v2)[16], int n_valid, uint32_t *sh /* 64 words */, int t, int slot,
+                               Reload reload /* reload(q): value q (0..31) of this thread, re-read from memory */) {
 #define VAL(i) (((i) & 1) ? v2[(i) >> 1].y : v2[(i) >> 1].x)
     constexpr int NW = (T + 31) / 32;
     const int lane = t & 31, warp = t >> 5;
@@ -204,6 +205,14 @@ __device__ float select_median(const float2 (&v2)[16], int n_valid, uint32_t *sh
 
     float lo = -CUDART_INF_F, hi = CUDART_INF_F;  // bracket [lo, hi): c_lo = #(v < lo) <= r_lo, c_hi = #(v < hi) > r_hi
     int c_lo = 0, c_hi = n_valid;
+    // per-thread sign words of the rounds that set the bracket ends (bit 31-q: value q is below that end); their
+    // difference is the set of values inside the final bracket, so the gather needs no further comparisons
+    unsigned mask_lo = 0u, mask_hi = 0xffffffffu;
+    if (!FULL) {
+        mask_hi = 0u;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mask_hi = (mask_hi << 1) | (VAL(i) < CUDART_INF_F ? 1u : 0u);
+    }
     float pivot = mean;
     for (int round = 0;; ++round) {
         if (round > 0) {
@@ -246,9 +255,11 @@ __device__ float select_median(const float2 (&v2)[16], int n_valid, uint32_t *sh
         if (tot <= r_lo) {  // both middle order statistics are >= pivot
             lo = pivot;
             c_lo = tot;
+            mask_lo = signs;
         } else if (tot > r_hi) {  // both are < pivot
             hi = pivot;
             c_hi = tot;
+            mask_hi = signs;
         } else {
             // even n and the pivot separates the two middles: lower = max{v < pivot}, upper = min{v >= pivot}
             float below = -CUDART_INF_F, above = CUDART_INF_F;
@@ -279,12 +290,11 @@ __device__ float select_median(const float2 (&v2)[16], int n_valid, uint32_t *sh
     // <= 32 values in [lo, hi), or one distinct value: gather and rank inside each warp (every warp computes the same)
     if (t == 0) sh[16] = 0;
     group_sync<T>(slot);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        if (VAL(i) >= lo && VAL(i) < hi) {
-            const uint32_t pos = atomicAdd(&sh[16], 1u);
-            if (pos < 32u) shf[32 + pos] = VAL(i);
-        }
+    for (unsigned inb = ~mask_lo & mask_hi; inb; ) {  // at most 32 bits in the whole window (or one repeated value)
+        const int q = __clz(inb);
+        inb &= ~(0x80000000u >> q);
+        const uint32_t pos = atomicAdd(&sh[16], 1u);
+        if (pos < 32u) shf[32 + pos] = reload(q);
     }
     group_sync<T>(slot);
     const int cnt = (int)sh[16];
@@ -360,7 +370,12 @@ __device__ __forceinline__ void k1_forward(const float *__restrict__ samples, co
                     if (2 * zi + 1 >= n_samples) v[g * R1 + n1].y = CUDART_INF_F;
                 }
         }
-        shift = select_median<T, FULL>(v, n_samples, sel_w, t, wslot);
+        // value q of this thread = component q&1 of complex slot q>>1 = (g, n1) -> sample 2*(n1*S1 + t + T*g) + (q&1)
+        auto reload = [&](int q) {
+            const int j = q >> 1;
+            return __ldg(x + 2 * ((j % R1) * S1 + t + T * (j / R1)) + (q & 1));
+        };
+        shift = select_median<T, FULL>(v, n_samples, sel_w, t, wslot, reload);
         if (!full) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
