@@ -106,8 +106,12 @@ size_t peaks_large_workspace_bytes(int64_t n);
 template <typename T>
 int launch_peaks_large(apda_ctx *ctx, cudaStream_t st, const T *d_spec, int64_t n, int64_t batch, double fs,
                        const double *d_fs, int k, int rec_cap, int flexible, void *d_rec, void *ws);
-int launch_peaks_general_listed(apda_ctx *ctx, cudaStream_t st, const float *d_spec, int64_t n, int64_t batch, double fs,
+template <typename T>
+int launch_peaks_general_listed(apda_ctx *ctx, cudaStream_t st, const T *d_spec, int64_t n, int64_t batch, double fs,
                                 const double *d_fs, int k, int rec_cap, int flexible, void *d_rec, const int *list);
+bool peaks_f64_fast_supports(int64_t n, int k, int rec_cap);
+int launch_peaks_f64_fast(apda_ctx *ctx, cudaStream_t st, const double *d_spec, int64_t n, int64_t batch, double fs,
+                          const double *d_fs, int k, int flexible, void *d_rec);
 int launch_peaks_f32_fast(apda_ctx *ctx, cudaStream_t st, const float *d_spec, int64_t n, int64_t batch, double fs,
                           const double *d_fs, int k, int flexible, void *d_rec);
 int launch_center_f64(apda_ctx *ctx, cudaStream_t st, const double *d_in, int64_t n, double *d_out);

@@ -7,7 +7,7 @@
 // in memory.  This is a throughput variant: the drop-in start_fft contract (N bins materialised) stays with the
 // pipeline kernels, and results are reported under their own byte accounting (never mixed with B_alg numbers).
 #include "fft_f32_fast.cuh"
-#include "peaks_f32_fast.cuh"
+#include "peaks_fast.cuh"
 
 int fft_f32_fast_get_tables(apda_ctx *ctx, int64_t N, const float2 **tw1, const float2 **twu);
 
@@ -19,7 +19,7 @@ fused_f32_kernel(const float *__restrict__ samples, int n_samples, int64_t ld, i
                  const float2 *__restrict__ tw1, const float2 *__restrict__ twu, double df_all,
                  const double *__restrict__ d_fs, int k, unsigned char *__restrict__ recs, int *__restrict__ repair) {
     using P = Plan<N>;
-    using Q = K3<N / 2>;
+    using Q = K3<float, N / 2>;
     constexpr int M = N / 2, R1 = P::R1, R2 = P::R2, R3 = P::R3, T = M / 16;
     constexpr int S1 = R2 * R3, LD = S1 + 16 / R1;
     extern __shared__ __align__(16) unsigned char dyn_smem[];  // FFT buffer, then K3's per-window region
@@ -96,7 +96,7 @@ fused_f32_kernel(const float *__restrict__ samples, int n_samples, int64_t ld, i
     Slot *slots = reinterpret_cast<Slot *>(s);
     constexpr int kSlotCap = M / 5 + 8;
     static_assert(kSlotCap * sizeof(Slot) <= sizeof(float2) * R1 * LD, "slot list must fit the FFT buffer");
-    k3_tail<M, FLEX>(mags, slots, kSlotCap, rec_s, &nslot_s, sd, thr_f, df, k, lane, win, recs, repair);
+    k3_tail<float, M, FLEX>(mags, slots, kSlotCap, rec_s, &nslot_s, sd, thr_f, df, k, lane, win, recs, repair);
 }
 
 // this translation unit owns its own copy of the __constant__ pass-2 twiddles (anonymous namespace in the header)
@@ -146,7 +146,7 @@ int launch_fused_n(apda_ctx *ctx, cudaStream_t st, const float *d_samples, int64
     }
 #undef PICK
     using P = Plan<N>;
-    const size_t smem = sizeof(float2) * P::R1 * (P::R2 * P::R3 + 16 / P::R1) + K3<N / 2>::BYTES;
+    const size_t smem = sizeof(float2) * P::R1 * (P::R2 * P::R3 + 16 / P::R1) + K3<float, N / 2>::BYTES;
     APDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)batch, N / 32, smem, st>>>(d_samples, (int)n_samples, ld, batch, tw1, twu, fs / (double)N, d_fs, k,
                                             reinterpret_cast<unsigned char *>(d_rec), ctx->repair);

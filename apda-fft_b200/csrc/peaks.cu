@@ -352,10 +352,15 @@ static int launch_peaks_general(apda_ctx *ctx, cudaStream_t st, const T *d_spec,
     return APDA_OK;
 }
 
-int launch_peaks_general_listed(apda_ctx *ctx, cudaStream_t st, const float *d_spec, int64_t n, int64_t batch, double fs,
+template <typename T>
+int launch_peaks_general_listed(apda_ctx *ctx, cudaStream_t st, const T *d_spec, int64_t n, int64_t batch, double fs,
                                 const double *d_fs, int k, int rec_cap, int flexible, void *d_rec, const int *list) {
-    return launch_peaks_general<float>(ctx, st, d_spec, n, batch, fs, d_fs, k, rec_cap, flexible, d_rec, nullptr, list);
+    return launch_peaks_general<T>(ctx, st, d_spec, n, batch, fs, d_fs, k, rec_cap, flexible, d_rec, nullptr, list);
 }
+template int launch_peaks_general_listed<float>(apda_ctx *, cudaStream_t, const float *, int64_t, int64_t, double,
+                                                const double *, int, int, int, void *, const int *);
+template int launch_peaks_general_listed<double>(apda_ctx *, cudaStream_t, const double *, int64_t, int64_t, double,
+                                                 const double *, int, int, int, void *, const int *);
 
 template <typename T>
 int launch_peaks(apda_ctx *ctx, cudaStream_t st, const T *d_spec, int64_t n, int64_t batch, double fs,
@@ -363,6 +368,9 @@ int launch_peaks(apda_ctx *ctx, cudaStream_t st, const T *d_spec, int64_t n, int
     using V2 = typename vec2<T>::type;
     if (sizeof(T) == 4 && !ctx->generic_only && peaks_f32_fast_supports(n, k, rec_cap))
         return launch_peaks_f32_fast(ctx, st, reinterpret_cast<const float *>(d_spec), n, batch, fs, d_fs, k, flexible,
+                                     d_rec);
+    if (sizeof(T) == 8 && !ctx->generic_only && peaks_f64_fast_supports(n, k, rec_cap))
+        return launch_peaks_f64_fast(ctx, st, reinterpret_cast<const double *>(d_spec), n, batch, fs, d_fs, k, flexible,
                                      d_rec);
     if (peaks_large_supports(n) && !ctx->generic_only && d_mag_ws)
         return launch_peaks_large<T>(ctx, st, d_spec, n, batch, fs, d_fs, k, rec_cap, flexible, d_rec, d_mag_ws);

@@ -1,5 +1,5 @@
-// K3 (fp32 fast form): the pipeline kernel (spectrum in HBM -> records).  The algorithm lives in peaks_f32_fast.cuh.
-#include "peaks_f32_fast.cuh"
+// K3 (fp32 fast form): the pipeline kernel (spectrum in HBM -> records).  The algorithm lives in peaks_fast.cuh.
+#include "peaks_fast.cuh"
 
 namespace {
 
@@ -7,7 +7,7 @@ template <int HALF, bool FLEX>
 __global__ void __launch_bounds__(32 * kWPC)
 peaks_f32_fast_kernel(const float2 *__restrict__ spec, int64_t batch, double df_all, const double *__restrict__ d_fs,
                       int k, unsigned char *__restrict__ recs, int *__restrict__ repair) {
-    using P = K3<HALF>;
+    using P = K3<float, HALF>;
     constexpr int C = P::C;
     constexpr int N = 2 * HALF;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -58,14 +58,14 @@ peaks_f32_fast_kernel(const float2 *__restrict__ spec, int64_t batch, double df_
     const float thr_f = __double2float_rd(thr);  // for floats m:  m > thr  <=>  m > thr_f
     const double df = d_fs ? div_rn(d_fs[win], (double)N) : df_all;  // fs / n (host-side division when fs is shared)
     __syncwarp();
-    k3_tail<HALF, FLEX>(mags, slots, P::SLOTS, rec_s, &nslot_s[warp], sd, thr_f, df, k, lane, win, recs, repair);
+    k3_tail<float, HALF, FLEX>(mags, slots, P::SLOTS, rec_s, &nslot_s[warp], sd, thr_f, df, k, lane, win, recs, repair);
 }
 
 
 template <int HALF>
 int launch_half(apda_ctx *ctx, cudaStream_t st, const float *d_spec, int64_t batch, double fs, const double *d_fs,
                 int k, int flexible, void *d_rec) {
-    const int smem = kWPC * K3<HALF>::BYTES;
+    const int smem = kWPC * K3<float, HALF>::BYTES;
     auto kern = flexible ? peaks_f32_fast_kernel<HALF, true> : peaks_f32_fast_kernel<HALF, false>;
     APDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int64_t blocks = (batch + kWPC - 1) / kWPC;

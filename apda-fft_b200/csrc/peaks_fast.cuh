@@ -1,4 +1,5 @@
-// K3 (fp32 fast form) for n = 1024 / 2048 / 4096 / 8192 bins per window, k <= 5, 128-byte records: the headline picker.
+// K3 (fast form) for n = 1024 / 2048 / 4096 / 8192 bins per window, k <= 5, 128-byte records: the headline picker.
+// Templated on the magnitude type T: float (peaks_f32_fast.cu, fused_f32.cu) and double (peaks_f64_fast.cu).
 //
 // One WARP per window, four windows per CTA, no block-level barrier.
 //   phase 1  32 lanes stream the half spectrum with coalesced 128-bit loads (8 in flight per lane), take magnitudes,
@@ -24,23 +25,44 @@ namespace {
 
 constexpr int kWPC = 2;  // windows (warps) per CTA
 
-struct Slot {
+template <typename T>
+struct SlotT {
     uint16_t idx;
     uint16_t width;  // flexible: half-power bins if the candidate passed every gate, else 0
-    float prom;
+    T prom;
 };
+using Slot = SlotT<float>;
 
-template <int HALF>
+template <typename T, int HALF>
 struct K3 {
     static constexpr int C = HALF / 32;                // bins per lane chunk
-    static constexpr int MAGW = HALF + 4 * 32;         // magnitude words incl. 4-word pad per chunk
+    static constexpr int PAD = 16 / (int)sizeof(T);    // 16-byte pad per chunk: the lanes' 128-bit LDS are conflict free
+    static constexpr int MAGW = HALF + PAD * 32;       // magnitude elements incl. the pads
     static constexpr int SLOTS = 96;                   // candidates / hot bins kept on chip; more -> repair list (general kernel)
-    static constexpr int REC_OFF = MAGW * 4 + SLOTS * 8;
+    static constexpr int REC_OFF = MAGW * (int)sizeof(T) + SLOTS * (int)sizeof(SlotT<T>);
     static constexpr int BYTES = (REC_OFF + 128 + 15) & ~15;
-    __device__ static __forceinline__ int addr(int b) { return b + 4 * (b / C); }
-    // word offset of the 64-bin row R (R = r0 + u with r0 a multiple of 8: row_off is additive in that split)
-    __device__ static __forceinline__ int row_off(int R) { return 64 * R + (C <= 64 ? 4 * (64 / C) * R : 4 * (R / (C / 64))); }
+    __device__ static __forceinline__ int addr(int b) { return b + PAD * (b / C); }
+    // element offset of the 64-bin row R (R = r0 + u with r0 a multiple of 8: row_off is additive in that split)
+    __device__ static __forceinline__ int row_off(int R) { return 64 * R + (C <= 64 ? PAD * (64 / C) * R : PAD * (R / (C / 64))); }
 };
+
+// type-generic spellings of the few operations that differ between the two magnitude types
+__device__ __forceinline__ float vmin(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ float vmax(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double vmin(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ double vmax(double a, double b) { return fmax(a, b); }
+template <typename T>
+struct Quad {
+    T x, y, z, w;
+};
+__device__ __forceinline__ Quad<float> lds_quad(const float *p) {  // 4 consecutive magnitudes, 16-byte aligned
+    const float4 v = *reinterpret_cast<const float4 *>(p);
+    return {v.x, v.y, v.z, v.w};
+}
+__device__ __forceinline__ Quad<double> lds_quad(const double *p) {
+    const double2 a = reinterpret_cast<const double2 *>(p)[0], b = reinterpret_cast<const double2 *>(p)[1];
+    return {a.x, a.y, b.x, b.y};
+}
 
 __device__ __forceinline__ double round_dec4_d(double x) {  // exact emulation of Python round(x, 4); see peaks.cu
     const double p = 1e4;
@@ -53,9 +75,11 @@ __device__ __forceinline__ double round_dec4_d(double x) {  // exact emulation o
     return div_rn(n, p);
 }
 
-__device__ __forceinline__ float sqrt_fast(float x) {  // MUFU.SQRT: <= 1 ulp, far inside the fp32 path's 1e-5 contract
+// MUFU.SQRT: <= 1 ulp, far inside the fp32 path's 1e-5 contract.  .ftz: one instruction instead of the five of the
+// denormal-preserving form (a squared magnitude below 1.2e-38 - a bin below 1e-19 - counts as zero)
+__device__ __forceinline__ float sqrt_fast(float x) {
     float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 
@@ -89,13 +113,13 @@ __device__ __forceinline__ float4 ldg_stream(const float4 *p) {
 
 // one direction of the prominence walk inside [lo_b, hi_b] (a piece of one chunk), 32 bins per step.
 // DIR = -1: from hi_b downwards, +1: from lo_b upwards.  Returns true when a bin strictly higher than p stopped it.
-template <int HALF, int DIR>
-__device__ __forceinline__ bool scan_piece(const float *mags, int lo_b, int hi_b, float p, float &floor_lane, int lane) {
+template <typename T, int HALF, int DIR>
+__device__ __forceinline__ bool scan_piece(const T *mags, int lo_b, int hi_b, T p, T &floor_lane, int lane) {
     if (DIR < 0) {
         for (int base = hi_b; base >= lo_b; base -= 32) {
             const int i = base - lane;
             const bool valid = i >= lo_b;
-            const float v = valid ? mags[K3<HALF>::addr(i)] : p;
+            const T v = valid ? mags[K3<T, HALF>::addr(i)] : p;
             const unsigned higher = __ballot_sync(0xffffffffu, valid && v > p);
             const int stop = higher ? (__ffs(higher) - 1) : 32;
             if (lane < stop && v < floor_lane) floor_lane = v;
@@ -105,7 +129,7 @@ __device__ __forceinline__ bool scan_piece(const float *mags, int lo_b, int hi_b
         for (int base = lo_b; base <= hi_b; base += 32) {
             const int i = base + lane;
             const bool valid = i <= hi_b;
-            const float v = valid ? mags[K3<HALF>::addr(i)] : p;
+            const T v = valid ? mags[K3<T, HALF>::addr(i)] : p;
             const unsigned higher = __ballot_sync(0xffffffffu, valid && v > p);
             const int stop = higher ? (__ffs(higher) - 1) : 32;
             if (lane < stop && v < floor_lane) floor_lane = v;
@@ -116,68 +140,68 @@ __device__ __forceinline__ bool scan_piece(const float *mags, int lo_b, int hi_b
 }
 
 // utils/get_peak_prominence.py:32-54 on the chunk summaries (cmax/cmin: this lane's chunk maximum / minimum)
-template <int HALF>
-__device__ float coop_prominence(const float *mags, int j, float cmax, float cmin, int lane) {
-    constexpr int C = K3<HALF>::C;
-    const float p = mags[K3<HALF>::addr(j)];
+template <typename T, int HALF>
+__device__ T coop_prominence(const T *mags, int j, T cmax, T cmin, int lane) {
+    constexpr int C = K3<T, HALF>::C;
+    const T p = mags[K3<T, HALF>::addr(j)];
     const int cj = j / C;
     const unsigned above = __ballot_sync(0xffffffffu, cmax > p);
-    float fl = p, fr = p;
-    if (!scan_piece<HALF, -1>(mags, C * cj, j - 1, p, fl, lane)) {
+    T fl = p, fr = p;
+    if (!scan_piece<T, HALF, -1>(mags, C * cj, j - 1, p, fl, lane)) {
         const unsigned hl = above & ((1u << cj) - 1u);
         const int L = hl ? 31 - __clz(hl) : -1;
         if (lane > L && lane < cj && cmin < fl) fl = cmin;
-        if (L >= 0) scan_piece<HALF, -1>(mags, C * L, C * (L + 1) - 1, p, fl, lane);
+        if (L >= 0) scan_piece<T, HALF, -1>(mags, C * L, C * (L + 1) - 1, p, fl, lane);
     }
-    if (!scan_piece<HALF, +1>(mags, j + 1, C * (cj + 1) - 1, p, fr, lane)) {
+    if (!scan_piece<T, HALF, +1>(mags, j + 1, C * (cj + 1) - 1, p, fr, lane)) {
         const unsigned hr = above & ~((2u << cj) - 1u);
         const int R = hr ? __ffs(hr) - 1 : 32;
         if (lane > cj && lane < R && cmin < fr) fr = cmin;
-        if (R < 32) scan_piece<HALF, +1>(mags, C * R, C * (R + 1) - 1, p, fr, lane);
+        if (R < 32) scan_piece<T, HALF, +1>(mags, C * R, C * (R + 1) - 1, p, fr, lane);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        fl = fminf(fl, __shfl_xor_sync(0xffffffffu, fl, o));
-        fr = fminf(fr, __shfl_xor_sync(0xffffffffu, fr, o));
+        fl = vmin(fl, __shfl_xor_sync(0xffffffffu, fl, o));
+        fr = vmin(fr, __shfl_xor_sync(0xffffffffu, fr, o));
     }
-    return __fsub_rn(p, fmaxf(fl, fr));
+    return sub_rn(p, vmax(fl, fr));
 }
 
-template <int HALF>
-__device__ __forceinline__ int half_power_bins_f(const float *mags, float prom, int j) {
-    const float top = mags[K3<HALF>::addr(j)];
-    const float level = __fadd_rn(__fsub_rn(top, prom), __fmul_rn(prom, 0.707f));
+template <typename T, int HALF>
+__device__ __forceinline__ int half_power_bins_f(const T *mags, T prom, int j) {
+    const T top = mags[K3<T, HALF>::addr(j)];
+    const T level = add_rn(sub_rn(top, prom), mul_rn(prom, (T)0.707));
     int lo = j;
-    while (lo > 0 && mags[K3<HALF>::addr(lo)] > level) {
-        if (mags[K3<HALF>::addr(lo)] > top) break;
+    while (lo > 0 && mags[K3<T, HALF>::addr(lo)] > level) {
+        if (mags[K3<T, HALF>::addr(lo)] > top) break;
         --lo;
     }
     int hi = j;
-    while (hi < HALF - 1 && mags[K3<HALF>::addr(hi)] > level) {
-        if (mags[K3<HALF>::addr(hi)] > top) break;
+    while (hi < HALF - 1 && mags[K3<T, HALF>::addr(hi)] > level) {
+        if (mags[K3<T, HALF>::addr(hi)] > top) break;
         ++hi;
     }
     const int w = hi - lo;
     return w > 1 ? w : 1;
 }
 
-template <int HALF>
-__device__ __forceinline__ int half_height_bins_f(const float *mags, int j) {
-    const float level = __fmul_rn(0.707f, mags[K3<HALF>::addr(j)]);
+template <typename T, int HALF>
+__device__ __forceinline__ int half_height_bins_f(const T *mags, int j) {
+    const T level = mul_rn((T)0.707, mags[K3<T, HALF>::addr(j)]);
     int lo = j;
-    while (lo > 0 && mags[K3<HALF>::addr(lo)] > level) --lo;
+    while (lo > 0 && mags[K3<T, HALF>::addr(lo)] > level) --lo;
     int hi = j;
-    while (hi < HALF && mags[K3<HALF>::addr(hi)] > level) ++hi;
+    while (hi < HALF && mags[K3<T, HALF>::addr(hi)] > level) ++hi;
     return hi - lo;
 }
 
 // The reference sorts the gated candidates by round(mag, 4) descending (stable: ties keep ascending idx) and walks that
 // order with the greedy "hump" exclusion.  Each lane owns PER slots; a slot's place in the order is its rank (number of
 // passing slots that precede it), computed once with shuffles.  Accepted peaks go straight into the record.
-template <int HALF, int PER>
-__device__ __forceinline__ int order_and_exclude(const Slot *slots, int nslot, const float *mags, unsigned char *rec_s,
+template <typename T, int HALF, int PER>
+__device__ __forceinline__ int order_and_exclude(const SlotT<T> *slots, int nslot, const T *mags, unsigned char *rec_s,
                                                  double df, int k, int lane) {
-    using P = K3<HALF>;
+    using P = K3<T, HALF>;
     double key[PER];
     int sidx[PER], srank[PER];
     unsigned passm[PER];
@@ -212,8 +236,8 @@ __device__ __forceinline__ int order_and_exclude(const Slot *slots, int nslot, c
             if (hit) e_sel = (__ffs(hit) - 1) + 32 * r;
         }
         const int c_idx = slots[e_sel].idx;
-        const float cprom = slots[e_sel].prom;
-        const float cmag = mags[P::addr(c_idx)];
+        const T cprom = slots[e_sel].prom;
+        const T cmag = mags[P::addr(c_idx)];
         bool hump = false;
         for (int a = 0; a < na && !hump; ++a) {
             const int ja = reinterpret_cast<const int *>(rec_s + 8 + 24 * a)[0];
@@ -242,10 +266,10 @@ __device__ __forceinline__ int order_and_exclude(const Slot *slots, int nslot, c
 
 // Same order / exclusion for any number of slots (only reached with > 96 gated candidates, i.e. noise-like windows in
 // the fused kernel, whose slot list lives in the free FFT buffer): extract the order one element at a time.
-template <int HALF>
-__device__ int order_and_exclude_any(const Slot *slots, int nslot, const float *mags, unsigned char *rec_s, double df,
+template <typename T, int HALF>
+__device__ int order_and_exclude_any(const SlotT<T> *slots, int nslot, const T *mags, unsigned char *rec_s, double df,
                                      int k, int lane) {
-    using P = K3<HALF>;
+    using P = K3<T, HALF>;
     double prev_key = CUDART_INF;
     int prev_idx = -1, na = 0;
     while (na < k) {
@@ -276,8 +300,8 @@ __device__ int order_and_exclude_any(const Slot *slots, int nslot, const float *
         if (best_e < 0) break;
         prev_key = best;
         prev_idx = best_idx;
-        const float cprom = slots[best_e].prom;
-        const float cmag = mags[P::addr(best_idx)];
+        const T cprom = slots[best_e].prom;
+        const T cmag = mags[P::addr(best_idx)];
         bool hump = false;
         for (int a = 0; a < na && !hump; ++a) {
             const int ja = reinterpret_cast<const int *>(rec_s + 8 + 24 * a)[0];
@@ -301,31 +325,32 @@ __device__ int order_and_exclude_any(const Slot *slots, int nslot, const float *
 
 // Everything after the magnitudes are in shared memory: hot-bin list, picker, record.  Shared by the pipeline kernel
 // (peaks_f32_fast.cu) and the fused window->record kernel (fused_f32.cu).  Runs on ONE warp.
-template <int HALF, bool FLEX>
-__device__ __forceinline__ void k3_tail(float *mags, Slot *slots, const int slot_cap, unsigned char *rec_s,
+// thr_f: largest T with  m > thr  <=>  m > thr_f  for every magnitude m (the threshold itself when T is double).
+template <typename T, int HALF, bool FLEX>
+__device__ __forceinline__ void k3_tail(T *mags, SlotT<T> *slots, const int slot_cap, unsigned char *rec_s,
                                         int *nslot_ptr, const double sd,
-                                        const float thr_f, const double df, const int k, const int lane,
+                                        const T thr_f, const double df, const int k, const int lane,
                                         const int64_t win, unsigned char *__restrict__ recs, int *__restrict__ repair) {
-    using P = K3<HALF>;
+    using P = K3<T, HALF>;
     constexpr int C = P::C;
     // ---- phase 2: contiguous chunk per lane: chunk max/min, hot bins -> slot list -------------------------------------
-    float cmax = -CUDART_INF_F, cmin = CUDART_INF_F;
+    T cmax = -(T)CUDART_INF_F, cmin = (T)CUDART_INF_F;
     {
-        const float4 *ch = reinterpret_cast<const float4 *>(mags + P::addr(C * lane));
-        unsigned hotq = 0;  // bit q: the q-th float4 of this chunk holds a bin above the threshold (C/4 <= 32 groups)
+        const T *ch = mags + P::addr(C * lane);
+        unsigned hotq = 0;  // bit q: the q-th group of 4 bins of this chunk holds a bin above the threshold (C/4 <= 32 groups)
 #pragma unroll
         for (int q = 0; q < C / 4; ++q) {
-            const float4 v = ch[q];
-            const float m4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
-            cmax = fmaxf(cmax, m4);
-            cmin = fminf(cmin, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
+            const Quad<T> v = lds_quad(ch + 4 * q);
+            const T m4 = vmax(vmax(v.x, v.y), vmax(v.z, v.w));
+            cmax = vmax(cmax, m4);
+            cmin = vmin(cmin, vmin(vmin(v.x, v.y), vmin(v.z, v.w)));
             if (m4 > thr_f) hotq |= 1u << q;
         }
         while (hotq) {  // rare: a handful of bins per window
             const int q = __ffs(hotq) - 1;
             hotq &= hotq - 1;
-            const float4 v = ch[q];
-            const float e[4] = {v.x, v.y, v.z, v.w};
+            const Quad<T> v = lds_quad(ch + 4 * q);
+            const T e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 if (e[u] > thr_f) {
@@ -355,7 +380,7 @@ __device__ __forceinline__ void k3_tail(float *mags, Slot *slots, const int slot
         // ---- A: cooperative prominence per candidate -----------------------------------------------------------------
         for (int c = 0; c < nslot; ++c) {
             const int j = slots[c].idx;
-            const float prom = coop_prominence<HALF>(mags, j, cmax, cmin, lane);
+            const T prom = coop_prominence<T, HALF>(mags, j, cmax, cmin, lane);
             if (lane == 0) slots[c].prom = prom;
         }
         __syncwarp();
@@ -363,10 +388,10 @@ __device__ __forceinline__ void k3_tail(float *mags, Slot *slots, const int slot
         const double half_sd = mul_rn(0.5, sd);
         for (int c = lane; c < nslot; c += 32) {
             const int j = slots[c].idx;
-            const float prom = slots[c].prom;
+            const T prom = slots[c].prom;
             int width = 0;
             if ((double)prom > half_sd) {
-                const int bins = half_power_bins_f<HALF>(mags, prom, j);
+                const int bins = half_power_bins_f<T, HALF>(mags, prom, j);
                 const double width_hz = mul_rn((double)bins, df);
                 if (width_hz > 0.0) {
                     const double fn = mul_rn((double)j, df);
@@ -385,9 +410,9 @@ __device__ __forceinline__ void k3_tail(float *mags, Slot *slots, const int slot
         }
         __syncwarp();
         // ---- C: order "descending round(mag,4), ascending idx" (stable sort of the reference), greedy hump exclusion ------
-        na = nslot <= 32   ? order_and_exclude<HALF, 1>(slots, nslot, mags, rec_s, df, k, lane)
-             : nslot <= 96 ? order_and_exclude<HALF, 3>(slots, nslot, mags, rec_s, df, k, lane)
-                           : order_and_exclude_any<HALF>(slots, nslot, mags, rec_s, df, k, lane);
+        na = nslot <= 32   ? order_and_exclude<T, HALF, 1>(slots, nslot, mags, rec_s, df, k, lane)
+             : nslot <= 96 ? order_and_exclude<T, HALF, 3>(slots, nslot, mags, rec_s, df, k, lane)
+                           : order_and_exclude_any<T, HALF>(slots, nslot, mags, rec_s, df, k, lane);
         if (lane == 0) {
             reinterpret_cast<int *>(rec_s)[0] = na;
             reinterpret_cast<int *>(rec_s)[1] = status;
@@ -400,11 +425,11 @@ __device__ __forceinline__ void k3_tail(float *mags, Slot *slots, const int slot
         for (int a = 0; a < 5; ++a) acc_idx[a] = -1;
         __syncwarp();
         while (na < k) {
-            float bm = -1.f;
+            T bm = (T)-1;
             int bj = -1;
             for (int e = lane; e < nslot; e += 32) {
                 const int j = slots[e].idx;
-                const float m = mags[P::addr(j)];
+                const T m = mags[P::addr(j)];
                 if (j >= 1 && j <= HALF - 2 && m > thr_f && m > mags[P::addr(j - 1)] && m > mags[P::addr(j + 1)] &&
                     (m > bm || (m == bm && j < bj))) {
                     bm = m;
@@ -413,7 +438,7 @@ __device__ __forceinline__ void k3_tail(float *mags, Slot *slots, const int slot
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                const float m2 = __shfl_xor_sync(0xffffffffu, bm, o);
+                const T m2 = __shfl_xor_sync(0xffffffffu, bm, o);
                 const int j2 = __shfl_xor_sync(0xffffffffu, bj, o);
                 if (j2 >= 0 && (bj < 0 || m2 > bm || (m2 == bm && j2 < bj))) {
                     bm = m2;
@@ -421,14 +446,14 @@ __device__ __forceinline__ void k3_tail(float *mags, Slot *slots, const int slot
                 }
             }
             if (bj < 0) break;
-            const int w2 = half_height_bins_f<HALF>(mags, bj);
+            const int w2 = half_height_bins_f<T, HALF>(mags, bj);
             bool separated = true;
 #pragma unroll
             for (int a = 0; a < 5; ++a) {
                 if (a < na && separated) {
                     // an accepted peak's own bin was zeroed when it was found, so its half-height width is 0 (the
                     // reference's resolution() degenerates to 1.18*dist/w_candidate); walk only if that ever fails
-                    const int w1 = mags[P::addr(acc_idx[a])] == 0.f ? 0 : half_height_bins_f<HALF>(mags, acc_idx[a]);
+                    const int w1 = mags[P::addr(acc_idx[a])] == (T)0 ? 0 : half_height_bins_f<T, HALF>(mags, acc_idx[a]);
                     bool ok = false;
                     if (w1 + w2 != 0) {
                         const double num = mul_rn(1.18, (double)abs(bj - acc_idx[a])), den = 1.5 * (double)(w1 + w2);
@@ -467,7 +492,7 @@ __device__ __forceinline__ void k3_tail(float *mags, Slot *slots, const int slot
             const int reach = (int)reach_d;
             const int z0 = max(0, bj - reach), z1 = min(HALF, bj + reach + 1);
             __syncwarp();
-            for (int b = z0 + lane; b < z1; b += 32) mags[P::addr(b)] = 0.f;
+            for (int b = z0 + lane; b < z1; b += 32) mags[P::addr(b)] = (T)0;
             __syncwarp();
         }
         if (lane == 0) {

@@ -82,14 +82,43 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "configs.json"))
     ap.add_argument("--max-log2n", type=int, default=24)
+    ap.add_argument("--only", default="", help="comma-separated subset of cfg1,cfg2,cfg3,cfg4,cfg5,ingest")
     args = ap.parse_args()
+    only = set(filter(None, args.only.split(",")))
+
+    def want(name):
+        return not only or name in only
     dev = torch.device("cuda:0")
     torch.cuda.set_device(0)
     an = apda_fft_b200.Analyzer(0)
     an.use_stream(torch.cuda.current_stream(dev).cuda_stream)
     out = {"peak_gbs": PEAK, "gpu": torch.cuda.get_device_name(0)}
 
-    # cfg1: drop-in modules, one 3-axis sensor (three independent single-axis windows, N=1024, fp64)
+    if want("cfg1"):
+        cfg1(out)
+    if want("cfg2"):
+        out["cfg2"] = batch_config(an, dev, 10_000, 4096, "f64", True)[0]
+    if want("cfg3"):
+        cfg3(an, dev, out)
+    if want("cfg4"):
+        cfg4(an, dev, out, args.max_log2n)
+    if want("cfg5"):
+        # per-kernel split, both centring modes
+        for name, center in (("cfg5_median", _cabi.CENTER_MEDIAN), ("cfg5_mean", _cabi.CENTER_MEAN)):
+            out[name] = batch_config(an, dev, 1_000_000, 4096, "f32", True, center=center)[0]
+            torch.cuda.empty_cache()
+        out["cfg5_rigid_median"] = batch_config(an, dev, 1_000_000, 4096, "f32", False)[0]
+    if want("ingest"):
+        ingest_rows(an, out)
+
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    with open(args.out, "w") as fh:
+        json.dump(out, fh, indent=1)
+    print(json.dumps(out, indent=1))
+
+
+def cfg1(out):
+    # drop-in modules, one 3-axis sensor (three independent single-axis windows, N=1024, fp64)
     from metrics.fft_iterativa import start_fft
     from utils.get_peak_prominence import get_top_peaks_prominence
     axes = [apda_fft_b200.synth.fleet_window(w, 1024).tolist() for w in range(3)]
@@ -103,10 +132,10 @@ def main():
                    "ms_per_3axis_window": (time.perf_counter() - t0) / reps * 1e3,
                    "idx": [[p["idx"] for p in pk] for pk in peaks]}
 
-    # cfg2
-    r, _, _ = batch_config(an, dev, 10_000, 4096, "f64", True)
-    out["cfg2"] = r
-    # cfg3 (+ tolerance report)
+
+
+def cfg3(an, dev, out):
+    # 100k x 8192 rigid, fp32 and fp64 (+ tolerance report)
     r32, rec32, d_x32 = batch_config(an, dev, 100_000, 8192, "f32", False)
     x64 = d_x32.double()
     del d_x32
@@ -128,10 +157,13 @@ def main():
     del x64, d_spec, d_rec
     torch.cuda.empty_cache()
 
-    # cfg4: large single transforms
+
+
+def cfg4(an, dev, out, max_log2n):
+    # large single transforms
     cfg4 = []
     for log2n in (20, 22, 24):
-        if log2n > args.max_log2n:
+        if log2n > max_log2n:
             continue
         n = 1 << log2n
         for dtype, tdt, s in (("f64", torch.float64, 8), ("f32", torch.float32, 4)):
@@ -153,14 +185,9 @@ def main():
             torch.cuda.empty_cache()
     out["cfg4"] = cfg4
 
-    # cfg5 per-kernel split, both centring modes
-    for name, center in (("cfg5_median", _cabi.CENTER_MEDIAN), ("cfg5_mean", _cabi.CENTER_MEAN)):
-        r, _, _ = batch_config(an, dev, 1_000_000, 4096, "f32", True, center=center)
-        out[name] = r
-        torch.cuda.empty_cache()
-    r, _, _ = batch_config(an, dev, 1_000_000, 4096, "f32", False)
-    out["cfg5_rigid_median"] = r
 
+
+def ingest_rows(an, out):
     # ingest rows: text logs and 16-bit wire samples -> records, host buffers in, records out
     import ctypes
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -197,11 +224,6 @@ def main():
                     float(tok); cnt += 1
     ingest["python_float_parse_logs_per_s_per_core"] = 3 / (time.perf_counter() - t0)
     out["ingest"] = ingest
-
-    os.makedirs(os.path.dirname(args.out), exist_ok=True)
-    with open(args.out, "w") as fh:
-        json.dump(out, fh, indent=1)
-    print(json.dumps(out, indent=1))
 
 
 if __name__ == "__main__":

@@ -405,6 +405,39 @@ def test_f64_fast_kernel_bit_exact_incl_median_and_padding(n_fft, an):
     assert np.array_equal(fast.view(np.float64), slow.view(np.float64))
 
 
+@pytest.mark.parametrize("n", [1024, 2048, 4096, 8192])
+def test_f64_fast_picker_equals_general_and_oracle(n, an):
+    """Warp-per-window fp64 K3 vs the general CTA-per-window kernel: byte-identical records on tone, noise and
+    heavy-tailed spectra (both pickers), and the oracle's dicts on a sample; covers zero / huge / tiny / subnormal bins
+    (full-range hypot path) and the candidate-list overflow hand-over (noise windows)."""
+    import apda_fft_b200.synth as synth
+    rng = np.random.default_rng(n + 3)
+    tones = an.fft(synth.fleet_windows(500, 96, n))
+    noise = an.fft(np.stack([synth.noise_window(w, n) for w in range(24)]))
+    spiky = _real_spiky_spectra(rng, 48, n).astype(np.complex128)
+    spiky[:, : n // 2] *= np.exp(1j * rng.uniform(0, 6.28, (48, n // 2)))
+    odd = spiky[:8].copy()
+    odd[0, 5:40] = 0.0                       # exact zeros (glibc: ax >= ay / EPS shortcut)
+    odd[1, 7] = 1e300 + 1e300j               # scaled-down branch
+    odd[2, 9:200] *= 1e-300                  # scaled-up branch
+    odd[3, 11] = 5e-324 + 3e-320j            # subnormals
+    odd[4, 13] = 1.0 + 1e-20j                # ay negligible
+    odd[5, 100:110] = 3.0 + 4.0j             # plateau: equal magnitudes are never peaks
+    for z, check in ((tones, 16), (noise, 4), (spiky, 12), (odd, 8)):
+        for flexible in (True, False):
+            fast = an.peaks(z, 125.0, flexible=flexible)
+            an.ctx.set_generic_only(True)
+            try:
+                slow = an.peaks(z, 125.0, flexible=flexible)
+            finally:
+                an.ctx.set_generic_only(False)
+            assert fast.tobytes() == slow.tobytes(), (n, flexible)
+            for w in range(check):
+                zl = z[w].tolist()
+                want = ref_port.top_peaks_prominence(zl, 125.0) if flexible else ref_port.top_peaks_resolution(zl, 125.0)
+                assert _dicts(fast[w], 125.0, n, flexible) == want, (n, flexible, w)
+
+
 def test_fft_large_tma_equals_plain_tail_passes(an):
     """K2 tail passes: the TMA-staged kernel and the plain-load kernel give the same bits (fp64 and fp32)."""
     rng = np.random.default_rng(11)
