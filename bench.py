@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--center", choices=["median", "mean"], default="median")
     ap.add_argument("--e2e-windows", type=int, default=131072, help="windows per GPU of the host-buffer (e2e) leg")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--gather-slices", type=int, default=8,
+                    help="N>1: sub-batches per step whose record gather overlaps the next sub-batch's compute")
     ap.add_argument("--cpu-seconds", type=float, default=60.0, help="CPU work budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -141,7 +143,8 @@ def workload_config(args, world):
         "workload": f"fleet sweep: {args.windows} windows/GPU x N={args.n} {args.dtype}, {args.picker} picker "
                     f"(k={'4' if args.picker == 'flexible' else '5'}), K1 FFT + K3 peaks + gather of 128 B records",
         "windows_per_gpu": args.windows, "n_fft": args.n, "picker": args.picker, "centering": args.center,
-        "parallelism": f"batch-sharded x{world}, records gathered to rank 0",
+        "parallelism": f"batch-sharded x{world}, records gathered to rank 0"
+                       + (f" in {args.gather_slices} slices overlapped with compute" if world > 1 else ""),
         "l2": "inputs (windows*N*s bytes) and spectra far exceed the 126 MB L2; no flush needed",
     }
 
@@ -224,7 +227,7 @@ def run_ours(args):
 
     import apda_fft_b200
     from apda_fft_b200 import _cabi
-    from apda_fft_b200.fleet import gather_records
+    from apda_fft_b200.fleet import RecordGatherer, gather_records
     from apda_fft_b200.records import record_dtype
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -254,20 +257,24 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     k1_events = []
+    # N > 1: the shard is analysed in a few slices and the records of each slice travel to rank 0 (NCCL, its own
+    # stream) while the next slice is computed; only the last slice's transfer is exposed.  N = 1: one slice.
+    gatherer = RecordGatherer(b, 128, dev)
+    slices = gatherer.slices(args.gather_slices)
 
     def step(record_k1: bool, center=center, flexible=flexible, events=k1_events):
-        if record_k1:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-        an.fft_device(d_x.data_ptr(), b, n, n, args.dtype, d_spec.data_ptr(), center=center)
-        if record_k1:
-            e1.record(stream)
-            events.append((e0, e1))
-        an.peaks_device(d_spec.data_ptr(), b, n, args.dtype, fs, d_rec.data_ptr(), flexible=flexible,
-                        k=4 if flexible else 5, rec_cap=5)
-        if world > 1:
-            return gather_records(d_rec, b * world, dst=0)
-        return d_rec
+        for lo, hi in slices:
+            if record_k1:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+            an.fft_device(d_x[lo:].data_ptr(), hi - lo, n, n, args.dtype, d_spec[lo:].data_ptr(), center=center)
+            if record_k1:
+                e1.record(stream)
+                events.append((e0, e1))
+            an.peaks_device(d_spec[lo:].data_ptr(), hi - lo, n, args.dtype, fs, d_rec[lo:].data_ptr(), flexible=flexible,
+                            k=4 if flexible else 5, rec_cap=5)
+            gatherer.start(d_rec, lo, hi)
+        return gatherer.finish()
 
     def fence():
         if world > 1:
@@ -291,7 +298,7 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     launches = an.launch_count() - launches0
     elapsed_ms = t_start.elapsed_time(t_stop)
-    k1_ms = sum(a.elapsed_time(z) for a, z in k1_events) / max(len(k1_events), 1)
+    k1_ms = sum(a.elapsed_time(z) for a, z in k1_events) / max(args.steps, 1)   # all K1 launches of one step
     red = torch.tensor([elapsed_ms, k1_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
@@ -309,7 +316,7 @@ def run_ours(args):
             step(True, v_center, v_flexible, ev)
         z.record(stream)
         fence()
-        vals = torch.tensor([a.elapsed_time(z), sum(p.elapsed_time(q) for p, q in ev) / max(len(ev), 1)],
+        vals = torch.tensor([a.elapsed_time(z), sum(p.elapsed_time(q) for p, q in ev) / max(args.steps, 1)],
                             dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(vals, op=dist.ReduceOp.MAX)
@@ -437,7 +444,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, world),
             "roofline": {"bound": "hbm", "kernel": "K1 fft (samples -> N complex bins)", "achieved": k1_gbs,
                          "peak": peak, "unit": "GB/s", "frac": k1_gbs / peak, "peak_source": peak_src,
-                         "bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms,
+                         "bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms, "launches_per_step": len(slices),
                          "traffic": ncu_traffic(f"k1_{args.dtype}_n{n}", b),
                          "traffic_source": "profiles/traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per window x windows per launch)"},
             "pipeline": {"b_alg_bytes_per_window": 4 * s_bytes * n + 128,

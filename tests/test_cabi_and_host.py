@@ -100,6 +100,17 @@ def _gloo_worker(rank, world, port, total, tmp):
         np.save(os.path.join(tmp, "table.npy"), table.numpy())
     else:
         assert table is None
+    # the sliced, overlapped gather used by the fleet sweep gives the same table (two consecutive steps reuse it)
+    from apda_fft_b200.fleet import RecordGatherer
+    g = RecordGatherer(shard_capacity(total, world), 128, local.device)
+    for _ in range(2):
+        for a, z in g.slices(3):
+            g.start(local, a, z)
+        sliced = g.finish()
+        if rank == 0:
+            assert np.array_equal(sliced[:total].numpy(), table.numpy())
+        else:
+            assert sliced is None
     dist.barrier()
     dist.destroy_process_group()
 
