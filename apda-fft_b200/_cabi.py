@@ -69,6 +69,12 @@ SIGNATURES = {
     "apda_half_height_bins_f64_host": (_int, [_p, _p, _i64, _i64, _c.POINTER(_i64)]),
     "apda_synth_f64_dev": (_int, [_p, _i64, _i64, _i64, _u64, _int, _p]),
     "apda_synth_f32_dev": (_int, [_p, _i64, _i64, _i64, _u64, _int, _p]),
+    "apda_peer_table_create": (_int, [_p, _i64, _c.POINTER(_p), _p]),
+    "apda_peer_table_open": (_int, [_p, _p, _c.POINTER(_p)]),
+    "apda_peer_table_close": (_int, [_p, _p]),
+    "apda_peer_table_destroy": (_int, [_p, _p]),
+    "apda_peer_signal": (_int, [_p, _p, _c.c_uint32]),
+    "apda_peer_wait": (_int, [_p, _p, _int, _c.c_uint32, _dbl, _p]),
 }
 
 

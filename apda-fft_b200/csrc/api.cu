@@ -1005,3 +1005,95 @@ extern "C" int apda_synth_f32_dev(apda_ctx *ctx, int64_t first_window, int64_t c
     APDA_CUDA(cudaSetDevice(ctx->device));
     return launch_synth<float>(ctx, ctx->stream, first_window, count, N, seed, on_bin, d_out);
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// fleet record table in peer memory: rank 0 owns one table for the whole fleet; every other rank maps it
+// through CUDA IPC and its K3 kernels store their 128-byte records straight into their rows over NVLink - the
+// "gather" is fused into the producing kernel's epilogue store and needs no collective, no staging copy and no SMs.
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int apda_peer_table_create(apda_ctx *ctx, int64_t bytes, void **d_table, unsigned char *handle64) {
+    if (!ctx || !d_table || !handle64 || bytes <= 0) return APDA_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
+    APDA_CUDA(cudaSetDevice(ctx->device));
+    void *p = nullptr;
+    APDA_CUDA(cudaMalloc(&p, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return apda_cuda_fail(e, "cudaIpcGetMemHandle");
+    }
+    memcpy(handle64, &h, 64);
+    *d_table = p;
+    return APDA_OK;
+}
+extern "C" int apda_peer_table_open(apda_ctx *ctx, const unsigned char *handle64, void **d_table) {
+    if (!ctx || !d_table || !handle64) return APDA_ERR_INVALID;
+    APDA_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void *p = nullptr;
+    APDA_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *d_table = p;
+    return APDA_OK;
+}
+extern "C" int apda_peer_table_close(apda_ctx *ctx, void *d_table) {
+    if (!ctx || !d_table) return APDA_ERR_INVALID;
+    APDA_CUDA(cudaSetDevice(ctx->device));
+    APDA_CUDA(cudaIpcCloseMemHandle(d_table));
+    return APDA_OK;
+}
+extern "C" int apda_peer_table_destroy(apda_ctx *ctx, void *d_table) {
+    if (!ctx || !d_table) return APDA_ERR_INVALID;
+    APDA_CUDA(cudaSetDevice(ctx->device));
+    APDA_CUDA(cudaFree(d_table));
+    return APDA_OK;
+}
+
+// Completion flags of the peer table: one 32-bit step counter per rank, living in the owner's memory next to the rows.
+// A producer rank enqueues apda_peer_signal after its pickers (release at system scope: the records it stored over
+// NVLink are visible before the flag), the owner enqueues apda_peer_wait (acquire) before it consumes the table - the
+// whole exchange stays on the device timelines, no host synchronisation, no collective.
+namespace {
+__global__ void peer_signal_kernel(unsigned *flag, unsigned value) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+__global__ void peer_wait_kernel(const unsigned *flags, int world, unsigned value, long long timeout_cycles,
+                                 int *timed_out) {
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    const long long t0 = clock64();
+    while (true) {
+        unsigned v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
+        if ((int)(v - value) >= 0) break;
+        if (clock64() - t0 > timeout_cycles) {  // a peer died: never hang the device
+            *timed_out = 1;
+            break;
+        }
+        __nanosleep(200);
+    }
+}
+}  // namespace
+
+extern "C" int apda_peer_signal(apda_ctx *ctx, void *d_flag, uint32_t value) {
+    if (!ctx || !d_flag) return APDA_ERR_INVALID;
+    APDA_CUDA(cudaSetDevice(ctx->device));
+    peer_signal_kernel<<<1, 1, 0, ctx->stream>>>(reinterpret_cast<unsigned *>(d_flag), value);
+    ctx->launches++;
+    APDA_CUDA(cudaGetLastError());
+    return APDA_OK;
+}
+extern "C" int apda_peer_wait(apda_ctx *ctx, const void *d_flags, int world, uint32_t value, double timeout_s,
+                              int *d_timed_out) {
+    if (!ctx || !d_flags || !d_timed_out || world < 1 || world > 32) return APDA_ERR_INVALID;
+    APDA_CUDA(cudaSetDevice(ctx->device));
+    int khz = 0;
+    APDA_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device));
+    peer_wait_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const unsigned *>(d_flags), world, value,
+                                               (long long)(timeout_s * 1e3 * (double)khz), d_timed_out);
+    ctx->launches++;
+    APDA_CUDA(cudaGetLastError());
+    return APDA_OK;
+}

@@ -92,3 +92,103 @@ class RecordGatherer:
         if not self.active:
             return self.local
         return self.table
+
+
+class PeerRecordTable:
+    """The fleet's record table in the destination rank's HBM, mapped into every rank (CUDA IPC over NVLink).
+
+    Rank ``dst`` allocates ``world * per`` records; the others open the allocation and hand
+    ``table + rank * per * rec_bytes`` to the pickers as their record pointer, so the K3 kernels' own 128-byte epilogue
+    stores land in the owner's memory: the gather of SURVEY 8(e) fused into the producing kernel, with no collective,
+    no staging copy and no SM time.  ``torch.distributed`` only carries the 64-byte handle and the barriers.
+
+        t = PeerRecordTable(analyzer.ctx, per, 128, device)       # once (collective: every rank calls it)
+        ... an.peaks_device(..., d_rec=t.local_ptr, ...) ...      # every step, any number of launches
+        table = t.complete()                                      # stream sync + barrier; rank dst: uint8 [world*per, rec_bytes]
+        t.close()
+    """
+
+    def __init__(self, ctx, per: int, rec_bytes: int, device, dst: int = 0, group=None):
+        import ctypes
+
+        import torch
+        import torch.distributed as dist
+        self.ctx, self.per, self.rec_bytes, self.dst, self.group = ctx, per, rec_bytes, dst, group
+        self.device = device
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.owner = self.rank == dst
+        self.nbytes = self.world * per * rec_bytes
+        self.flags_off = (self.nbytes + 255) & ~255          # one uint32 step counter per rank, then a time-out word
+        base = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        if self.owner:
+            ctx.call("apda_peer_table_create", ctypes.c_int64(self.flags_off + 256), ctypes.byref(base), handle)
+        if self.world > 1:
+            h = torch.tensor(list(handle), dtype=torch.uint8, device=device)
+            dist.broadcast(h, src=dst, group=group)
+            if not self.owner:
+                raw = (ctypes.c_ubyte * 64)(*h.cpu().tolist())
+                ctx.call("apda_peer_table_open", raw, ctypes.byref(base))
+        self.base = int(base.value)
+        self.local_ptr = self.base + self.rank * per * rec_bytes
+        self._closed = False
+        if self.owner:  # counters start at 0
+            view = self._raw(self.flags_off, 256)
+            view.zero_()
+            torch.cuda.synchronize(device)
+        if self.world > 1:
+            dist.barrier(group=group)
+
+    def row_ptr(self, row: int) -> int:
+        """Device pointer of local row ``row`` (for sub-batch launches)."""
+        return self.local_ptr + row * self.rec_bytes
+
+    def _raw(self, offset: int, nbytes: int):
+        import torch
+
+        class _Mem:  # the allocation belongs to libapda_b200, torch only views it
+            pass
+        m = _Mem()
+        m.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (self.base + offset, False),
+                                      "version": 3, "strides": None}
+        return torch.as_tensor(m, device=self.device)
+
+    def _tensor(self):
+        return self._raw(0, self.nbytes).view(self.world * self.per, self.rec_bytes)
+
+    def signal(self, step: int):
+        """Enqueue (after this rank's pickers, same stream): publish `step` - my rows of this step are in the table."""
+        import ctypes
+        self.ctx.call("apda_peer_signal", ctypes.c_void_p(self.base + self.flags_off + 4 * self.rank), int(step) & 0xffffffff)
+
+    def wait(self, step: int, timeout_s: float = 5.0):
+        """Owner only: hold the stream until every rank has published `step`; returns the table view."""
+        import ctypes
+        assert self.owner
+        self.ctx.call("apda_peer_wait", ctypes.c_void_p(self.base + self.flags_off), self.world, int(step) & 0xffffffff,
+                      float(timeout_s), ctypes.c_void_p(self.base + self.flags_off + 128))
+        return self._tensor()
+
+    def timed_out(self) -> bool:
+        """Owner only (synchronises): did any wait give up?"""
+        return bool(self._raw(self.flags_off + 128, 4).view(-1).cpu().numpy().view("int32")[0])
+
+    def complete(self):
+        """Every rank: wait for the local stream's kernels, then a process barrier; the owner gets the table view."""
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        return self._tensor() if self.owner else None
+
+    def close(self):
+        import ctypes
+        if self._closed:
+            return
+        self._closed = True
+        if self.owner:
+            self.ctx.call("apda_peer_table_destroy", ctypes.c_void_p(self.base))
+        else:
+            self.ctx.call("apda_peer_table_close", ctypes.c_void_p(self.base))

@@ -44,6 +44,9 @@ def parse_args():
     ap.add_argument("--center", choices=["median", "mean"], default="median")
     ap.add_argument("--e2e-windows", type=int, default=131072, help="windows per GPU of the host-buffer (e2e) leg")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--gather", choices=["peer", "nccl"], default="peer",
+                    help="N>1: records stored straight into rank 0's table over NVLink peer memory (default), or "
+                         "gathered with NCCL in slices overlapped with compute")
     ap.add_argument("--gather-slices", type=int, default=8,
                     help="N>1: sub-batches per step whose record gather overlaps the next sub-batch's compute")
     ap.add_argument("--cpu-seconds", type=float, default=60.0, help="CPU work budget of the cpu_baseline leg")
@@ -143,8 +146,10 @@ def workload_config(args, world):
         "workload": f"fleet sweep: {args.windows} windows/GPU x N={args.n} {args.dtype}, {args.picker} picker "
                     f"(k={'4' if args.picker == 'flexible' else '5'}), K1 FFT + K3 peaks + gather of 128 B records",
         "windows_per_gpu": args.windows, "n_fft": args.n, "picker": args.picker, "centering": args.center,
-        "parallelism": f"batch-sharded x{world}, records gathered to rank 0"
-                       + (f" in {args.gather_slices} slices overlapped with compute" if world > 1 else ""),
+        "parallelism": f"batch-sharded x{world}, " + (
+            "records gathered to rank 0" if world == 1 else
+            "K3 stores its records into rank 0's table over NVLink peer memory (no collective)" if args.gather == "peer"
+            else f"records gathered to rank 0 with NCCL in {args.gather_slices} slices overlapped with compute"),
         "l2": "inputs (windows*N*s bytes) and spectra far exceed the 126 MB L2; no flush needed",
     }
 
@@ -227,7 +232,7 @@ def run_ours(args):
 
     import apda_fft_b200
     from apda_fft_b200 import _cabi
-    from apda_fft_b200.fleet import RecordGatherer, gather_records
+    from apda_fft_b200.fleet import PeerRecordTable, RecordGatherer, gather_records
     from apda_fft_b200.records import record_dtype
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -260,9 +265,28 @@ def run_ours(args):
     # N > 1: the shard is analysed in a few slices and the records of each slice travel to rank 0 (NCCL, its own
     # stream) while the next slice is computed; only the last slice's transfer is exposed.  N = 1: one slice.
     gatherer = RecordGatherer(b, 128, dev)
-    slices = gatherer.slices(args.gather_slices)
+    # Default for N > 1: no collective at all - the record table lives in rank 0's HBM, mapped into every rank (CUDA IPC),
+    # and each rank's K3 stores its 128-byte records straight into its rows over NVLink; per-rank step counters
+    # (release/acquire at system scope) tell rank 0's stream when the table of a step is complete.
+    use_peer = world > 1 and args.gather == "peer"
+    peer = PeerRecordTable(an.ctx, b, 128, dev) if use_peer else None
+    slices = gatherer.slices(1 if use_peer else args.gather_slices)
+    step_no = [0]
 
-    def step(record_k1: bool, center=center, flexible=flexible, events=k1_events):
+    def step(record_k1: bool, center=center, flexible=flexible, events=k1_events, peer_ok=True):
+        if use_peer and peer_ok:
+            if record_k1:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+            an.fft_device(d_x.data_ptr(), b, n, n, args.dtype, d_spec.data_ptr(), center=center)
+            if record_k1:
+                e1.record(stream)
+                events.append((e0, e1))
+            an.peaks_device(d_spec.data_ptr(), b, n, args.dtype, fs, peer.local_ptr, flexible=flexible,
+                            k=4 if flexible else 5, rec_cap=5)
+            step_no[0] += 1
+            peer.signal(step_no[0])
+            return peer.wait(step_no[0]) if peer.owner else None
         for lo, hi in slices:
             if record_k1:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -359,6 +383,20 @@ def run_ours(args):
         if n in (1024, 2048, 4096, 8192):
             variants["fused_kernel_median"] = fused_variant(_cabi.CENTER_MEDIAN)
             variants["fused_kernel_mean"] = fused_variant(_cabi.CENTER_MEAN)
+    nccl_equal = None
+    if use_peer:   # the same step through the NCCL gather: byte-identical table (also leaves the local records in d_rec)
+        fence()
+        peer_table = peer._tensor().clone() if rank == 0 else None
+        if args.dtype == "f32" and not args.no_variants:   # the variants overwrote the peer table: redo the headline
+            step(False)
+            fence()
+            peer_table = peer._tensor().clone() if rank == 0 else None
+        nccl_table = step(False, peer_ok=False)
+        fence()
+        if rank == 0:
+            nccl_equal = bool(torch.equal(peer_table, nccl_table[: b * world]))
+            table = peer_table
+    elif args.dtype == "f32" and not args.no_variants:
         step(False)            # leave the headline configuration's records in d_rec for the checks below
         fence()
 
@@ -368,6 +406,9 @@ def run_ours(args):
         recs = table.cpu().numpy().view(record_dtype(5)).reshape(-1)
         summary = {"windows_in_table": int(recs.shape[0]), "mean_peaks_per_window": float(recs["count"].mean()),
                    "status_nonzero": int((recs["status"] != 0).sum())}
+        if use_peer:
+            summary["peer_table_equals_nccl_gather"] = nccl_equal
+            summary["peer_wait_timed_out"] = peer.timed_out()
 
     # ---- e2e: host buffers through the C ABI, copies inside the clock ------------------------------------------------
     e2e = None
@@ -462,6 +503,9 @@ def run_ours(args):
                                     "sample": f"{done} windows of the same generator ({per_core} per core) in {t:.1f} s; "
                                               "oracle/ref_port.py (pure-Python restatement, fp64)"}
         print(json.dumps(line), flush=True)
+    if peer is not None:
+        fence()
+        peer.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

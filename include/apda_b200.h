@@ -209,6 +209,24 @@ int apda_synth_f64_dev(apda_ctx *ctx, int64_t first_window, int64_t count, int64
 int apda_synth_f32_dev(apda_ctx *ctx, int64_t first_window, int64_t count, int64_t N, uint64_t seed, int on_bin,
                        float *d_out);
 
+/* ---- fleet record table in peer memory (multi-GPU sweep; nothing like it exists in the reference, whose
+ * work_flow_fft stores one dict per sensor in fft_dict, GT_FFT_v5.py:644-659) -------------------------------------
+ * One process per GPU.  The destination rank creates the table (bytes = total windows * record size) and hands the
+ * 64-byte handle to the other processes (any channel); they open it and pass `table + first_window * record size` as
+ * d_rec to apda_peaks_* / apda_analyze_*: the K3 kernels then store their records straight into the owner's memory
+ * over NVLink.  After every rank has synchronised its stream (and a process barrier) the owner reads the full table
+ * in window order.  Same-node GPUs with peer access only (NVSwitch); open fails with APDA_ERR_CUDA otherwise. */
+int apda_peer_table_create(apda_ctx *ctx, int64_t bytes, void **d_table, unsigned char *handle64);
+int apda_peer_table_open(apda_ctx *ctx, const unsigned char *handle64, void **d_table);
+int apda_peer_table_close(apda_ctx *ctx, void *d_table);    /* importer side */
+int apda_peer_table_destroy(apda_ctx *ctx, void *d_table);  /* owner side */
+/* Completion on the device timelines: every rank owns one uint32 step counter in the owner's memory (the caller
+ * reserves them, e.g. behind the rows).  apda_peer_signal (producer, after its pickers, same stream) publishes
+ * `value` with release semantics at system scope; apda_peer_wait (owner) holds the stream until all `world` counters
+ * have reached `value` (acquire), or sets *d_timed_out = 1 after timeout_s seconds instead of hanging. */
+int apda_peer_signal(apda_ctx *ctx, void *d_flag, uint32_t value);
+int apda_peer_wait(apda_ctx *ctx, const void *d_flags, int world, uint32_t value, double timeout_s, int *d_timed_out);
+
 #ifdef __cplusplus
 }
 #endif

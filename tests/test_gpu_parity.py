@@ -3,6 +3,7 @@
 Bars (north_star): fp64 - spectrum bit-exact (SHA-256 of the doubles), peak indices/counts exact, magnitudes and
 prominences within rel 1e-12; fp32 - indices/counts exact on the well-separated inputs, values within rel 1e-5.
 """
+import os
 import statistics
 
 import numpy as np
@@ -614,3 +615,49 @@ def test_text_ingest_matches_load_sensor(golden, tmp_path, an):
                 p(nv.ctypes.data), p(fl.ctypes.data))
     assert fl[0] == 0 and out[0, : nv[0]].tolist() == [0.5, -1.25, 3.0, 0.125, 7.0, 0.5, -0.0, 123456789.012345, 1e-06]
     assert np.signbit(out[0, 6])
+
+
+def _peer_worker(rank, world, port, tmp):
+    import torch
+    import torch.distributed as dist
+    import apda_fft_b200
+    from apda_fft_b200.fleet import PeerRecordTable, gather_records
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=dev)
+    an = apda_fft_b200.Analyzer(rank)
+    an.use_stream(torch.cuda.current_stream(dev).cuda_stream)
+    per, n = 3000, 4096
+    x = torch.empty((per, n), dtype=torch.float32, device=dev)
+    spec = torch.empty((per, n, 2), dtype=torch.float32, device=dev)
+    rec = torch.zeros((per, 128), dtype=torch.uint8, device=dev)
+    an.synth_device(rank * per, per, n, "f32", x.data_ptr())
+    table = PeerRecordTable(an.ctx, per, 128, dev)
+    for step in (1, 2):
+        an.fft_device(x.data_ptr(), per, n, n, "f32", spec.data_ptr())
+        an.peaks_device(spec.data_ptr(), per, n, "f32", 125.0, table.local_ptr)
+        table.signal(step)
+        if table.owner:
+            table.wait(step)
+    got = table.complete()
+    an.peaks_device(spec.data_ptr(), per, n, "f32", 125.0, rec.data_ptr())
+    want = gather_records(rec, per * world, dst=0)
+    if rank == 0:
+        assert not table.timed_out()
+        assert torch.equal(got, want)
+        open(os.path.join(tmp, "ok"), "w").write("1")
+    dist.barrier()
+    table.close()
+    dist.destroy_process_group()
+
+
+def test_peer_record_table_equals_nccl_gather(tmp_path):
+    """N>1 on GPUs: K3 storing its records into rank 0's table over NVLink peer memory (CUDA IPC + device-side step
+    counters) gives the table an NCCL gather gives, byte for byte.  Needs two GPUs (skipped on a single-GPU box)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    port = 29700 + os.getpid() % 200
+    mp.spawn(_peer_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(os.path.join(str(tmp_path), "ok"))
