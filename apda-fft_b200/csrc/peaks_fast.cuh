@@ -51,6 +51,34 @@ __device__ __forceinline__ float vmin(float a, float b) { return fminf(a, b); }
 __device__ __forceinline__ float vmax(float a, float b) { return fmaxf(a, b); }
 __device__ __forceinline__ double vmin(double a, double b) { return fmin(a, b); }
 __device__ __forceinline__ double vmax(double a, double b) { return fmax(a, b); }
+// warp minimum of non-negative magnitudes; fp32: the bit patterns order like the values, one REDUX instruction
+__device__ __forceinline__ float warp_min_nonneg(float v) {
+    return __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(v)));
+}
+__device__ __forceinline__ double warp_min_nonneg(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// warp arg-max of (m, j) over the lanes with j >= 0 (their m is > 0): largest m, ties -> lowest j; j = -1 if no lane has one
+__device__ __forceinline__ void warp_argmax(float &m, int &j) {
+    const unsigned key = j >= 0 ? __float_as_uint(m) : 0u;
+    const unsigned best = __reduce_max_sync(0xffffffffu, key);
+    const int jb = __reduce_min_sync(0xffffffffu, (j >= 0 && key == best) ? j : 0x7fffffff);
+    m = __uint_as_float(best);
+    j = best ? jb : -1;
+}
+__device__ __forceinline__ void warp_argmax(double &m, int &j) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double m2 = __shfl_xor_sync(0xffffffffu, m, o);
+        const int j2 = __shfl_xor_sync(0xffffffffu, j, o);
+        if (j2 >= 0 && (j < 0 || m2 > m || (m2 == m && j2 < j))) {
+            m = m2;
+            j = j2;
+        }
+    }
+}
 template <typename T>
 struct Quad {
     T x, y, z, w;
@@ -159,11 +187,8 @@ __device__ T coop_prominence(const T *mags, int j, T cmax, T cmin, int lane) {
         if (lane > cj && lane < R && cmin < fr) fr = cmin;
         if (R < 32) scan_piece<T, HALF, +1>(mags, C * R, C * (R + 1) - 1, p, fr, lane);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        fl = vmin(fl, __shfl_xor_sync(0xffffffffu, fl, o));
-        fr = vmin(fr, __shfl_xor_sync(0xffffffffu, fr, o));
-    }
+    fl = warp_min_nonneg(fl);
+    fr = warp_min_nonneg(fr);
     return sub_rn(p, vmax(fl, fr));
 }
 
@@ -436,15 +461,7 @@ __device__ __forceinline__ void k3_tail(T *mags, SlotT<T> *slots, const int slot
                     bj = j;
                 }
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const T m2 = __shfl_xor_sync(0xffffffffu, bm, o);
-                const int j2 = __shfl_xor_sync(0xffffffffu, bj, o);
-                if (j2 >= 0 && (bj < 0 || m2 > bm || (m2 == bm && j2 < bj))) {
-                    bm = m2;
-                    bj = j2;
-                }
-            }
+            warp_argmax(bm, bj);
             if (bj < 0) break;
             const int w2 = half_height_bins_f<T, HALF>(mags, bj);
             bool separated = true;
