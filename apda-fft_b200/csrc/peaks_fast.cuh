@@ -220,6 +220,32 @@ __device__ __forceinline__ int half_height_bins_f(const T *mags, int j) {
     return hi - lo;
 }
 
+// width_half_magnitude with the whole warp (all lanes call it with the same j): 32 bins per side and step instead of a
+// serial walk - same result as half_height_bins_f (utils/get_peak_resolution.py:30-44)
+template <typename T, int HALF>
+__device__ __forceinline__ int half_height_bins_warp(const T *mags, int j, int lane) {
+    using P = K3<T, HALF>;
+    const T level = mul_rn((T)0.707, mags[P::addr(j)]);
+    int lo = 0, hi = HALF;
+    for (int base = j; base > 0; base -= 32) {  // left = first i <= j with mags[i] <= level, else 0 (bin 0 is never tested)
+        const int i = base - lane;
+        const unsigned stop = __ballot_sync(0xffffffffu, i <= 0 || !(mags[P::addr(i > 0 ? i : 0)] > level));
+        if (stop) {
+            lo = max(base - (__ffs(stop) - 1), 0);
+            break;
+        }
+    }
+    for (int base = j; base < HALF; base += 32) {  // right = first i >= j with i == HALF or mags[i] <= level
+        const int i = base + lane;
+        const unsigned stop = __ballot_sync(0xffffffffu, i >= HALF || !(mags[P::addr(i < HALF ? i : HALF - 1)] > level));
+        if (stop) {
+            hi = base + (__ffs(stop) - 1);
+            break;
+        }
+    }
+    return hi - lo;
+}
+
 // The reference sorts the gated candidates by round(mag, 4) descending (stable: ties keep ascending idx) and walks that
 // order with the greedy "hump" exclusion.  Each lane owns PER slots; a slot's place in the order is its rank (number of
 // passing slots that precede it), computed once with shuffles.  Accepted peaks go straight into the record.
@@ -463,7 +489,7 @@ __device__ __forceinline__ void k3_tail(T *mags, SlotT<T> *slots, const int slot
             }
             warp_argmax(bm, bj);
             if (bj < 0) break;
-            const int w2 = half_height_bins_f<T, HALF>(mags, bj);
+            const int w2 = half_height_bins_warp<T, HALF>(mags, bj, lane);
             bool separated = true;
 #pragma unroll
             for (int a = 0; a < 5; ++a) {
