@@ -3,6 +3,11 @@
 
 namespace {
 
+#ifndef APDA_K3_BATCH
+#define APDA_K3_BATCH 8
+#endif
+constexpr int kK3Batch = APDA_K3_BATCH;  // 128-bit loads in flight per lane in phase 1
+
 template <int HALF, bool FLEX>
 __global__ void __launch_bounds__(32 * kWPC)
 peaks_f32_fast_kernel(const float2 *__restrict__ spec, int64_t batch, double df_all, const double *__restrict__ d_fs,
@@ -26,7 +31,7 @@ peaks_f32_fast_kernel(const float2 *__restrict__ spec, int64_t batch, double df_
     // ---- phase 1: stream the half spectrum, magnitudes -> shared memory, statistics in registers -------------------
     const float4 *src = reinterpret_cast<const float4 *>(spec + win * (int64_t)N);
     float sum = 0.f, sumsq = 0.f;
-    constexpr int ROWS = HALF / 64, BATCH = ROWS < 8 ? ROWS : 8;
+    constexpr int ROWS = HALF / 64, BATCH = ROWS < kK3Batch ? ROWS : kK3Batch;
     // shared-memory word of bin b = 64*R + 2*lane is  row_off(R) + lane_off  (4-word pad per chunk of C bins)
     const int lane_off = P::addr(2 * lane);
 #pragma unroll 1
