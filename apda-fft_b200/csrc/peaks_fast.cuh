@@ -55,10 +55,13 @@ __device__ __forceinline__ double vmax(double a, double b) { return fmax(a, b); 
 __device__ __forceinline__ float warp_min_nonneg(float v) {
     return __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(v)));
 }
+// fp64: non-negative doubles order like their 64-bit patterns - REDUX on the high words, then on the low words of the
+// lanes that hold the winning high word
 __device__ __forceinline__ double warp_min_nonneg(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned bhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned blo = __reduce_min_sync(0xffffffffu, hi == bhi ? lo : 0xffffffffu);
+    return __hiloint2double((int)bhi, (int)blo);
 }
 // warp arg-max of (m, j) over the lanes with j >= 0 (their m is > 0): largest m, ties -> lowest j; j = -1 if no lane has one
 __device__ __forceinline__ void warp_argmax(float &m, int &j) {
@@ -69,15 +72,12 @@ __device__ __forceinline__ void warp_argmax(float &m, int &j) {
     j = best ? jb : -1;
 }
 __device__ __forceinline__ void warp_argmax(double &m, int &j) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double m2 = __shfl_xor_sync(0xffffffffu, m, o);
-        const int j2 = __shfl_xor_sync(0xffffffffu, j, o);
-        if (j2 >= 0 && (j < 0 || m2 > m || (m2 == m && j2 < j))) {
-            m = m2;
-            j = j2;
-        }
-    }
+    const unsigned hi = j >= 0 ? (unsigned)__double2hiint(m) : 0u, lo = j >= 0 ? (unsigned)__double2loint(m) : 0u;
+    const unsigned bhi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned blo = __reduce_max_sync(0xffffffffu, hi == bhi ? lo : 0u);
+    const int jb = __reduce_min_sync(0xffffffffu, (j >= 0 && hi == bhi && lo == blo) ? j : 0x7fffffff);
+    m = __hiloint2double((int)bhi, (int)blo);
+    j = jb == 0x7fffffff ? -1 : jb;
 }
 template <typename T>
 struct Quad {
