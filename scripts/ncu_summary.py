@@ -60,11 +60,13 @@ def main():
             if windows:
                 entry["dram_bytes_per_window"] = (rd + wr) / windows
             import re
-            m = re.search(r"(fft_f32_fast|fft_f64_fast|peaks_f32_fast|fft_smem|peaks)_kernel<\(?(?:int\))?(\d+)", name)
-            if m and m.group(1).startswith("fft"):
-                key = f"k1_{'f64' if 'f64' in m.group(1) else 'f32'}_n{m.group(2)}"
-            elif m and m.group(1) == "peaks_f32_fast":
-                key = f"k3_f32_n{2 * int(m.group(2))}"
+            m = re.search(r"(fft_f32_fast|fft_f64_fast|peaks_f32_fast|peaks_f64_fast|fft_smem|peaks)_kernel<\(?(?:int\))?(\d+)", name)
+            if m and m.group(1) == "fft_f64_fast":      # templated on log2(N)
+                key = f"k1_f64_n{1 << int(m.group(2))}"
+            elif m and m.group(1).startswith("fft"):
+                key = f"k1_f32_n{m.group(2)}"
+            elif m and m.group(1) in ("peaks_f32_fast", "peaks_f64_fast"):
+                key = f"k3_{m.group(1)[6:9]}_n{2 * int(m.group(2))}"
             else:
                 key = name[:60]
             traffic.setdefault(key, entry)
@@ -76,8 +78,14 @@ def main():
         lines.append("")
     with open(out_prefix + "_summary.md", "w") as fh:
         fh.write("\n".join(lines) + "\n")
-    with open(os.path.join(os.path.dirname(out_prefix), "traffic.json"), "w") as fh:
-        json.dump(traffic, fh, indent=1)
+    tpath = os.path.join(os.path.dirname(out_prefix), "traffic.json")
+    try:
+        merged = json.load(open(tpath))
+    except Exception:  # noqa: BLE001
+        merged = {}
+    merged.update(traffic)
+    with open(tpath, "w") as fh:
+        json.dump(merged, fh, indent=1)
     print("\n".join(lines[:40]))
 
 
