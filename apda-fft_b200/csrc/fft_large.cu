@@ -41,6 +41,57 @@ __device__ __forceinline__ void butterfly(typename vec2<T>::type &u, typename ve
     v = b;
 }
 
+// QR radix-2 stages (t0+1 .. t0+QR of this pass) on 2^QR register-resident values per work item: one shared-memory round
+// trip and one barrier per QR stages instead of per stage, 2^QR - 1 twiddle loads per QR * 2^(QR-1) butterflies.
+// Element (row r, column c) of the pass's working set lives at tile[r * rs + c * cs]; rows r = (hi << (t0+QR)) + (k << t0) + jr.
+// Twiddle of stage t for row r: T_{s0+t}[((r mod 2^(t-1)) << s0) + lo0 + c]  (head pass: s0 = 0 and no column term - its
+// columns are independent sub-transforms).  Same dataflow graph and individually rounded operations as before.
+template <typename T, int QR, bool HEAD>
+__device__ __forceinline__ void stage_round(typename vec2<T>::type *tile, int rs, int cs, int logC, int q, int t0,
+                                            const typename vec2<T>::type *__restrict__ tw, int s0, int64_t lo0, int tid) {
+    using V2 = typename vec2<T>::type;
+    constexpr int R = 1 << QR;
+    const int items = 1 << (logC + q - QR);
+    for (int item = tid; item < items; item += kThreads) {
+        const int c = item & ((1 << logC) - 1), rest = item >> logC;
+        const int jr = rest & ((1 << t0) - 1), hi = rest >> t0;
+        V2 *p = tile + (size_t)(((hi << (t0 + QR)) + jr)) * rs + (size_t)c * cs;
+        const int kstride = rs << t0;
+        V2 v[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) v[k] = p[k * kstride];
+#pragma unroll
+        for (int u = 1; u <= QR; ++u) {
+            const int t = t0 + u;  // stage of this pass (1-based): pairs rows that differ in bit t-1
+            const V2 *tab = tw + (((int64_t)1 << (s0 + t - 1)) - 1) + (HEAD ? 0 : lo0 + c);
+            V2 w[R / 2];
+#pragma unroll
+            for (int m = 0; m < (1 << (u - 1)); ++m) w[m] = __ldg(tab + ((int64_t)(jr + (m << t0)) << s0));
+#pragma unroll
+            for (int k = 0; k < R; ++k)
+                if ((k & (1 << (u - 1))) == 0) butterfly<T>(v[k], v[k + (1 << (u - 1))], w[k & ((1 << (u - 1)) - 1)]);
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) p[k * kstride] = v[k];
+    }
+}
+
+// all q stages of a pass, three at a time (the remainder as 2+2, 2 or 1), one barrier per round
+template <typename T, bool HEAD>
+__device__ __forceinline__ void run_stages(typename vec2<T>::type *tile, int rs, int cs, int logC, int q,
+                                           const typename vec2<T>::type *__restrict__ tw, int s0, int64_t lo0, int tid) {
+    int t0 = 0;
+    while (t0 < q) {
+        const int left = q - t0;
+        const int qr = left > 4 ? 3 : (left == 4 ? 2 : left);
+        if (qr == 3) stage_round<T, 3, HEAD>(tile, rs, cs, logC, q, t0, tw, s0, lo0, tid);
+        else if (qr == 2) stage_round<T, 2, HEAD>(tile, rs, cs, logC, q, t0, tw, s0, lo0, tid);
+        else stage_round<T, 1, HEAD>(tile, rs, cs, logC, q, t0, tw, s0, lo0, tid);
+        __syncthreads();
+        t0 += qr;
+    }
+}
+
 // ---- head pass ------------------------------------------------------------------------------------------------------
 template <typename T, bool COMPLEX_IN>
 __global__ void __launch_bounds__(kThreads)
@@ -58,8 +109,9 @@ large_head_kernel(const T *__restrict__ samples, int64_t n_samples, int64_t ld, 
     const T med = med_ptr ? med_ptr[win] : T(0);
     const int rows = 1 << q;
 
+    const int logC = 31 - __clz(C);  // C is a power of two
     for (int e = tid; e < (C << q); e += kThreads) {
-        const int c = e % C, jh = e / C;
+        const int c = e & (C - 1), jh = e >> logC;
         const int64_t j = ((int64_t)jh << (n - q)) + lo0 + c;
         V2 val;
         if (COMPLEX_IN) {
@@ -73,21 +125,7 @@ large_head_kernel(const T *__restrict__ samples, int64_t n_samples, int64_t ld, 
     }
     __syncthreads();
 
-    for (int t = 0; t < q; ++t) {
-        const int half = 1 << t;
-        const V2 *tab = tw + (half - 1);
-        for (int e = tid; e < (C << (q - 1)); e += kThreads) {
-            const int c = e >> (q - 1), b = e & ((rows >> 1) - 1);
-            const int j = b & (half - 1);
-            const int lo = ((b >> t) << (t + 1)) + j;
-            V2 *col = work + c * LDW;
-            V2 u = col[lo], v = col[lo + half];
-            butterfly<T>(u, v, __ldg(tab + j));
-            col[lo] = u;
-            col[lo + half] = v;
-        }
-        __syncthreads();
-    }
+    run_stages<T, true>(work, 1, LDW, logC, q, tw, 0, 0, tid);
 
     V2 *out = spec + win * N;
     for (int e = tid; e < (C << q); e += kThreads) {
@@ -114,29 +152,17 @@ large_tail_kernel(typename vec2<T>::type *__restrict__ spec, int n, int s0, int 
     V2 *base = spec + (int64_t)blockIdx.y * N + (hi << (s0 + q)) + lo0;
     const int rows = 1 << q;
 
+    const int logC = 31 - __clz(C);  // C is a power of two
     for (int e = tid; e < (C << q); e += kThreads) {
-        const int c = e % C, r = e / C;
+        const int c = e & (C - 1), r = e >> logC;
         tile[r * LD + c] = base[((int64_t)r << s0) + c];
     }
     __syncthreads();
 
-    for (int t = 1; t <= q; ++t) {
-        const int halfr = 1 << (t - 1);
-        const V2 *tab = tw + (((int64_t)1 << (s0 + t - 1)) - 1) + lo0;
-        for (int e = tid; e < (C << (q - 1)); e += kThreads) {
-            const int c = e % C, pb = e / C;
-            const int jr = pb & (halfr - 1);
-            const int ra = ((pb >> (t - 1)) << t) + jr;
-            V2 u = tile[ra * LD + c], v = tile[(ra + halfr) * LD + c];
-            butterfly<T>(u, v, __ldg(tab + ((int64_t)jr << s0) + c));
-            tile[ra * LD + c] = u;
-            tile[(ra + halfr) * LD + c] = v;
-        }
-        __syncthreads();
-    }
+    run_stages<T, false>(tile, LD, 1, logC, q, tw, s0, lo0, tid);
 
     for (int e = tid; e < (C << q); e += kThreads) {
-        const int c = e % C, r = e / C;
+        const int c = e & (C - 1), r = e >> logC;
         V2 val = tile[r * LD + c];
         if (zero_dc && hi == 0 && lo0 == 0 && r == 0 && c == 0) val.x = val.y = T(0);  // reference: res[0] = 0
         base[((int64_t)r << s0) + c] = val;
@@ -197,20 +223,7 @@ large_tail_tma_kernel(const __grid_constant__ CUtensorMap tmap, int n, int s0, i
         }
     }
 
-    for (int t = 1; t <= q; ++t) {
-        const int halfr = 1 << (t - 1);
-        const V2 *tab = tw + (((int64_t)1 << (s0 + t - 1)) - 1) + lo0;
-        for (int e = tid; e < (C << (q - 1)); e += kThreads) {
-            const int c = e % C, pb = e / C;
-            const int jr = pb & (halfr - 1);
-            const int ra = ((pb >> (t - 1)) << t) + jr;
-            V2 u = tile[ra * C + c], v = tile[(ra + halfr) * C + c];
-            butterfly<T>(u, v, __ldg(tab + ((int64_t)jr << s0) + c));
-            tile[ra * C + c] = u;
-            tile[(ra + halfr) * C + c] = v;
-        }
-        __syncthreads();
-    }
+    run_stages<T, false>(tile, C, 1, 31 - __clz(C), q, tw, s0, lo0, tid);
     if (zero_dc && hi == 0 && lo0 == 0 && tid == 0) tile[0].x = tile[0].y = T(0);  // reference: res[0] = 0
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk store
     __syncthreads();
