@@ -122,14 +122,30 @@ class PeerRecordTable:
         self.flags_off = (self.nbytes + 255) & ~255          # one uint32 step counter per rank, then a time-out word
         base = ctypes.c_void_p()
         handle = (ctypes.c_ubyte * 64)()
+        err = None
         if self.owner:
-            ctx.call("apda_peer_table_create", ctypes.c_int64(self.flags_off + 256), ctypes.byref(base), handle)
+            try:
+                ctx.call("apda_peer_table_create", ctypes.c_int64(self.flags_off + 256), ctypes.byref(base), handle)
+            except Exception as exc:  # noqa: BLE001 - reported after the collective steps below, never before
+                err = exc
         if self.world > 1:
             h = torch.tensor(list(handle), dtype=torch.uint8, device=device)
             dist.broadcast(h, src=dst, group=group)
             if not self.owner:
-                raw = (ctypes.c_ubyte * 64)(*h.cpu().tolist())
-                ctx.call("apda_peer_table_open", raw, ctypes.byref(base))
+                try:
+                    raw = (ctypes.c_ubyte * 64)(*h.cpu().tolist())
+                    ctx.call("apda_peer_table_open", raw, ctypes.byref(base))
+                except Exception as exc:  # noqa: BLE001
+                    err = exc
+            # every rank learns whether all mappings exist, so that a failure raises everywhere instead of hanging
+            good = torch.tensor([0.0 if err else 1.0], device=device)
+            dist.all_reduce(good, op=dist.ReduceOp.MIN, group=group)
+            if float(good[0]) < 1.0:
+                if base.value:
+                    ctx.call("apda_peer_table_destroy" if self.owner else "apda_peer_table_close", ctypes.c_void_p(base.value))
+                raise err or RuntimeError("peer table: another rank could not map the allocation")
+        elif err:
+            raise err
         self.base = int(base.value)
         self.local_ptr = self.base + self.rank * per * rec_bytes
         self._closed = False

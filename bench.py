@@ -269,7 +269,21 @@ def run_ours(args):
     # and each rank's K3 stores its 128-byte records straight into its rows over NVLink; per-rank step counters
     # (release/acquire at system scope) tell rank 0's stream when the table of a step is complete.
     use_peer = world > 1 and args.gather == "peer"
-    peer = PeerRecordTable(an.ctx, b, 128, dev) if use_peer else None
+    peer, peer_note = None, None
+    if use_peer:
+        try:
+            peer = PeerRecordTable(an.ctx, b, 128, dev)
+            ok = torch.ones(1, device=dev)
+        except Exception as exc:  # CUDA IPC unavailable in this container / no peer access: every rank falls back together
+            peer_note = f"peer table unavailable ({type(exc).__name__}: {exc}); NCCL gather used"
+            ok = torch.zeros(1, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok[0]) < 1.0:
+            if peer is not None:
+                peer.close()
+            peer, use_peer = None, False
+            peer_note = peer_note or "peer table unavailable on another rank; NCCL gather used"
+            args.gather = "nccl"
     slices = gatherer.slices(1 if use_peer else args.gather_slices)
     step_no = [0]
 
@@ -305,7 +319,9 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    # peer path: a few extra untimed steps so that the NVLink links carrying the (small) record traffic are out of their
+    # idle power state before the clock starts
+    for _ in range(max(args.warmup, 3) + (5 if use_peer else 0)):
         step(False)
     fence()
     sampler = ClockSampler(local)
@@ -406,6 +422,8 @@ def run_ours(args):
         recs = table.cpu().numpy().view(record_dtype(5)).reshape(-1)
         summary = {"windows_in_table": int(recs.shape[0]), "mean_peaks_per_window": float(recs["count"].mean()),
                    "status_nonzero": int((recs["status"] != 0).sum())}
+        if peer_note:
+            summary["note"] = peer_note
         if use_peer:
             summary["peer_table_equals_nccl_gather"] = nccl_equal
             summary["peer_wait_timed_out"] = peer.timed_out()
