@@ -3,6 +3,8 @@ the only exchange is a gather of the fixed-size peak records to rank 0 (torch.di
 CPU tests).  No collective touches the data path."""
 from __future__ import annotations
 
+import os
+
 
 def shard_bounds(total: int, world: int, rank: int) -> tuple[int, int]:
     """Rank r owns windows [r*ceil(total/world), min(total, (r+1)*ceil(total/world)))."""
@@ -133,6 +135,8 @@ class PeerRecordTable:
             dist.broadcast(h, src=dst, group=group)
             if not self.owner:
                 try:
+                    if os.environ.get("APDA_TEST_PEER_OPEN_FAILS"):  # exercises the collective fail-over (tests only)
+                        raise RuntimeError("peer table open disabled by APDA_TEST_PEER_OPEN_FAILS")
                     raw = (ctypes.c_ubyte * 64)(*h.cpu().tolist())
                     ctx.call("apda_peer_table_open", raw, ctypes.byref(base))
                 except Exception as exc:  # noqa: BLE001
