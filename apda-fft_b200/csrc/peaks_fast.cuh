@@ -253,40 +253,40 @@ template <typename T, int HALF, int PER>
 __device__ __forceinline__ int order_and_exclude(const SlotT<T> *slots, int nslot, const T *mags, unsigned char *rec_s,
                                                  double df, int k, int lane) {
     using P = K3<T, HALF>;
+    // each lane owns PER slots; the order is extracted one element at a time with a warp arg-max (REDUX on the key's
+    // words: largest round(mag, 4), ties -> lowest idx), at most k + rejected times
     double key[PER];
-    int sidx[PER], srank[PER];
-    unsigned passm[PER];
-    int npass = 0;
+    int sidx[PER];
 #pragma unroll
     for (int r = 0; r < PER; ++r) {
         const int e = lane + 32 * r;
         const bool ok = e < nslot && slots[e].width != 0;
-        sidx[r] = ok ? (int)slots[e].idx : 0x7fffffff;
-        key[r] = -1.0;
-        if (ok) key[r] = round_dec4_units((double)mags[P::addr(sidx[r])]);
-        passm[r] = __ballot_sync(0xffffffffu, ok);
-        npass += __popc(passm[r]);
-        srank[r] = 0;
-    }
-#pragma unroll
-    for (int r2 = 0; r2 < PER; ++r2) {
-        for (unsigned m = passm[r2]; m; m &= m - 1) {
-            const int src = __ffs(m) - 1;
-            const double ko = __shfl_sync(0xffffffffu, key[r2], src);
-            const int io = __shfl_sync(0xffffffffu, sidx[r2], src);
-#pragma unroll
-            for (int r = 0; r < PER; ++r) srank[r] += (ko > key[r]) || (ko == key[r] && io < sidx[r]);
-        }
+        sidx[r] = ok ? (int)slots[e].idx : -1;
+        key[r] = ok ? round_dec4_units((double)mags[P::addr(sidx[r])]) : -1.0;
     }
     int na = 0;
-    for (int pos = 0; pos < npass && na < k; ++pos) {
-        int e_sel = -1;
+    while (na < k) {
+        double bk = key[0];
+        int bi = sidx[0], br = 0;
 #pragma unroll
-        for (int r = 0; r < PER; ++r) {
-            const unsigned hit = __ballot_sync(0xffffffffu, (passm[r] >> lane & 1u) && srank[r] == pos);
-            if (hit) e_sel = (__ffs(hit) - 1) + 32 * r;
+        for (int r = 1; r < PER; ++r) {
+            if (sidx[r] >= 0 && (bi < 0 || key[r] > bk || (key[r] == bk && sidx[r] < bi))) {
+                bk = key[r];
+                bi = sidx[r];
+                br = r;
+            }
         }
-        const int c_idx = slots[e_sel].idx;
+        const int mine = bi;
+        warp_argmax(bk, bi);
+        if (bi < 0) break;
+        const bool owner = mine == bi;  // bin indices are unique
+        const int e_sel = __reduce_max_sync(0xffffffffu, owner ? lane + 32 * br : -1);
+        if (owner) {
+#pragma unroll
+            for (int r = 0; r < PER; ++r)
+                if (r == br) sidx[r] = -1;
+        }
+        const int c_idx = bi;
         const T cprom = slots[e_sel].prom;
         const T cmag = mags[P::addr(c_idx)];
         bool hump = false;
@@ -296,9 +296,7 @@ __device__ __forceinline__ int order_and_exclude(const SlotT<T> *slots, int nslo
             // |round4(fc) - round4(fa)| >= |fc - fa| - 1e-4 and round4(fa) <= fa + 5e-5: most pairs are provably > 5 % apart
             if (fabs(fc - fa) - 1.0e-4 > 0.05 * (fa + 5.0e-5) * (1.0 + 1e-9)) continue;
             const double cf = round_dec4_d(fc), af = round_dec4_d(fa);
-            if (div_rn(fabs(sub_rn(cf, af)), af) < 0.05 &&
-                div_rn((double)cprom, div_rn(round_dec4_units((double)cmag), 1e4)) < 0.10)
-                hump = true;
+            if (div_rn(fabs(sub_rn(cf, af)), af) < 0.05 && div_rn((double)cprom, div_rn(bk, 1e4)) < 0.10) hump = true;
         }
         if (!hump) {
             if (lane == 0) {
