@@ -542,11 +542,8 @@ __device__ __forceinline__ void k3_tail(T *mags, SlotT<T> *slots, const int slot
         }
     }
     __syncwarp();
-    if (lane < 16) {
-        const double2 *s2 = reinterpret_cast<const double2 *>(rec_s);
-        (void)s2;
+    if (lane < 16)  // one coalesced 128-byte store (local HBM, or the fleet table in a peer's HBM over NVLink)
         reinterpret_cast<uint64_t *>(recs + win * 128)[lane] = reinterpret_cast<const uint64_t *>(rec_s)[lane];
-    }
 }
 
 }  // namespace
