@@ -661,3 +661,37 @@ def test_peer_record_table_equals_nccl_gather(tmp_path):
     port = 29700 + os.getpid() % 200
     mp.spawn(_peer_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(os.path.join(str(tmp_path), "ok"))
+
+
+def _outcome(fn, *args, **kw):
+    try:
+        return {"ok": fn(*args, **kw)}
+    except Exception as exc:  # the shim raises the reference's exception types
+        return {"error": type(exc).__name__}
+
+
+def test_fuzz_small_windows_and_spectra_vs_oracle(an):
+    """The adversarial inputs that pin the oracle to the live reference (tests/test_oracle.py, 400 windows of length
+    1..256 with ties / plateaus / offsets and 300 hand-shaped spectra with k = 1..7), through the CUDA path: fp64 spectra
+    bit-identical, peak dicts equal objects, same exception types for degenerate sizes."""
+    from apda_fft_b200.records import prominence_dicts, resolution_dicts
+    from test_oracle import _fuzz_inputs, _fuzz_spectra
+    for x in _fuzz_inputs(20260101, 400):
+        xs = np.asarray(x, dtype=np.float64)
+        want = ref_port.start_fft(list(x), 125.0)
+        n = len(want)
+        got = an.fft(xs)[0]
+        assert np.array_equal(got.view(np.float64), np.asarray(want, dtype=np.complex128).view(np.float64)), x
+        for flexible, port, conv in ((True, ref_port.top_peaks_prominence, prominence_dicts),
+                                     (False, ref_port.top_peaks_resolution, resolution_dicts)):
+            ref = _outcome(port, list(want), 125.0)
+            mine = _outcome(lambda: [conv(r, 125.0, n) for r in an.analyze(xs, 125.0, flexible=flexible)][0])
+            assert ref == mine, (x, flexible)
+    for spec, fs, k in _fuzz_spectra(7, 300):
+        z = np.asarray(spec, dtype=np.complex128)
+        n = z.shape[0]
+        for flexible, port, conv in ((True, ref_port.top_peaks_prominence, prominence_dicts),
+                                     (False, ref_port.top_peaks_resolution, resolution_dicts)):
+            ref = _outcome(port, list(spec), fs, k)
+            mine = _outcome(lambda: conv(an.peaks(z, fs, flexible=flexible, k=k)[0], fs, n))
+            assert ref == mine, (n, fs, k, flexible)

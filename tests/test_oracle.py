@@ -146,3 +146,58 @@ def test_log_parsing_port_and_split(golden, tmp_path):
         else:
             rows = io.StringIO(parts[1].decode("utf-8"), newline=None).readlines()
             assert parts[0] == lines[:4] and ref_port.parse_log_sample_lines(rows) == got
+
+
+def _fuzz_inputs(seed, count):
+    """Deterministic adversarial inputs: ties, plateaus, odd lengths, DC offsets, spiky magnitude spectra."""
+    rng = np.random.default_rng(seed)
+    for i in range(count):
+        n = int(rng.integers(1, 70)) if i % 3 else int(rng.choice([2, 3, 4, 7, 8, 16, 31, 32, 64, 100, 128, 200, 256]))
+        kind = i % 4
+        if kind == 0:
+            x = np.round(rng.standard_normal(n), 1)                       # many ties
+        elif kind == 1:
+            x = np.round(np.sin(np.arange(n) * rng.uniform(0.1, 2.5)) + 0.05 * rng.standard_normal(n) + rng.uniform(-3, 3), 6)
+        elif kind == 2:
+            x = rng.integers(-3, 4, n).astype(np.float64)                 # plateaus, repeated medians
+        else:
+            x = np.round(np.exp(rng.standard_normal(n)), 3)               # skewed
+        yield x.tolist()
+
+
+def _fuzz_spectra(seed, count):
+    rng = np.random.default_rng(seed)
+    for i in range(count):
+        n = int(rng.choice([8, 16, 32, 64, 128, 256]))
+        mags = np.round(np.exp(1.4 * rng.standard_normal(n)), int(rng.integers(0, 4)))   # rounded: equal neighbours occur
+        mags[0] = 0.0
+        phase = np.exp(1j * rng.uniform(0, 2 * np.pi, n)) if i % 2 else np.ones(n)
+        yield (mags * phase).tolist(), float(rng.choice([31.25, 62.5, 125.0, 250.0, 500.0])), int(rng.integers(1, 8))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="live reference only exists in the build container")
+def test_port_fuzz_against_live_reference():
+    """Oracle pin beyond the fixed goldens: 400 adversarial sample windows and 300 hand-shaped spectra through the
+    UNMODIFIED reference and through the port - equal objects (spectra bit for bit, peak dicts, exception types)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden
+    ref = make_golden.import_reference()
+    for x in _fuzz_inputs(20260101, 400):
+        want = _run(ref["fft_iterativa"].start_fft, list(x), 125.0)
+        got = _run(ref_port.start_fft, list(x), 125.0)
+        assert want.keys() == got.keys(), x
+        if "ok" in want:
+            assert len(want["ok"]) == len(got["ok"])
+            assert all(complex(a) == complex(b) for a, b in zip(want["ok"], got["ok"])), x
+            spec = want["ok"]
+            for fn_ref, fn_port in ((ref["get_peak_prominence"].get_top_peaks_prominence, ref_port.top_peaks_prominence),
+                                    (ref["get_peak_resolution"].get_top_peaks_resolution, ref_port.top_peaks_resolution)):
+                assert _run(fn_ref, list(spec), 125.0) == _run(fn_port, list(spec), 125.0), x
+            if len(x) >= 2:
+                c = c_oracle.start_fft_batch(np.asarray(x, dtype=np.float64))[0]
+                assert cases.spectrum_sha16(c) == cases.spectrum_sha16(spec)
+    for spec, fs, k in _fuzz_spectra(7, 300):
+        assert _run(ref["get_peak_prominence"].get_top_peaks_prominence, list(spec), fs, k) == \
+            _run(ref_port.top_peaks_prominence, list(spec), fs, k)
+        assert _run(ref["get_peak_resolution"].get_top_peaks_resolution, list(spec), fs, k) == \
+            _run(ref_port.top_peaks_resolution, list(spec), fs, k)
