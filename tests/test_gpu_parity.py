@@ -671,27 +671,22 @@ def _outcome(fn, *args, **kw):
 
 
 def test_fuzz_small_windows_and_spectra_vs_oracle(an):
-    """The adversarial inputs that pin the oracle to the live reference (tests/test_oracle.py, 400 windows of length
-    1..256 with ties / plateaus / offsets and 300 hand-shaped spectra with k = 1..7), through the CUDA path: fp64 spectra
-    bit-identical, peak dicts equal objects, same exception types for degenerate sizes."""
-    from apda_fft_b200.records import prominence_dicts, resolution_dicts
+    """The adversarial inputs that pin the oracle to the live reference (tests/test_oracle.py: 400 windows of length
+    1..256 with ties / plateaus / offsets, 300 hand-shaped spectra with k = 1..7) through the drop-in modules, i.e.
+    the reference's own call signatures on the CUDA path: spectra equal element by element (fp64 bit-exact), peak
+    lists equal objects, same exception types for degenerate sizes."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "apda-fft_b200"))
+    from metrics.fft_iterativa import start_fft
+    from utils.get_peak_prominence import get_top_peaks_prominence
+    from utils.get_peak_resolution import get_top_peaks_resolution
     from test_oracle import _fuzz_inputs, _fuzz_spectra
     for x in _fuzz_inputs(20260101, 400):
-        xs = np.asarray(x, dtype=np.float64)
         want = ref_port.start_fft(list(x), 125.0)
-        n = len(want)
-        got = an.fft(xs)[0]
-        assert np.array_equal(got.view(np.float64), np.asarray(want, dtype=np.complex128).view(np.float64)), x
-        for flexible, port, conv in ((True, ref_port.top_peaks_prominence, prominence_dicts),
-                                     (False, ref_port.top_peaks_resolution, resolution_dicts)):
-            ref = _outcome(port, list(want), 125.0)
-            mine = _outcome(lambda: [conv(r, 125.0, n) for r in an.analyze(xs, 125.0, flexible=flexible)][0])
-            assert ref == mine, (x, flexible)
+        got = start_fft(list(x), 125.0)
+        assert len(got) == len(want) and all(complex(a) == complex(b) for a, b in zip(got, want)), x
+        assert _outcome(get_top_peaks_prominence, got, 125.0) == _outcome(ref_port.top_peaks_prominence, list(want), 125.0), x
+        assert _outcome(get_top_peaks_resolution, got, 125.0) == _outcome(ref_port.top_peaks_resolution, list(want), 125.0), x
     for spec, fs, k in _fuzz_spectra(7, 300):
-        z = np.asarray(spec, dtype=np.complex128)
-        n = z.shape[0]
-        for flexible, port, conv in ((True, ref_port.top_peaks_prominence, prominence_dicts),
-                                     (False, ref_port.top_peaks_resolution, resolution_dicts)):
-            ref = _outcome(port, list(spec), fs, k)
-            mine = _outcome(lambda: conv(an.peaks(z, fs, flexible=flexible, k=k)[0], fs, n))
-            assert ref == mine, (n, fs, k, flexible)
+        assert _outcome(get_top_peaks_prominence, list(spec), fs, k) == _outcome(ref_port.top_peaks_prominence, list(spec), fs, k)
+        assert _outcome(get_top_peaks_resolution, list(spec), fs, k) == _outcome(ref_port.top_peaks_resolution, list(spec), fs, k)
