@@ -4,7 +4,7 @@
 namespace {
 
 template <int N, int CENTER, bool FULL>
-__global__ void __launch_bounds__(Plan<N>::WPB *(N / 32))
+__global__ void __launch_bounds__(Plan<N>::WPB *(N / 32), Plan<N>::MINB)
 fft_f32_fast_kernel(const float *__restrict__ samples, int n_samples, int64_t ld, int64_t batch,
                     const float2 *__restrict__ tw1,  // [R1][S1]: W_M^{c*k1}
                     const float2 *__restrict__ twu,  // [M]: -i/2 * W_N^k

@@ -132,16 +132,23 @@ __device__ __forceinline__ const float2 *const_tw2() {
     return N == 1024 ? c_tw2_1024 : N == 2048 ? c_tw2_2048 : N == 4096 ? c_tw2_4096 : c_tw2_8192;
 }
 
+// Resident CTAs per SM the pipeline K1 is compiled for at N = 4096.  One window per CTA and a serial chain of phases
+// (load, median rounds, three passes, split) make the kernel's rate "resident CTAs / per-window latency": 9 CTAs
+// (56 registers, no spills) measured 7-9 % faster than the 8 that 60 registers allow, 10 (48 registers, spills) slower;
+// a shared-memory carve-out that leaves less L1 for the twiddle tables costs 15 %.
+#ifndef APDA_K1_MINB
+#define APDA_K1_MINB 9
+#endif
 template <int N>
 struct Plan;
 template <>
-struct Plan<8192> { static constexpr int R1 = 16, R2 = 16, R3 = 16, WPB = 1; };
+struct Plan<8192> { static constexpr int R1 = 16, R2 = 16, R3 = 16, WPB = 1, MINB = 1; };
 template <>
-struct Plan<4096> { static constexpr int R1 = 16, R2 = 16, R3 = 8, WPB = 1; };
+struct Plan<4096> { static constexpr int R1 = 16, R2 = 16, R3 = 8, WPB = 1, MINB = APDA_K1_MINB; };
 template <>
-struct Plan<2048> { static constexpr int R1 = 16, R2 = 8, R3 = 8, WPB = 2; };
+struct Plan<2048> { static constexpr int R1 = 16, R2 = 8, R3 = 8, WPB = 2, MINB = 1; };
 template <>
-struct Plan<1024> { static constexpr int R1 = 8, R2 = 8, R3 = 8, WPB = 4; };
+struct Plan<1024> { static constexpr int R1 = 8, R2 = 8, R3 = 8, WPB = 4, MINB = 1; };
 
 // ---- per-window barrier: windows that share a block do not run in lockstep ------------------------------------------
 template <int T>
