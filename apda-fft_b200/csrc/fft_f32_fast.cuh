@@ -136,25 +136,39 @@ __device__ __forceinline__ const float2 *const_tw2() {
 // (load, median rounds, three passes, split) make the kernel's rate "resident CTAs / per-window latency": 9 CTAs
 // (56 registers, no spills) measured 7-9 % faster than the 8 that 60 registers allow, 10 (48 registers, spills) slower;
 // a shared-memory carve-out that leaves less L1 for the twiddle tables costs 15 %.
+// Same reasoning for the other sizes (same-box A/B, exact-median K1): N = 8192 with 4 CTAs (64 registers) instead of the 3
+// that 84 registers allow: 5.32 -> 3.91 ms per 200k windows (mean centring: 6.0-6.2 TB/s, 92-94 % of the copy
+// bandwidth); N = 2048 / 1024 with 8 CTAs of 128 threads (64 registers instead of 88 / 84): -12 % / -8 %.
+#ifndef APDA_K1_MINB_2048
+#define APDA_K1_MINB_2048 8
+#endif
+#ifndef APDA_K1_MINB_1024
+#define APDA_K1_MINB_1024 8
+#endif
+#ifndef APDA_K1_MINB_8192
+#define APDA_K1_MINB_8192 4
+#endif
 #ifndef APDA_K1_MINB
 #define APDA_K1_MINB 9
 #endif
 template <int N>
 struct Plan;
 template <>
-struct Plan<8192> { static constexpr int R1 = 16, R2 = 16, R3 = 16, WPB = 1, MINB = 1; };
+struct Plan<8192> { static constexpr int R1 = 16, R2 = 16, R3 = 16, WPB = 1, MINB = APDA_K1_MINB_8192; };
 template <>
 struct Plan<4096> { static constexpr int R1 = 16, R2 = 16, R3 = 8, WPB = 1, MINB = APDA_K1_MINB; };
 template <>
-struct Plan<2048> { static constexpr int R1 = 16, R2 = 8, R3 = 8, WPB = 2, MINB = 1; };
+struct Plan<2048> { static constexpr int R1 = 16, R2 = 8, R3 = 8, WPB = 2, MINB = APDA_K1_MINB_2048; };
 template <>
-struct Plan<1024> { static constexpr int R1 = 8, R2 = 8, R3 = 8, WPB = 4, MINB = 1; };
+struct Plan<1024> { static constexpr int R1 = 8, R2 = 8, R3 = 8, WPB = 4, MINB = APDA_K1_MINB_1024; };
 
 // ---- per-window barrier: windows that share a block do not run in lockstep ------------------------------------------
 template <int T>
 __device__ __forceinline__ void group_sync(int slot) {
+    // literal barrier ids (at most two windows per block use barriers): a register id would reserve all 16 per CTA
     if (T == 32) __syncwarp();
-    else asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "r"(T) : "memory");
+    else if (slot == 0) asm volatile("bar.sync 1, %0;" ::"n"(T) : "memory");
+    else asm volatile("bar.sync 2, %0;" ::"n"(T) : "memory");
 }
 
 __device__ __forceinline__ float next_above(float v) {  // smallest float strictly greater than v (finite v)
