@@ -178,7 +178,7 @@ large_tail_kernel(typename vec2<T>::type *__restrict__ spec, int n, int s0, int 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 3 : 1)  // fp32: 3 tiles per SM in flight (load / compute / store)
 large_tail_tma_kernel(const __grid_constant__ CUtensorMap tmap, int n, int s0, int q, int C,
                       const typename vec2<T>::type *__restrict__ tw, int zero_dc) {
     using V2 = typename vec2<T>::type;
