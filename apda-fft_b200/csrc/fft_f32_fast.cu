@@ -9,12 +9,10 @@ fft_f32_fast_kernel(const float *__restrict__ samples, int n_samples, int64_t ld
                     const float2 *__restrict__ tw1,  // [R1][S1]: W_M^{c*k1}
                     const float2 *__restrict__ twu,  // [M]: -i/2 * W_N^k
                     float2 *__restrict__ spec, const int *__restrict__ nv) {
-    constexpr int center = CENTER;
     using P = Plan<N>;
     constexpr int M = N / 2, R1 = P::R1, R2 = P::R2, R3 = P::R3, T = M / 16, WPB = P::WPB;
     constexpr int S1 = R2 * R3;            // columns of pass 1
     constexpr int LD = S1 + 16 / R1;       // padded row stride (complex elements): LD*R1 >= M
-    constexpr int G1 = 16 / R1, G2 = 16 / R2, G3 = 16 / R3;
     static_assert(R1 * R2 * R3 == M, "plan");
     __shared__ __align__(16) float2 sm[WPB][R1 * LD];
     __shared__ uint32_t sel[WPB][64];

@@ -13,7 +13,6 @@ __global__ void __launch_bounds__(32 * kWPC)
 peaks_f32_fast_kernel(const float2 *__restrict__ spec, int64_t batch, double df_all, const double *__restrict__ d_fs,
                       int k, unsigned char *__restrict__ recs, int *__restrict__ repair) {
     using P = K3<float, HALF>;
-    constexpr int C = P::C;
     constexpr int N = 2 * HALF;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int nslot_s[kWPC];
