@@ -193,3 +193,18 @@ def test_gateway_entry_and_fleet_table(golden):
     count, idx, freq, mag = fleet_table(recs, 125.0, 1024)
     assert count.tolist() == [2, 0] and idx[0, :2].tolist() == [25, 63] and freq[0, 0] == 25 * (125.0 / 1024)
     assert np.isnan(freq[1]).all() and mag[0, 1] == 149.3
+
+
+def _build_c_example(tmp_path):
+    import subprocess
+    exe = os.path.join(str(tmp_path), "analyze_host")
+    libdir = os.path.join(ROOT, "apda-fft_b200")
+    subprocess.check_call(["gcc", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "analyze_host.c"), "-L", libdir, "-lapda_b200",
+                           f"-Wl,-rpath,{libdir}", "-lm", "-o", exe])
+    return exe
+
+
+def test_c_host_example_compiles_and_links(lib, tmp_path):
+    """include/apda_b200.h is a plain-C header and the library links from C (no CUDA headers, no Python)."""
+    assert os.path.exists(_build_c_example(tmp_path))

@@ -690,3 +690,14 @@ def test_fuzz_small_windows_and_spectra_vs_oracle(an):
     for spec, fs, k in _fuzz_spectra(7, 300):
         assert _outcome(get_top_peaks_prominence, list(spec), fs, k) == _outcome(ref_port.top_peaks_prominence, list(spec), fs, k)
         assert _outcome(get_top_peaks_resolution, list(spec), fs, k) == _outcome(ref_port.top_peaks_resolution, list(spec), fs, k)
+
+
+def test_c_host_example_runs(tmp_path):
+    """examples/analyze_host.c (plain C over the C ABI): three tones per window at the expected bins."""
+    import subprocess
+    from test_cabi_and_host import _build_c_example
+    out = subprocess.check_output([_build_c_example(tmp_path)], text=True)
+    rows = [r for r in out.splitlines() if r.startswith("window")]
+    assert len(rows) == 8
+    for w, row in enumerate(rows):
+        assert f"window {w}: 3 peaks" in row and "idx 252" in row and "idx 498" in row and f"idx {round(101.6 + w)}" in row, row
