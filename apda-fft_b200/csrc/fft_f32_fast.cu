@@ -1,4 +1,6 @@
 // K1 (fp32 fast form): the pipeline kernel (samples -> N complex bins in HBM).  The transform lives in fft_f32_fast.cuh.
+#include <mutex>
+
 #include "fft_f32_fast.cuh"
 
 namespace {
@@ -65,13 +67,20 @@ struct FastTables {
 struct FastCache {
     std::map<int64_t, FastTables> tabs;
 };
-static std::map<apda_ctx *, FastCache> g_fast;  // contexts are single-threaded by contract
+// one entry per context; a context belongs to one host thread, but different threads may hold different contexts, so the
+// map itself is guarded (the entries are only touched by their owner)
+static std::map<apda_ctx *, FastCache> g_fast;
+static std::mutex g_fast_mu;
+static FastCache &fast_cache_of(apda_ctx *ctx) {
+    std::lock_guard<std::mutex> lock(g_fast_mu);
+    return g_fast[ctx];  // std::map nodes are stable: the reference stays valid while other contexts come and go
+}
 
 template <int N>
 static int fast_tables(apda_ctx *ctx, FastTables *out) {
     using P = Plan<N>;
     constexpr int M = N / 2, R1 = P::R1, R2 = P::R2, R3 = P::R3, S1 = R2 * R3;
-    auto &cache = g_fast[ctx].tabs;
+    auto &cache = fast_cache_of(ctx).tabs;
     auto it = cache.find(N);
     if (it != cache.end()) {
         *out = it->second;
@@ -157,6 +166,7 @@ int launch_fft_f32_fast(apda_ctx *ctx, cudaStream_t st, const float *d_samples, 
 }
 
 void fft_f32_fast_release(apda_ctx *ctx) {
+    std::lock_guard<std::mutex> lock(g_fast_mu);
     auto it = g_fast.find(ctx);
     if (it == g_fast.end()) return;
     for (auto &kv : it->second.tabs) {

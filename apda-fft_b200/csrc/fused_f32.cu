@@ -6,6 +6,8 @@
 // s*N bytes in and 128 bytes out (16 512 B at N = 4096) instead of the pipeline's 4*s*N + 128: the spectrum never exists
 // in memory.  This is a throughput variant: the drop-in start_fft contract (N bins materialised) stays with the
 // pipeline kernels, and results are reported under their own byte accounting (never mixed with B_alg numbers).
+#include <mutex>
+
 #include "fft_f32_fast.cuh"
 #include "peaks_fast.cuh"
 
@@ -100,10 +102,14 @@ fused_f32_kernel(const float *__restrict__ samples, int n_samples, int64_t ld, i
 }
 
 // this translation unit owns its own copy of the __constant__ pass-2 twiddles (anonymous namespace in the header)
+// (constant memory is per device: uploaded once per device the library is used on)
 template <int N>
-int upload_tw2() {
-    static bool done = false;
-    if (done) return APDA_OK;
+int upload_tw2(int device) {
+    static std::vector<int> done;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    for (int d : done)
+        if (d == device) return APDA_OK;
     using P = Plan<N>;
     constexpr int R2 = P::R2, R3 = P::R3;
     const double two_pi = 6.283185307179586476925286766559;
@@ -116,7 +122,7 @@ int upload_tw2() {
     const void *sym = N == 1024 ? (const void *)c_tw2_1024 : N == 2048 ? (const void *)c_tw2_2048
                     : N == 4096 ? (const void *)c_tw2_4096 : (const void *)c_tw2_8192;
     APDA_CUDA(cudaMemcpyToSymbol(sym, h2.data(), h2.size() * sizeof(float2)));
-    done = true;
+    done.push_back(device);
     return APDA_OK;
 }
 
@@ -125,7 +131,7 @@ int launch_fused_n(apda_ctx *ctx, cudaStream_t st, const float *d_samples, int64
                    int flags, int flexible, double fs, const double *d_fs, int k, void *d_rec) {
     const float2 *tw1, *twu;
     APDA_TRY(fft_f32_fast_get_tables(ctx, N, &tw1, &twu));
-    APDA_TRY(upload_tw2<N>());
+    APDA_TRY(upload_tw2<N>(ctx->device));
     const size_t need = ((size_t)batch + 1) * sizeof(int);
     if (need > ctx->repair_bytes) {
         APDA_CUDA(cudaStreamSynchronize(st));
