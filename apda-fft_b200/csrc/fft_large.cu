@@ -292,6 +292,9 @@ struct SelectState {            // device resident
     long long rank;             // rank still to resolve inside the prefix bucket
     unsigned hist[256];
     unsigned long long found[2];  // lower / upper middle keys
+    // compaction after the first two digit passes: the bucket that holds the median, copied out
+    unsigned long long above_min;  // smallest key in the buckets above it
+    unsigned long long m;          // elements in the bucket
 };
 
 template <typename T>
@@ -334,6 +337,8 @@ __global__ void select_reset_kernel(SelectState *st, long long rank) {
         st->prefix = 0;
         st->mask = 0;
         st->rank = rank;
+        st->above_min = ~0ull;
+        st->m = 0;
     }
     st->hist[threadIdx.x] = 0;
 }
@@ -376,8 +381,139 @@ __global__ void select_prepare_upper_kernel(SelectState *st) {
     st->mask = ~0ull;
 }
 
+// After two digit passes the bucket of the median holds a small fraction of the window (sensor samples: a few percent).
+// One more pass over the window copies that bucket out (warp-aggregated append) and records the smallest key of the
+// buckets above it; everything else runs on the copy, in one CTA.
 template <typename T>
-int large_median(apda_ctx *ctx, cudaStream_t st, const T *d_x, int64_t n, SelectState *state, T *d_med) {
+__global__ void __launch_bounds__(256) select_compact_kernel(const T *__restrict__ x, int64_t n, SelectState *st,
+                                                             T *__restrict__ bucket) {
+    using K = typename KeyT<T>::type;
+    __shared__ unsigned long long blk_min[8];
+    const K prefix = (K)st->prefix, mask = (K)st->mask;
+    const int lane = threadIdx.x & 31;
+    unsigned long long above = ~0ull;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t rounds = (n + stride - 1) / stride;
+    for (int64_t it = 0; it < rounds; ++it) {
+        const int64_t i = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const bool valid = i < n;
+        const T v = valid ? x[i] : T(0);
+        const K k = ordered_key(v);
+        const bool in = valid && (k & mask) == prefix;
+        if (valid && (k & mask) > prefix && (unsigned long long)k < above) above = (unsigned long long)k;
+        const unsigned hit = __ballot_sync(0xffffffffu, in);
+        if (hit) {
+            unsigned long long base = 0;
+            if (lane == __ffs(hit) - 1) base = atomicAdd(&st->m, (unsigned long long)__popc(hit));
+            base = __shfl_sync(0xffffffffu, base, __ffs(hit) - 1);
+            if (in) bucket[base + __popc(hit & ((1u << lane) - 1u))] = v;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, above, o);
+        above = other < above ? other : above;
+    }
+    if (lane == 0) blk_min[threadIdx.x >> 5] = above;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) above = blk_min[w] < above ? blk_min[w] : above;
+        if (above != ~0ull) atomicMin(&st->above_min, above);
+    }
+}
+
+// the remaining digits, the upper middle value and statistics.median itself, on the copied bucket, one CTA
+template <typename T>
+__global__ void __launch_bounds__(1024) select_small_kernel(const T *__restrict__ bucket, SelectState *st, int64_t n,
+                                                             int first_shift, T *med_out) {
+    using K = typename KeyT<T>::type;
+    __shared__ unsigned h[256];
+    __shared__ unsigned long long s_prefix, s_mask, s_le, s_above;
+    __shared__ long long s_rank;
+    const long long m = (long long)st->m;
+    if (threadIdx.x == 0) {
+        s_prefix = st->prefix;
+        s_mask = st->mask;
+        s_rank = st->rank;  // rank of the lower middle inside the bucket
+        s_le = 0;
+        s_above = ~0ull;
+    }
+    for (int shift = first_shift; shift >= 0; shift -= 8) {
+        if (threadIdx.x < 256) h[threadIdx.x] = 0;
+        __syncthreads();
+        const K prefix = (K)s_prefix, mask = (K)s_mask;
+        for (long long i = threadIdx.x; i < m; i += blockDim.x) {
+            const K k = ordered_key(bucket[i]);
+            if ((k & mask) == prefix) atomicAdd(&h[(unsigned)(k >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long rank = s_rank;
+            unsigned long long acc = 0;
+            int digit = 255;
+            for (int d = 0; d < 256; ++d) {
+                if (rank < (long long)(acc + h[d])) {
+                    digit = d;
+                    break;
+                }
+                acc += h[d];
+            }
+            s_rank = rank - (long long)acc;
+            s_prefix |= (unsigned long long)digit << shift;
+            s_mask |= 255ull << shift;
+        }
+        __syncthreads();
+    }
+    // lower middle = s_prefix.  Upper middle: the same key if its duplicates reach across the midpoint, else the smallest
+    // key above it (inside the bucket, or the smallest key of the buckets above)
+    const K lo = (K)s_prefix;
+    unsigned long long le = 0, above = ~0ull;
+    for (long long i = threadIdx.x; i < m; i += blockDim.x) {
+        const K k = ordered_key(bucket[i]);
+        le += (k <= lo);
+        if (k > lo && (unsigned long long)k < above) above = (unsigned long long)k;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        le += __shfl_xor_sync(0xffffffffu, le, o);
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, above, o);
+        above = other < above ? other : above;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_le, le);
+        atomicMin(&s_above, above);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // elements below the bucket: the rank the search started with minus the rank left when the bucket was fixed
+        const long long below = (long long)((n - 1) / 2) - st->rank;
+        const unsigned long long up = s_above < st->above_min ? s_above : st->above_min;
+        const K hi = (below + (long long)s_le >= (long long)(n / 2 + 1)) ? lo : (K)up;
+        const T a = key_value(lo, T(0)), b = key_value(hi, T(0));
+        *med_out = div_rn(add_rn(a, b), T(2));  // statistics.median: middle value, or (a + b) / 2 for even n
+    }
+}
+
+template <typename T>
+int large_median(apda_ctx *ctx, cudaStream_t st, const T *d_x, int64_t n, SelectState *state, T *d_med, T *d_bucket) {
+    const int bits = (int)sizeof(T) * 8;
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8);
+    select_reset_kernel<<<1, 256, 0, st>>>(state, (long long)((n - 1) / 2));
+    for (int shift = bits - 8; shift >= bits - 16; shift -= 8) {  // two most significant digits on the whole window
+        select_hist_kernel<T><<<grid, 256, 0, st>>>(d_x, n, shift, state);
+        select_pick_kernel<<<1, 32, 0, st>>>(state, shift, 0, 0);
+    }
+    select_compact_kernel<T><<<grid, 256, 0, st>>>(d_x, n, state, d_bucket);
+    select_small_kernel<T><<<1, 1024, 0, st>>>(d_bucket, state, n, bits - 24, d_med);
+    ctx->launches += 7;
+    APDA_CUDA(cudaGetLastError());
+    return APDA_OK;
+}
+
+// the earlier form (eight full histogram passes + one pass for the upper middle); kept as the reference implementation for
+// apda_ctx_set_generic_only
+template <typename T>
+int large_median_passes(apda_ctx *ctx, cudaStream_t st, const T *d_x, int64_t n, SelectState *state, T *d_med) {
     const int bits = (int)sizeof(T) * 8;
     const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8);
     select_reset_kernel<<<1, 256, 0, st>>>(state, (long long)((n - 1) / 2));
@@ -428,7 +564,8 @@ int launch_fft_large(apda_ctx *ctx, cudaStream_t st, const T *d_samples, int64_t
     T *d_med = nullptr;
     if (!complex_input && flags != APDA_CENTER_NONE) {
         // per-stream scratch: the two host-pipeline streams may run long transforms concurrently
-        const size_t need = 2048 + (size_t)batch * sizeof(T);
+        const size_t med_bytes = ((size_t)batch * sizeof(T) + 255) & ~(size_t)255;
+        const size_t need = 2048 + med_bytes + (size_t)n_samples * sizeof(T);  // state, medians, bucket copy (worst case: all samples)
         auto &slot = ctx->stream_scratch[st];
         if (need > slot.second) {
             APDA_CUDA(cudaStreamSynchronize(st));
@@ -436,7 +573,11 @@ int launch_fft_large(apda_ctx *ctx, cudaStream_t st, const T *d_samples, int64_t
         }
         SelectState *state = reinterpret_cast<SelectState *>(slot.first);
         d_med = reinterpret_cast<T *>(reinterpret_cast<char *>(slot.first) + 2048);
-        for (int64_t w = 0; w < batch; ++w) APDA_TRY(large_median<T>(ctx, st, d_samples + w * ld, n_samples, state, d_med + w));
+        T *d_bucket = reinterpret_cast<T *>(reinterpret_cast<char *>(slot.first) + 2048 + med_bytes);
+        for (int64_t w = 0; w < batch; ++w) {
+            if (ctx->generic_only) APDA_TRY(large_median_passes<T>(ctx, st, d_samples + w * ld, n_samples, state, d_med + w));
+            else APDA_TRY(large_median<T>(ctx, st, d_samples + w * ld, n_samples, state, d_med + w, d_bucket));
+        }
     }
 
     {  // head pass
