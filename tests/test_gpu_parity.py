@@ -701,3 +701,32 @@ def test_c_host_example_runs(tmp_path):
     assert len(rows) == 8
     for w, row in enumerate(rows):
         assert f"window {w}: 3 peaks" in row and "idx 252" in row and "idx 498" in row and f"idx {round(101.6 + w)}" in row, row
+
+
+@pytest.mark.parametrize("n_samples", [1 << 16, (1 << 16) - 1, 50_001])
+def test_large_window_median_adversarial(n_samples, an):
+    """K2's median (two digit passes, bucket copy, one-CTA finish) on distributions that stress it: constant windows,
+    three-level plateaus (the bucket is a third of the window), half the samples equal to the median, and middle
+    values that sit in different top-16-bit buckets (the upper middle comes from the buckets above).  The centred
+    spectrum must stay bit-identical to the C oracle, which takes the exact statistics.median."""
+    rng = np.random.default_rng(n_samples)
+    n = 1 << 16
+    half = n_samples // 2
+    rows = [np.full(n_samples, 0.731),
+            rng.integers(-1, 2, n_samples).astype(np.float64),
+            np.where(rng.random(n_samples) < 0.5, 0.25, np.round(rng.standard_normal(n_samples), 6)),
+            np.concatenate([np.full(half, 0.99999), np.full(n_samples - half, 1.00001)]),
+            np.concatenate([np.full(half, -2.5), np.full(n_samples - half, 3.0e5)]),
+            np.round(np.exp(3.0 * rng.standard_normal(n_samples)), 6)]
+    for r, x in enumerate(rows):
+        x = rng.permutation(x)
+        got = an.fft(x[None, :], n_fft=n)
+        want = c_oracle.start_fft_batch(x[None, :], n_fft=n)
+        assert np.array_equal(got.view(np.float64), want.view(np.float64)), (n_samples, r)
+        x32 = x.astype(np.float32)
+        got32 = an.fft(x32[None, :], n_fft=n)[0]
+        centred = x32 - np.float32(np.median(x32))                   # exact in fp32: midpoint of two floats
+        ref32 = np.fft.fft(np.concatenate([centred.astype(np.float64), np.zeros(n - n_samples)]))
+        ref32[0] = 0
+        scale = np.abs(ref32).max() + 1e-30
+        assert np.abs(got32 - ref32).max() <= 2e-5 * scale + 1e-3, (n_samples, r)
