@@ -312,23 +312,30 @@ __global__ void __launch_bounds__(256) select_hist_kernel(const T *__restrict__ 
     if (h[threadIdx.x]) atomicAdd(&st->hist[threadIdx.x], h[threadIdx.x]);
 }
 
-__global__ void select_pick_kernel(SelectState *st, int shift, int which, int last) {
-    if (threadIdx.x == 0) {
-        long long rank = st->rank;
-        unsigned long long acc = 0;
-        int digit = 255;
-        for (int d = 0; d < 256; ++d) {
-            if (rank < (long long)(acc + st->hist[d])) {
-                digit = d;
-                break;
-            }
-            acc += st->hist[d];
-        }
-        st->rank = rank - (long long)acc;
-        st->prefix |= (unsigned long long)digit << shift;
+__global__ void __launch_bounds__(256) select_pick_kernel(SelectState *st, int shift, int which, int last) {
+    // 256 threads: inclusive scan of the digit histogram, the digit whose cumulative count first exceeds the rank wins
+    __shared__ unsigned long long cum[256];
+    const int d = threadIdx.x;
+    const unsigned mine = st->hist[d];
+    cum[d] = mine;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+        const unsigned long long add = d >= o ? cum[d - o] : 0ull;
+        __syncthreads();
+        cum[d] += add;
+        __syncthreads();
+    }
+    const long long rank = st->rank;
+    const unsigned long long before = cum[d] - mine;
+    const bool winner = rank >= (long long)before && rank < (long long)cum[d];
+    const bool none = d == 255 && rank >= (long long)cum[255];  // cannot happen for a consistent state: keep digit 255
+    __syncthreads();
+    st->hist[d] = 0;
+    if (winner || none) {
+        st->rank = rank - (long long)(none ? cum[254] : before);
+        st->prefix |= (unsigned long long)d << shift;
         st->mask |= 255ull << shift;
         if (last) st->found[which] = st->prefix;
-        for (int d = 0; d < 256; ++d) st->hist[d] = 0;
     }
 }
 
@@ -501,7 +508,7 @@ int large_median(apda_ctx *ctx, cudaStream_t st, const T *d_x, int64_t n, Select
     select_reset_kernel<<<1, 256, 0, st>>>(state, (long long)((n - 1) / 2));
     for (int shift = bits - 8; shift >= bits - 16; shift -= 8) {  // two most significant digits on the whole window
         select_hist_kernel<T><<<grid, 256, 0, st>>>(d_x, n, shift, state);
-        select_pick_kernel<<<1, 32, 0, st>>>(state, shift, 0, 0);
+        select_pick_kernel<<<1, 256, 0, st>>>(state, shift, 0, 0);
     }
     select_compact_kernel<T><<<grid, 256, 0, st>>>(d_x, n, state, d_bucket);
     select_small_kernel<T><<<1, 1024, 0, st>>>(d_bucket, state, n, bits - 24, d_med);
@@ -519,7 +526,7 @@ int large_median_passes(apda_ctx *ctx, cudaStream_t st, const T *d_x, int64_t n,
     select_reset_kernel<<<1, 256, 0, st>>>(state, (long long)((n - 1) / 2));
     for (int shift = bits - 8; shift >= 0; shift -= 8) {
         select_hist_kernel<T><<<grid, 256, 0, st>>>(d_x, n, shift, state);
-        select_pick_kernel<<<1, 32, 0, st>>>(state, shift, 0, shift == 0);
+        select_pick_kernel<<<1, 256, 0, st>>>(state, shift, 0, shift == 0);
         ctx->launches += 2;
     }
     select_prepare_upper_kernel<<<1, 1, 0, st>>>(state);
