@@ -730,3 +730,38 @@ def test_large_window_median_adversarial(n_samples, an):
         ref32[0] = 0
         scale = np.abs(ref32).max() + 1e-30
         assert np.abs(got32 - ref32).max() <= 2e-5 * scale + 1e-3, (n_samples, r)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+def test_no_out_of_bounds_writes_guard_bands(dtype, an):
+    """compute-sanitizer is not available on this pool, so: every output buffer (spectra, records) sits between guard
+    bands that must come back untouched, for odd batch sizes (partly filled last CTA), every fast-path size, both pickers,
+    padded windows, and a K2 size."""
+    import torch
+    dev = torch.device("cuda:0")
+    an.use_stream(torch.cuda.current_stream(dev).cuda_stream)
+    tdt = torch.float32 if dtype == "f32" else torch.float64
+    s = 4 if dtype == "f32" else 8
+    guard = 8192
+    try:
+        for n, b, n_samples in ((1024, 37, 1024), (2048, 5, 2001), (4096, 33, 4096), (8192, 3, 8192), (4096, 1, 3000),
+                                (1 << 15, 2, 30000)):
+            x = torch.randn((b, n_samples), dtype=tdt, device=dev).round(decimals=4)
+            spec_raw = torch.full((guard + b * n * 2 * s + guard,), 0xA5, dtype=torch.uint8, device=dev)
+            rec_raw = torch.full((guard + b * 128 + guard,), 0x5A, dtype=torch.uint8, device=dev)
+            spec_ptr, rec_ptr = spec_raw.data_ptr() + guard, rec_raw.data_ptr() + guard
+            for flexible in (True, False):
+                an.fft_device(x.data_ptr(), b, n_samples, n, dtype, spec_ptr)
+                an.peaks_device(spec_ptr, b, n, dtype, 125.0, rec_ptr, flexible=flexible, k=4 if flexible else 5)
+                an.analyze_device(x.data_ptr(), b, n_samples, n, dtype, 125.0, rec_ptr, flexible=flexible,
+                                  k=4 if flexible else 5, d_spec_ws=spec_ptr)
+                if dtype == "f32" and n <= 8192:
+                    an.analyze_fused_device(x.data_ptr(), b, n_samples, n, 125.0, rec_ptr, flexible=flexible,
+                                            k=4 if flexible else 5)
+            torch.cuda.synchronize()
+            for raw, fill, what in ((spec_raw, 0xA5, "spectra"), (rec_raw, 0x5A, "records")):
+                assert bool((raw[:guard] == fill).all()) and bool((raw[-guard:] == fill).all()), (n, b, what)
+            recs = rec_raw[guard:-guard].cpu().numpy()
+            assert (recs.view(np.int32).reshape(b, 32)[:, 0] <= 5).all()      # count fields are sane
+    finally:
+        an.ctx.set_stream(None)
