@@ -64,3 +64,56 @@ def fleet_table(recs, fs, n: int, flexible: bool = True, k: int = 4):
     freq = np.where(idx >= 0, idx * (fs_col / n), np.nan)
     mag = np.where(idx >= 0, recs["pk"]["mag"][:, :k], np.nan)
     return recs["count"].astype(np.int64), idx, freq, mag
+
+
+def upload_metrics(summary: dict, axis: str, fft_entry: dict) -> dict:
+    """The ``metriche`` block the reference's uploader derives for one file (utils/fastapi_manager.py:37-47, 58-64):
+    RMS-vector angles from the summary line, the axis' own RMS and the top-4 peak arrays of ``gateway_entry``
+    (missing peaks are 0.0, as ``current_fft.get(..., 0.0)`` does there).  Pure host arithmetic, same operation order."""
+    from math import acos, atan2, degrees
+    m1, m2, m3 = summary["rms_x"], summary["rms_y"], summary["rms_z"]
+    accrms = (m1 ** 2 + m2 ** 2 + m3 ** 2) ** 0.5
+    return {
+        "temp": summary["temperature"],
+        "humidity": summary.get("humidity", 0.0),
+        "phi": degrees(atan2(m2, m1)),
+        "theta": degrees(acos(m3 / accrms)) if accrms != 0 else 0,
+        "rms_asse": {"X": m1, "Y": m2, "Z": m3}.get(axis, 0.0),
+        "fft_freqs": [fft_entry.get(f"peak_freq_{i}", 0.0) for i in range(1, 5)],
+        "fft_mags": [fft_entry.get(f"max_mag_{i}", 0.0) for i in range(1, 5)],
+    }
+
+
+def fleet_arrow(recs, fs, n: int, flexible: bool = True, k: int = 4, first_window: int = 0):
+    """Columnar table (pyarrow) of a record batch for bulk consumers on rank 0: one row per window,
+    list columns ``idx`` / ``freq`` / ``mag`` hold the ``count`` peaks in the picker's output order (raw doubles)."""
+    import numpy as np
+    import pyarrow as pa
+    count, idx, freq, mag = fleet_table(recs, fs, n, flexible, k)
+    count = np.minimum(count, k)
+    offsets = np.concatenate([[0], np.cumsum(count)]).astype(np.int32)
+    keep = np.arange(k)[None, :] < count[:, None]
+
+    def ragged(values, typ):
+        return pa.ListArray.from_arrays(pa.array(offsets), pa.array(values[keep], type=typ))
+    return pa.table({"window": pa.array(np.arange(first_window, first_window + count.shape[0], dtype=np.int64)),
+                     "count": pa.array(count), "idx": ragged(idx, pa.int64()), "freq": ragged(freq, pa.float64()),
+                     "mag": ragged(mag, pa.float64())})
+
+
+def write_fleet_jsonl(path, recs, fs, n: int, flexible: bool = True, k: int = 4, first_window: int = 0) -> int:
+    """One JSON object per window: ``{"window", "fft_freqs", "fft_mags"}`` with the reference's rounded values
+    (prominence_dicts / resolution_dicts), padded with 0.0 to k entries like the uploader's payload.  Returns the rows."""
+    import json
+    import numpy as np
+    recs = np.asarray(recs)
+    fs_col = np.broadcast_to(np.asarray(fs, dtype=np.float64), (recs.shape[0],))
+    conv = prominence_dicts if flexible else resolution_dicts
+    with open(path, "w") as fh:
+        for w in range(recs.shape[0]):
+            peaks = conv(recs[w], float(fs_col[w]), n)[:k]
+            row = {"window": first_window + w,
+                   "fft_freqs": [p["freq"] for p in peaks] + [0.0] * (k - len(peaks)),
+                   "fft_mags": [p["mag"] for p in peaks] + [0.0] * (k - len(peaks))}
+            fh.write(json.dumps(row) + "\n")
+    return int(recs.shape[0])

@@ -208,3 +208,44 @@ def _build_c_example(tmp_path):
 def test_c_host_example_compiles_and_links(lib, tmp_path):
     """include/apda_b200.h is a plain-C header and the library links from C (no CUDA headers, no Python)."""
     assert os.path.exists(_build_c_example(tmp_path))
+
+
+def test_result_packing_arrow_jsonl_and_upload_metrics(golden, tmp_path):
+    """columnar / JSONL packing of a record batch and the uploader's `metriche` block."""
+    import json
+    import subprocess
+    from apda_fft_b200.records import (fleet_arrow, gateway_entry, record_dtype, upload_metrics, write_fleet_jsonl,
+                                       prominence_dicts)
+    recs = np.zeros(3, dtype=record_dtype(5))
+    recs["pk"]["idx"] = -1
+    recs[0]["count"] = 2
+    recs[0]["pk"][0] = (25, 2, 195.8331234, 195.7)
+    recs[0]["pk"][1] = (63, 2, 149.3, 149.1)
+    recs[2]["count"] = 1
+    recs[2]["pk"][0] = (100, 3, 12.5, 12.0)
+    tab = fleet_arrow(recs, 125.0, 1024, first_window=40)
+    assert tab.column("window").to_pylist() == [40, 41, 42] and tab.column("count").to_pylist() == [2, 0, 1]
+    assert tab.column("idx").to_pylist() == [[25, 63], [], [100]]
+    assert tab.column("freq").to_pylist()[0] == [25 * (125.0 / 1024), 63 * (125.0 / 1024)]
+    assert tab.column("mag").to_pylist()[2] == [12.5]
+    path = os.path.join(str(tmp_path), "fleet.jsonl")
+    assert write_fleet_jsonl(path, recs, 125.0, 1024, first_window=40) == 3
+    rows = [json.loads(ln) for ln in open(path)]
+    want0 = prominence_dicts(recs[0], 125.0, 1024)
+    assert rows[0] == {"window": 40, "fft_freqs": [want0[0]["freq"], want0[1]["freq"], 0.0, 0.0],
+                       "fft_mags": [want0[0]["mag"], want0[1]["mag"], 0.0, 0.0]}
+    assert rows[1]["fft_freqs"] == [0.0] * 4 and rows[2]["fft_mags"][0] == 12.5
+
+    summary = {"temperature": 25.01, "rms_x": -0.0222, "rms_y": 0.011, "rms_z": 0.9981, "humidity": 85.0}
+    entry = gateway_entry(golden["cases"]["katA"]["prominence"]["ok"])
+    got = upload_metrics(summary, "Z", entry)
+    assert got["rms_asse"] == 0.9981 and got["fft_freqs"][:3] == [3.0518, 7.6904, 15.1367] and got["fft_freqs"][3] == 0.0
+    if os.path.isdir("/root/reference"):   # the live uploader's payload for the same file and fft_dict entry
+        log = os.path.join(str(tmp_path), "0013a20041e7f6b7_01_02_2024_03_04_05_Zaxis.log")
+        with open(log, "w") as fh:
+            fh.write(LOG_TEXT.replace("31.25 Hz;Z axis", "125.0 Hz;Z axis"))
+        code = ("import json,sys; sys.path.insert(0, '/root/reference'); from utils.fastapi_manager import FastAPIHandler; "
+                f"p = FastAPIHandler('x')._prepare_payload('mac', {os.path.basename(log)!r}, {str(tmp_path)!r}, "
+                f"{{'Z': {entry!r}}}); print(json.dumps(p['metriche']))")
+        ref = json.loads(subprocess.check_output([sys.executable, "-c", code], text=True))
+        assert ref == json.loads(json.dumps(got))
