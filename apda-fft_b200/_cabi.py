@@ -11,7 +11,8 @@ import statistics
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libapda_b200.so")
+# APDA_LIB: another build of the same library (same-box A/B measurements of kernel variants; see build.py APDA_LIB_OUT)
+LIB_PATH = os.environ.get("APDA_LIB") or os.path.join(HERE, "libapda_b200.so")
 
 OK = 0
 ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_STATS_MEAN, ERR_STATS_STDEV = -1, -2, -3, -4, -5, -6, -7

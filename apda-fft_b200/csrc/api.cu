@@ -47,6 +47,25 @@ int apda_reserve(void **buf, size_t *have, size_t need) {
     return APDA_OK;
 }
 
+static int stream_list(cudaStream_t st, int **buf, size_t *have, int64_t batch, int **out) {
+    const size_t need = ((size_t)batch + 1) * sizeof(int);
+    if (need > *have) {
+        APDA_CUDA(cudaStreamSynchronize(st));  // the old list may still be read by kernels queued on this stream
+        APDA_TRY(apda_reserve((void **)buf, have, need));
+    }
+    APDA_CUDA(cudaMemsetAsync(*buf, 0, sizeof(int), st));
+    *out = *buf;
+    return APDA_OK;
+}
+int apda_repair_list(apda_ctx *ctx, cudaStream_t st, int64_t batch, int **out) {
+    auto &l = ctx->stream_lists[st];
+    return stream_list(st, &l.repair, &l.repair_bytes, batch, out);
+}
+int apda_ragged_list(apda_ctx *ctx, cudaStream_t st, int64_t batch, int **out) {
+    auto &l = ctx->stream_lists[st];
+    return stream_list(st, &l.ragged, &l.ragged_bytes, batch, out);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------------------------
@@ -101,8 +120,10 @@ extern "C" int apda_ctx_destroy(apda_ctx *ctx) {
     fft_f32_fast_release(ctx);
     cudaFree(ctx->ws);
     cudaFree(ctx->ws_small);
-    cudaFree(ctx->repair);
-    cudaFree(ctx->ragged);
+    for (auto &kv : ctx->stream_lists) {
+        cudaFree(kv.second.repair);
+        cudaFree(kv.second.ragged);
+    }
     for (auto &kv : ctx->stream_scratch) cudaFree(kv.second.first);
     for (int i = 0; i < 2; ++i) {
         cudaFree(ctx->ws_pipe[i]);
@@ -287,11 +308,11 @@ __global__ void ragged_list_kernel(const int *__restrict__ nv, int64_t batch, in
 
 // record status of ragged windows: bit 2 = the window's own padded length differs from the batch N (the reference would
 // transform at that other length), bit 3 = empty window (the reference's pickers raise StatisticsError on start_fft([]))
-__global__ void ragged_status_kernel(const int *__restrict__ list, const int *__restrict__ nv, int64_t N,
+__global__ void ragged_status_kernel(const int *__restrict__ nv, int64_t batch, int64_t N,
                                      unsigned char *__restrict__ recs, int64_t rec_bytes) {
-    for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < list[0]; it += gridDim.x * blockDim.x) {
-        const int w = list[1 + it];
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < batch; w += (int64_t)gridDim.x * blockDim.x) {
         const int n = nv[w];
+        if (n == N) continue;
         int64_t p = 1;
         while (p < n) p <<= 1;
         int *hdr = reinterpret_cast<int *>(recs + (int64_t)w * rec_bytes);
@@ -302,15 +323,6 @@ __global__ void ragged_status_kernel(const int *__restrict__ list, const int *__
             hdr[1] |= 4;
         }
     }
-}
-
-static int reserve_ragged(apda_ctx *ctx, cudaStream_t st, int64_t batch) {
-    const size_t need = ((size_t)batch + 1) * sizeof(int);
-    if (need > ctx->ragged_bytes) {
-        APDA_CUDA(cudaStreamSynchronize(st));
-        APDA_TRY(apda_reserve((void **)&ctx->ragged, &ctx->ragged_bytes, need));
-    }
-    return APDA_OK;
 }
 
 template <typename T>
@@ -329,9 +341,9 @@ static int fft_dispatch_ragged(apda_ctx *ctx, cudaStream_t st, const T *d_sample
     const bool fast64 = sizeof(T) == 8 && !ctx->generic_only && fft_f64_fast_supports(N);
     if (!fast32 && !fast64)
         return launch_fft_smem<T>(ctx, st, d_samples, n_max, ld, batch, N, flags, d_spec, false, d_nv, nullptr);
-    APDA_TRY(reserve_ragged(ctx, st, batch));
-    APDA_CUDA(cudaMemsetAsync(ctx->ragged, 0, sizeof(int), st));
-    ragged_list_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, st>>>(d_nv, batch, (int)n_max, ctx->ragged);
+    int *ragged = nullptr;
+    APDA_TRY(apda_ragged_list(ctx, st, batch, &ragged));
+    ragged_list_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, st>>>(d_nv, batch, (int)n_max, ragged);
     ctx->launches++;
     if (fast32)
         APDA_TRY(launch_fft_f32_fast(ctx, st, reinterpret_cast<const float *>(d_samples), n_max, ld, batch, N, flags,
@@ -339,7 +351,7 @@ static int fft_dispatch_ragged(apda_ctx *ctx, cudaStream_t st, const T *d_sample
     else
         APDA_TRY(launch_fft_f64_fast(ctx, st, reinterpret_cast<const double *>(d_samples), n_max, ld, batch, N, flags,
                                      reinterpret_cast<double *>(d_spec), d_nv));
-    return launch_fft_smem<T>(ctx, st, d_samples, n_max, ld, batch, N, flags, d_spec, false, d_nv, ctx->ragged);
+    return launch_fft_smem<T>(ctx, st, d_samples, n_max, ld, batch, N, flags, d_spec, false, d_nv, ragged);
 }
 
 static int check_ragged_args(apda_ctx *ctx, const void *in, const void *nv, int64_t n_max, int64_t ld, int64_t batch,
@@ -357,10 +369,10 @@ static int analyze_ragged_dev(apda_ctx *ctx, cudaStream_t st, const T *d_samples
                               int rec_cap, T *d_spec, void *d_rec, void **ws, size_t *ws_bytes, size_t ws_off) {
     APDA_TRY(fft_dispatch_ragged<T>(ctx, st, d_samples, d_nv, n_max, ld, batch, N, flags, d_spec));
     APDA_TRY(peaks_dispatch<T>(ctx, st, d_spec, N, batch, fs, d_fs, k, rec_cap, flexible, d_rec, ws, ws_bytes, ws_off));
-    if (batch > 0 && ctx->ragged && ((sizeof(T) == 4 && !ctx->generic_only && fft_f32_fast_supports(N)) ||
-                                     (sizeof(T) == 8 && !ctx->generic_only && fft_f64_fast_supports(N)))) {
-        ragged_status_kernel<<<64, 256, 0, st>>>(ctx->ragged, d_nv, N, reinterpret_cast<unsigned char *>(d_rec),
-                                                 APDA_REC_BYTES(rec_cap));
+    if (batch > 0) {  // every ragged path (specialised or general kernels): the status bits only depend on d_nv
+        const unsigned blocks = (unsigned)std::min<int64_t>((batch + 255) / 256, 1024);
+        ragged_status_kernel<<<blocks, 256, 0, st>>>(d_nv, batch, N, reinterpret_cast<unsigned char *>(d_rec),
+                                                     APDA_REC_BYTES(rec_cap));
         ctx->launches++;
         APDA_CUDA(cudaGetLastError());
     }
@@ -528,12 +540,11 @@ static int host_pipeline(apda_ctx *ctx, HostMode mode, const T *h_in, int64_t n_
         if (batch <= chunk) break;  // single chunk: one stream is enough
     }
 
-    int status = APDA_OK;
-    int64_t done = 0;
-    for (int c = 0; done < batch && status == APDA_OK; ++c) {
+    // one chunk; an error returns from the lambda only, so the caller below always drains both streams before it
+    // reports (async copies from / into the caller's buffers must not outlive the call)
+    auto run_chunk = [&](int c, int64_t done, int64_t cnt) -> int {
         const int s = c & 1;
         cudaStream_t st = ctx->pipe[s];
-        const int64_t cnt = std::min<int64_t>(chunk, batch - done);
         char *base = (char *)ctx->ws_pipe[s];
         T *d_in = (T *)base;
         T *d_spec = (T *)(base + in_bytes);
@@ -553,28 +564,32 @@ static int host_pipeline(apda_ctx *ctx, HostMode mode, const T *h_in, int64_t n_
 
         const T *spec_for_peaks = d_in;
         if (mode == kFused) {
-            status = launch_fused_f32(ctx, st, reinterpret_cast<const float *>(d_in), n_samples, (int64_t)in_elems, cnt, N,
-                                      flags, flexible, fs, d_fs, k, d_rec);
-            if (status == APDA_OK)
-                APDA_CUDA(cudaMemcpyAsync((char *)h_rec_out + (size_t)done * rec_bytes, d_rec, cnt * rec_bytes,
-                                          cudaMemcpyDeviceToHost, st));
-            done += cnt;
-            continue;
+            APDA_TRY(launch_fused_f32(ctx, st, reinterpret_cast<const float *>(d_in), n_samples, (int64_t)in_elems, cnt, N,
+                                      flags, flexible, fs, d_fs, k, d_rec));
+            APDA_CUDA(cudaMemcpyAsync((char *)h_rec_out + (size_t)done * rec_bytes, d_rec, cnt * rec_bytes,
+                                      cudaMemcpyDeviceToHost, st));
+            return APDA_OK;
         }
         if (mode != kPeaksOnly) {
-            status = fft_dispatch<T>(ctx, st, d_in, n_samples, (int64_t)in_elems, cnt, N, flags, d_spec, complex_in);
+            APDA_TRY(fft_dispatch<T>(ctx, st, d_in, n_samples, (int64_t)in_elems, cnt, N, flags, d_spec, complex_in));
             spec_for_peaks = d_spec;
-            if (status == APDA_OK && mode == kFftOnly)
+            if (mode == kFftOnly)
                 APDA_CUDA(cudaMemcpyAsync(h_spec_out + (size_t)done * spec_elems, d_spec, cnt * spec_elems * sizeof(T),
                                           cudaMemcpyDeviceToHost, st));
         }
-        if (status == APDA_OK && mode != kFftOnly) {
-            status = peaks_dispatch<T>(ctx, st, spec_for_peaks, N, cnt, fs, d_fs, k, rec_cap, flexible, d_rec, &mag_ws,
-                                       &mag_have, 0);
-            if (status == APDA_OK)
-                APDA_CUDA(cudaMemcpyAsync((char *)h_rec_out + (size_t)done * rec_bytes, d_rec, cnt * rec_bytes,
-                                          cudaMemcpyDeviceToHost, st));
+        if (mode != kFftOnly) {
+            APDA_TRY(peaks_dispatch<T>(ctx, st, spec_for_peaks, N, cnt, fs, d_fs, k, rec_cap, flexible, d_rec, &mag_ws,
+                                       &mag_have, 0));
+            APDA_CUDA(cudaMemcpyAsync((char *)h_rec_out + (size_t)done * rec_bytes, d_rec, cnt * rec_bytes,
+                                      cudaMemcpyDeviceToHost, st));
         }
+        return APDA_OK;
+    };
+    int status = APDA_OK;
+    int c = 0;
+    for (int64_t done = 0; done < batch && status == APDA_OK; ++c) {
+        const int64_t cnt = std::min<int64_t>(chunk, batch - done);
+        status = run_chunk(c, done, cnt);
         done += cnt;
     }
     cudaError_t e0 = cudaStreamSynchronize(ctx->pipe[0]);
@@ -738,12 +753,9 @@ static int wire16_host(apda_ctx *ctx, const uint8_t *h_payload, int64_t n_max, i
         }
         if (batch <= chunk) break;
     }
-    int status = APDA_OK;
-    int64_t done = 0;
-    for (int c = 0; done < batch && status == APDA_OK; ++c) {
+    auto run_chunk = [&](int c, int64_t done, int64_t cnt) -> int {  // see host_pipeline: errors never skip the drain
         const int s = c & 1;
         cudaStream_t st = ctx->pipe[s];
-        const int64_t cnt = std::min<int64_t>(chunk, batch - done);
         char *base = (char *)ctx->ws_pipe[s];
         unsigned char *d_pay = (unsigned char *)base;
         double *d_fv = (double *)(base + pay_b);
@@ -762,20 +774,25 @@ static int wire16_host(apda_ctx *ctx, const uint8_t *h_payload, int64_t n_max, i
                                         (size_t)n_max * 2, cnt, cudaMemcpyHostToDevice, st));
         APDA_CUDA(cudaMemcpyAsync(d_fv, h_first_value + done, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
         if (d_fs) APDA_CUDA(cudaMemcpyAsync(d_fs, h_fs + done, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
-        status = launch_decode_wire16<T>(ctx, st, d_pay, n_max, (int64_t)n_max * 2, cnt, d_fv, d_smp, n_max, d_nv);
-        if (status != APDA_OK) break;
+        APDA_TRY(launch_decode_wire16<T>(ctx, st, d_pay, n_max, (int64_t)n_max * 2, cnt, d_fv, d_smp, n_max, d_nv));
         if (h_samples_out)
             APDA_CUDA(cudaMemcpyAsync(h_samples_out + (size_t)done * n_max, d_smp, cnt * (size_t)n_max * sizeof(T),
                                       cudaMemcpyDeviceToHost, st));
         if (h_n_valid_out)
             APDA_CUDA(cudaMemcpyAsync(h_n_valid_out + done, d_nv, cnt * sizeof(int), cudaMemcpyDeviceToHost, st));
         if (analyze) {
-            status = analyze_ragged_dev<T>(ctx, st, d_smp, d_nv, n_max, n_max, cnt, N, flags, flexible, fs, d_fs, k, rec_cap,
-                                           d_spec, d_rec, &mag_ws, &mag_have, 0);
-            if (status == APDA_OK)
-                APDA_CUDA(cudaMemcpyAsync((char *)h_rec + (size_t)done * rec_bytes, d_rec, cnt * rec_bytes,
-                                          cudaMemcpyDeviceToHost, st));
+            APDA_TRY(analyze_ragged_dev<T>(ctx, st, d_smp, d_nv, n_max, n_max, cnt, N, flags, flexible, fs, d_fs, k, rec_cap,
+                                           d_spec, d_rec, &mag_ws, &mag_have, 0));
+            APDA_CUDA(cudaMemcpyAsync((char *)h_rec + (size_t)done * rec_bytes, d_rec, cnt * rec_bytes,
+                                      cudaMemcpyDeviceToHost, st));
         }
+        return APDA_OK;
+    };
+    int status = APDA_OK;
+    int c = 0;
+    for (int64_t done = 0; done < batch && status == APDA_OK; ++c) {
+        const int64_t cnt = std::min<int64_t>(chunk, batch - done);
+        status = run_chunk(c, done, cnt);
         done += cnt;
     }
     cudaError_t e0 = cudaStreamSynchronize(ctx->pipe[0]);
@@ -854,13 +871,12 @@ static int text_host(apda_ctx *ctx, const char *h_text, const int64_t *h_offsets
         }
         if (batch <= chunk) break;
     }
-    std::vector<int64_t> rel[2];
-    int status = APDA_OK;
-    int64_t done = 0;
-    for (int c = 0; done < batch && status == APDA_OK; ++c) {
+    // chunk-relative offsets: one host vector per chunk, alive until the drain below (the H2D copies read them
+    // asynchronously), so no chunk has to wait for the previous one on its stream
+    std::vector<std::vector<int64_t>> rel((size_t)((batch + chunk - 1) / chunk));
+    auto run_chunk = [&](int c, int64_t done, int64_t cnt) -> int {  // see host_pipeline: errors never skip the drain
         const int s = c & 1;
         cudaStream_t st = ctx->pipe[s];
-        const int64_t cnt = std::min<int64_t>(chunk, batch - done);
         char *base = (char *)ctx->ws_pipe[s];
         char *d_txt = base;
         int64_t *d_off = (int64_t *)(base + txt_b);
@@ -872,26 +888,31 @@ static int text_host(apda_ctx *ctx, const char *h_text, const int64_t *h_offsets
         double *d_fs = fs_b ? (double *)(base + txt_b + off_b + smp_b + nv_b + fl_b + spec_b + recs_b) : nullptr;
         void *mag_ws = mag_b ? base + txt_b + off_b + smp_b + nv_b + fl_b + spec_b + recs_b + fs_b : nullptr;
         size_t mag_have = mag_b;
-        APDA_CUDA(cudaStreamSynchronize(st));  // rel[s] is reused: the previous chunk on this stream must have consumed it
-        rel[s].resize((size_t)cnt + 1);
-        for (int64_t i = 0; i <= cnt; ++i) rel[s][(size_t)i] = h_offsets[done + i] - h_offsets[done];
-        APDA_CUDA(cudaMemcpyAsync(d_txt, h_text + h_offsets[done], (size_t)rel[s][(size_t)cnt], cudaMemcpyHostToDevice, st));
-        APDA_CUDA(cudaMemcpyAsync(d_off, rel[s].data(), (size_t)(cnt + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        std::vector<int64_t> &r = rel[(size_t)c];
+        r.resize((size_t)cnt + 1);
+        for (int64_t i = 0; i <= cnt; ++i) r[(size_t)i] = h_offsets[done + i] - h_offsets[done];
+        APDA_CUDA(cudaMemcpyAsync(d_txt, h_text + h_offsets[done], (size_t)r[(size_t)cnt], cudaMemcpyHostToDevice, st));
+        APDA_CUDA(cudaMemcpyAsync(d_off, r.data(), (size_t)(cnt + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
         if (d_fs) APDA_CUDA(cudaMemcpyAsync(d_fs, h_fs + done, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
-        status = launch_parse_samples<T>(ctx, st, d_txt, d_off, cnt, n_max, d_smp, d_nv, d_fl);
-        if (status != APDA_OK) break;
+        APDA_TRY(launch_parse_samples<T>(ctx, st, d_txt, d_off, cnt, n_max, d_smp, d_nv, d_fl));
         if (h_samples_out)
             APDA_CUDA(cudaMemcpyAsync(h_samples_out + (size_t)done * n_max, d_smp, cnt * (size_t)n_max * sizeof(T),
                                       cudaMemcpyDeviceToHost, st));
         APDA_CUDA(cudaMemcpyAsync(h_n_valid + done, d_nv, cnt * sizeof(int), cudaMemcpyDeviceToHost, st));
         APDA_CUDA(cudaMemcpyAsync(h_flags + done, d_fl, cnt * sizeof(int), cudaMemcpyDeviceToHost, st));
         if (analyze) {
-            status = analyze_ragged_dev<T>(ctx, st, d_smp, d_nv, n_max, n_max, cnt, N, flags, flexible, fs, d_fs, k, rec_cap,
-                                           d_spec, d_rec, &mag_ws, &mag_have, 0);
-            if (status == APDA_OK)
-                APDA_CUDA(cudaMemcpyAsync((char *)h_rec + (size_t)done * rec_bytes, d_rec, cnt * rec_bytes,
-                                          cudaMemcpyDeviceToHost, st));
+            APDA_TRY(analyze_ragged_dev<T>(ctx, st, d_smp, d_nv, n_max, n_max, cnt, N, flags, flexible, fs, d_fs, k, rec_cap,
+                                           d_spec, d_rec, &mag_ws, &mag_have, 0));
+            APDA_CUDA(cudaMemcpyAsync((char *)h_rec + (size_t)done * rec_bytes, d_rec, cnt * rec_bytes,
+                                      cudaMemcpyDeviceToHost, st));
         }
+        return APDA_OK;
+    };
+    int status = APDA_OK;
+    int c = 0;
+    for (int64_t done = 0; done < batch && status == APDA_OK; ++c) {
+        const int64_t cnt = std::min<int64_t>(chunk, batch - done);
+        status = run_chunk(c, done, cnt);
         done += cnt;
     }
     cudaError_t e0 = cudaStreamSynchronize(ctx->pipe[0]);

@@ -36,10 +36,16 @@ struct apda_ctx {
     size_t ws_small_bytes = 0;
     int64_t launches = 0;
     std::map<cudaStream_t, std::pair<void *, size_t>> stream_scratch;  // K2 median state, one per stream
-    int *ragged = nullptr;  // ragged batches: windows whose length differs from the batch's common length
-    size_t ragged_bytes = 0;
-    int *repair = nullptr;  // K3 fast path: windows handed over to the general kernel
-    size_t repair_bytes = 0;
+    // device-side window lists ([0] = count, [1..] = window ids), one set PER STREAM: the two host-pipeline streams run
+    // chunks concurrently, so a list shared by the context would be zeroed / appended to by one chunk while the other
+    // chunk's kernels still read it
+    struct StreamLists {
+        int *ragged = nullptr;  // ragged batches: windows whose length differs from the batch's common length
+        size_t ragged_bytes = 0;
+        int *repair = nullptr;  // K3 fast path: windows handed over to the general kernel
+        size_t repair_bytes = 0;
+    };
+    std::map<cudaStream_t, StreamLists> stream_lists;
     int generic_only = 0;  // debug/test switch: bypass the specialised fp32 kernels
 };
 
@@ -58,6 +64,9 @@ int apda_cuda_fail(cudaError_t e, const char *what);
 
 int apda_get_twiddles(apda_ctx *ctx, int64_t N, TwiddleTables *out);
 int apda_reserve(void **buf, size_t *have, size_t need);
+// per-stream window lists of `batch + 1` ints, zero count enqueued on `st` (see apda_ctx::stream_lists)
+int apda_repair_list(apda_ctx *ctx, cudaStream_t st, int64_t batch, int **out);
+int apda_ragged_list(apda_ctx *ctx, cudaStream_t st, int64_t batch, int **out);
 
 static inline int ilog2_i64(int64_t v) {
     int l = 0;

@@ -132,12 +132,8 @@ int launch_fused_n(apda_ctx *ctx, cudaStream_t st, const float *d_samples, int64
     const float2 *tw1, *twu;
     APDA_TRY(fft_f32_fast_get_tables(ctx, N, &tw1, &twu));
     APDA_TRY(upload_tw2<N>(ctx->device));
-    const size_t need = ((size_t)batch + 1) * sizeof(int);
-    if (need > ctx->repair_bytes) {
-        APDA_CUDA(cudaStreamSynchronize(st));
-        APDA_TRY(apda_reserve((void **)&ctx->repair, &ctx->repair_bytes, need));
-    }
-    APDA_CUDA(cudaMemsetAsync(ctx->repair, 0, sizeof(int), st));
+    int *repair = nullptr;  // never appended to (the slot list is sized for the worst case); k3_tail wants a valid pointer
+    APDA_TRY(apda_repair_list(ctx, st, batch, &repair));
     const bool full = n_samples == N && (reinterpret_cast<uintptr_t>(d_samples) & 7u) == 0 && (ld & 1) == 0;
     const bool med = flags == APDA_CENTER_MEDIAN;
     void (*kern)(const float *, int, int64_t, int64_t, const float2 *, const float2 *, double, const double *, int,
@@ -155,7 +151,7 @@ int launch_fused_n(apda_ctx *ctx, cudaStream_t st, const float *d_samples, int64
     const size_t smem = sizeof(float2) * P::R1 * (P::R2 * P::R3 + 16 / P::R1) + K3<float, N / 2>::BYTES;
     APDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)batch, N / 32, smem, st>>>(d_samples, (int)n_samples, ld, batch, tw1, twu, fs / (double)N, d_fs, k,
-                                            reinterpret_cast<unsigned char *>(d_rec), ctx->repair);
+                                            reinterpret_cast<unsigned char *>(d_rec), repair);
     ctx->launches++;
     APDA_CUDA(cudaGetLastError());
     return APDA_OK;
@@ -163,7 +159,6 @@ int launch_fused_n(apda_ctx *ctx, cudaStream_t st, const float *d_samples, int64
 
 }  // namespace
 
-// windows whose candidate list overflowed are listed in ctx->repair; the caller re-runs them through the pipeline
 int launch_fused_f32(apda_ctx *ctx, cudaStream_t st, const float *d_samples, int64_t n_samples, int64_t ld, int64_t batch,
                      int64_t N, int flags, int flexible, double fs, const double *d_fs, int k, void *d_rec) {
     switch (N) {

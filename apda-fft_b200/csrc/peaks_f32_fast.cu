@@ -74,19 +74,15 @@ int launch_half(apda_ctx *ctx, cudaStream_t st, const float *d_spec, int64_t bat
     APDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int64_t blocks = (batch + kWPC - 1) / kWPC;
     // repair list: [0] = count, [1..] = windows whose candidate list did not fit on chip
-    const size_t need = ((size_t)batch + 1) * sizeof(int);
-    if (need > ctx->repair_bytes) {
-        APDA_CUDA(cudaStreamSynchronize(st));
-        APDA_TRY(apda_reserve((void **)&ctx->repair, &ctx->repair_bytes, need));
-    }
-    APDA_CUDA(cudaMemsetAsync(ctx->repair, 0, sizeof(int), st));
+    int *repair = nullptr;
+    APDA_TRY(apda_repair_list(ctx, st, batch, &repair));
     kern<<<(unsigned)blocks, 32 * kWPC, smem, st>>>(reinterpret_cast<const float2 *>(d_spec), batch,
                                                     fs / (double)(2 * HALF), d_fs, k,
-                                                    reinterpret_cast<unsigned char *>(d_rec), ctx->repair);
+                                                    reinterpret_cast<unsigned char *>(d_rec), repair);
     ctx->launches++;
     APDA_CUDA(cudaGetLastError());
     // the general kernel re-does the listed windows (grid-stride over the device-side count; exits at once if empty)
-    return launch_peaks_general_listed(ctx, st, d_spec, 2 * HALF, batch, fs, d_fs, k, 5, flexible, d_rec, ctx->repair);
+    return launch_peaks_general_listed(ctx, st, d_spec, 2 * HALF, batch, fs, d_fs, k, 5, flexible, d_rec, repair);
 }
 
 }  // namespace

@@ -207,19 +207,15 @@ int launch_half64(apda_ctx *ctx, cudaStream_t st, const double *d_spec, int64_t 
     APDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     APDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     const int64_t blocks = (batch + kWPC64 - 1) / kWPC64;
-    const size_t need = ((size_t)batch + 1) * sizeof(int);  // repair list, see peaks_f32_fast.cu
-    if (need > ctx->repair_bytes) {
-        APDA_CUDA(cudaStreamSynchronize(st));
-        APDA_TRY(apda_reserve((void **)&ctx->repair, &ctx->repair_bytes, need));
-    }
-    APDA_CUDA(cudaMemsetAsync(ctx->repair, 0, sizeof(int), st));
+    int *repair = nullptr;  // repair list, see peaks_f32_fast.cu
+    APDA_TRY(apda_repair_list(ctx, st, batch, &repair));
     kern<<<(unsigned)blocks, 32 * kWPWof<HALF> * kWPC64, smem, st>>>(reinterpret_cast<const double2 *>(d_spec), batch,
                                                       fs / (double)(2 * HALF), d_fs, k,
-                                                      reinterpret_cast<unsigned char *>(d_rec), ctx->repair);
+                                                      reinterpret_cast<unsigned char *>(d_rec), repair);
     ctx->launches++;
     APDA_CUDA(cudaGetLastError());
     return launch_peaks_general_listed<double>(ctx, st, d_spec, 2 * HALF, batch, fs, d_fs, k, 5, flexible, d_rec,
-                                               ctx->repair);
+                                               repair);
 }
 
 }  // namespace
