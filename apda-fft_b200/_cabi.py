@@ -79,6 +79,25 @@ SIGNATURES = {
 }
 
 
+def max_peaks(n: int) -> int:
+    """include/apda_b200.h APDA_MAX_PEAKS(n): most peaks one window of n bins can report."""
+    return int(n) // 8 + 8
+
+
+# record status bits (include/apda_b200.h)
+STATUS_TRUNCATED, STATUS_OTHER_LENGTH, STATUS_EMPTY, STATUS_FP32_TIE = 1, 4, 8, 16
+
+
+def check_record_status(recs) -> None:
+    """The drop-in modules return reference-equivalent results or raise: a record whose status is not 0 (candidate
+    list truncated, window transformed at another length, empty window) must never be handed out silently."""
+    import numpy as np
+    bad = np.flatnonzero(np.asarray(recs["status"]) != 0)
+    if bad.size:
+        raise ApdaError(ERR_UNSUPPORTED, f"record status {int(recs['status'][bad[0]])} on window {int(bad[0])} "
+                                         f"({bad.size} of {len(recs)} windows): the result is not reference-equivalent")
+
+
 class ApdaError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"libapda_b200 error {code}: {message}")

@@ -70,8 +70,10 @@ class Analyzer:
         return recs
 
     def analyze(self, samples: np.ndarray, fs, flexible: bool = True, k: int | None = None,
-                n_fft: int | None = None, center: int = _cabi.CENTER_MEDIAN, rec_cap: int | None = None) -> np.ndarray:
-        """[B, n_samples] real (float32 or float64) -> records[B]; spectra never leave the device."""
+                n_fft: int | None = None, center: int = _cabi.CENTER_MEDIAN, rec_cap: int | None = None,
+                resolve_ties: bool = True) -> np.ndarray:
+        """[B, n_samples] real (float32 or float64) -> records[B]; spectra never leave the device.  float32 windows
+        whose record carries APDA_STATUS_FP32_TIE are re-run in float64 (``resolve_ties``)."""
         x = np.ascontiguousarray(np.atleast_2d(samples))
         sfx = _suffix(x.dtype)
         b, ns = x.shape
@@ -82,7 +84,19 @@ class Analyzer:
         fs_scalar, fs_arr = self._fs(fs, b)
         self.ctx.call(f"apda_analyze_{sfx}_host", _p(x.ctypes.data), ns, ns, b, n, center, int(bool(flexible)),
                       fs_scalar, _p(fs_arr.ctypes.data if fs_arr is not None else 0), k, cap, _p(recs.ctypes.data))
+        if sfx == "f32" and resolve_ties:
+            self._resolve_fp32_ties(x, recs, fs, flexible, k, n, cap)
         return recs
+
+    def _resolve_fp32_ties(self, x, recs, fs, flexible, k, n, cap) -> int:
+        """Windows flagged APDA_STATUS_FP32_TIE (two equal fp32 magnitudes at a peak top: no strict local maximum, so
+        the fp32 picker dropped a peak the fp64 reference reports) are re-run through the fp64 pipeline on the same
+        samples and their records replaced.  About one window in 10^6 of the fleet generator."""
+        tied = np.flatnonzero(recs["status"] & _cabi.STATUS_FP32_TIE)
+        if tied.size:
+            fs_sel = fs if np.isscalar(fs) else np.asarray(fs, dtype=np.float64)[tied]
+            recs[tied] = self.analyze(x[tied].astype(np.float64), fs_sel, flexible=flexible, k=k, n_fft=n, rec_cap=cap)
+        return int(tied.size)
 
     def analyze_fused(self, samples: np.ndarray, fs, flexible: bool = True, k: int | None = None,
                       center: int = _cabi.CENTER_MEDIAN) -> np.ndarray:
@@ -117,8 +131,11 @@ class Analyzer:
         return out, nv
 
     def analyze_wire16(self, payload: np.ndarray, first_value, fs, n_fft: int | None = None, dtype: str = "f64",
-                       flexible: bool = True, k: int | None = None) -> np.ndarray:
-        """uint8[B, 2*n] payload rows -> records[B] (decode, drop non-finite, centre, FFT, pick; all on the device)."""
+                       flexible: bool = True, k: int | None = None, strict: bool = False) -> np.ndarray:
+        """uint8[B, 2*n] payload rows -> records[B] (decode, drop non-finite, centre, FFT, pick; all on the device).
+        Windows that lost samples keep their record but carry status bits (APDA_STATUS_OTHER_LENGTH: the reference
+        would have transformed them at their own padded length; APDA_STATUS_EMPTY: its pickers raise): inspect
+        ``recs["status"]``, or pass ``strict=True`` to raise when any window is not reference-equivalent."""
         pay = np.ascontiguousarray(np.atleast_2d(payload), dtype=np.uint8)
         b, nb = pay.shape
         n = nb // 2
@@ -131,6 +148,8 @@ class Analyzer:
         self.ctx.call(f"apda_analyze_wire16_{dtype}_host", _p(pay.ctypes.data), n, nb, b, _p(fv.ctypes.data), nfft,
                       _cabi.CENTER_MEDIAN, int(bool(flexible)), fs_scalar,
                       _p(fs_arr.ctypes.data if fs_arr is not None else 0), k, cap, _p(recs.ctypes.data))
+        if strict:
+            _cabi.check_record_status(recs)
         return recs
 
     def analyze_host_ptr(self, h_ptr: int, batch: int, n_samples: int, n_fft: int, dtype: str, fs: float,

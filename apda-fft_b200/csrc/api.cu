@@ -252,8 +252,11 @@ static int check_peaks_args(apda_ctx *ctx, const void *spec, int64_t n, int64_t 
         apda_set_error("stdev requires at least two data points");
         return APDA_ERR_STATS_STDEV;
     }
-    if (k < 1 || rec_cap < k || rec_cap > APDA_MAX_REC_CAP) {
-        apda_set_error("peaks: need 1 <= k (%d) <= rec_cap (%d) <= %d", k, rec_cap, APDA_MAX_REC_CAP);
+    // a window holds at most n/8 + 8 peaks (candidates are strict local maxima above mean + 2 sigma: < 20 % of the
+    // half spectrum's bins by Cantelli's inequality), so wider records than that are never needed
+    if (k < 1 || rec_cap < k || (rec_cap > APDA_MAX_REC_CAP && (int64_t)rec_cap > APDA_MAX_PEAKS(n))) {
+        apda_set_error("peaks: need 1 <= k (%d) <= rec_cap (%d) <= max(%d, n/8 + 8 = %lld)", k, rec_cap, APDA_MAX_REC_CAP,
+                       (long long)APDA_MAX_PEAKS(n));
         return APDA_ERR_INVALID;
     }
     return APDA_OK;
@@ -1083,6 +1086,8 @@ __global__ void peer_signal_kernel(unsigned *flag, unsigned value) {
 __global__ void peer_wait_kernel(const unsigned *flags, int world, unsigned value, long long timeout_cycles,
                                  int *timed_out) {
     const int r = threadIdx.x;
+    if (r == 0) *timed_out = 0;  // the word reports THIS wait, not an earlier one
+    __syncwarp();
     if (r >= world) return;
     const long long t0 = clock64();
     while (true) {
@@ -1090,7 +1095,7 @@ __global__ void peer_wait_kernel(const unsigned *flags, int world, unsigned valu
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
         if ((int)(v - value) >= 0) break;
         if (clock64() - t0 > timeout_cycles) {  // a peer died: never hang the device
-            *timed_out = 1;
+            atomicExch(timed_out, 1);
             break;
         }
         __nanosleep(200);

@@ -38,7 +38,7 @@ __device__ void load_magnitudes(const typename vec2<T>::type *spec, T *mags, int
 }
 
 struct Layout {  // per-window scratch: magnitudes, candidate indices, surviving candidates
-    size_t mags_off, cand_off, found_off, bytes;
+    size_t mags_off, cand_off, found_off, acc_off, bytes;
     int cap;
 };
 template <typename T>
@@ -50,6 +50,8 @@ __host__ __device__ inline Layout make_layout(int half) {
     l.found_off = o;
     o += (size_t)l.cap * sizeof(Found);
     l.cand_off = o;
+    o += (size_t)l.cap * sizeof(int);
+    l.acc_off = o;  // accepted peaks (slot / bin index): any k up to cap, not a fixed-size array
     o += (size_t)l.cap * sizeof(int);
     l.bytes = (o + 15) & ~(size_t)15;
     return l;
@@ -64,18 +66,19 @@ __device__ void peaks_prominence_window(const int64_t win, const typename vec2<T
     __shared__ dd red[64];
     __shared__ Stats stats_s;
     __shared__ int ncand_s, nfound_s;
-    __shared__ int acc_slot[APDA_MAX_REC_CAP];
     const Layout lay = make_layout<T>(half);
     unsigned char *base = SMEM ? smem_raw : ws + (size_t)blockIdx.x * lay.bytes;
     T *mags = reinterpret_cast<T *>(base + lay.mags_off);
     Found *found = reinterpret_cast<Found *>(base + lay.found_off);
     int *cand = reinterpret_cast<int *>(base + lay.cand_off);
+    int *acc_slot = reinterpret_cast<int *>(base + lay.acc_off);
     const int tid = threadIdx.x;
     unsigned char *rec = recs + win * APDA_REC_BYTES(rec_cap);
     const double fs = d_fs ? d_fs[win] : fs_all;
     const double df = div_rn(fs, (double)n);
 
-    if (tid == 0) ncand_s = nfound_s = 0;
+    __shared__ int tie_s;
+    if (tid == 0) ncand_s = nfound_s = tie_s = 0;
     load_magnitudes<T>(spec + win * n, mags, half);
     const Stats st = block_stats<T>(mags, half, red, &stats_s);
 
@@ -85,10 +88,11 @@ __device__ void peaks_prominence_window(const int64_t win, const typename vec2<T
             int pos = atomicAdd(&ncand_s, 1);
             if (pos < lay.cap) cand[pos] = j;
         }
+        if (sizeof(T) == 4 && fp32_tie_top(mags, half, j, m, st.thr)) tie_s = 1;
     }
     __syncthreads();
     const int ncand = min(ncand_s, lay.cap);
-    int status = ncand_s > lay.cap ? 1 : 0;
+    int status = (ncand_s > lay.cap ? APDA_STATUS_TRUNCATED : 0) | (tie_s ? APDA_STATUS_FP32_TIE : 0);
 
     const int warp = tid >> 5, nwarp = blockDim.x >> 5, lane = tid & 31;
     const double half_sd = mul_rn(0.5, st.sd);
@@ -189,10 +193,10 @@ __device__ void peaks_resolution_window(const int64_t win, const typename vec2<T
     __shared__ double best_m[32];
     __shared__ int best_j[32];
     __shared__ int ctl[4];  // chosen idx, zero start, zero end, accepted count
-    __shared__ int acc_idx[APDA_MAX_REC_CAP];
     const Layout lay = make_layout<T>(half);
     unsigned char *base = SMEM ? smem_raw : ws + (size_t)blockIdx.x * lay.bytes;
     T *mags = reinterpret_cast<T *>(base + lay.mags_off);
+    int *acc_idx = reinterpret_cast<int *>(base + lay.acc_off);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
     unsigned char *rec = recs + win * APDA_REC_BYTES(rec_cap);
     const double fs = d_fs ? d_fs[win] : fs_all;
@@ -201,8 +205,14 @@ __device__ void peaks_resolution_window(const int64_t win, const typename vec2<T
 
     load_magnitudes<T>(spec + win * n, mags, half);
     const Stats st = block_stats<T>(mags, half, red, &stats_s);
-    if (tid == 0) ctl[3] = 0;
+    __shared__ int tie_s;
+    if (tid == 0) ctl[3] = tie_s = 0;
     __syncthreads();
+    if (sizeof(T) == 4) {  // on the original magnitudes (the zeroing below makes equal bins of its own)
+        for (int j = 1 + tid; j < half - 1; j += blockDim.x)
+            if (fp32_tie_top(mags, half, j, mags[j], st.thr)) tie_s = 1;
+        __syncthreads();
+    }
 
     while (true) {
         // arg-max over strict local maxima above the threshold; ties resolve to the lowest index (first wins)
@@ -274,7 +284,7 @@ __device__ void peaks_resolution_window(const int64_t win, const typename vec2<T
     }
     if (tid == 0) {
         const int na = ctl[3];
-        write_rec_header(rec, na, 0);
+        write_rec_header(rec, na, tie_s ? APDA_STATUS_FP32_TIE : 0);
         for (int a = na; a < rec_cap; ++a) write_rec_peak(rec, a, -1, 0, 0.0, 0.0);
     }
 }

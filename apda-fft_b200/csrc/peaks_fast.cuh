@@ -384,9 +384,11 @@ __device__ __forceinline__ void k3_tail(T *mags, SlotT<T> *slots, const int slot
     constexpr int C = P::C;
     // ---- phase 2: contiguous chunk per lane: chunk max/min, hot bins -> slot list -------------------------------------
     T cmax = -(T)CUDART_INF_F, cmin = (T)CUDART_INF_F;
+    bool tie_lane = false;
     {
         const T *ch = mags + P::addr(C * lane);
         unsigned hotq = 0;  // bit q: the q-th group of 4 bins of this chunk holds a bin above the threshold (C/4 <= 32 groups)
+        bool &tie = tie_lane;  // fp32 only: a hot two-bin plateau top (see APDA_STATUS_FP32_TIE)
 #pragma unroll
         for (int q = 0; q < C / 4; ++q) {
             const Quad<T> v = lds_quad(ch + 4 * q);
@@ -411,6 +413,12 @@ __device__ __forceinline__ void k3_tail(T *mags, SlotT<T> *slots, const int slot
                         const int pos = atomicAdd(&(*nslot_ptr), 1);
                         if (pos < slot_cap) slots[pos].idx = (uint16_t)j;
                     }
+                    // Two adjacent bins that are EQUAL in fp32 and higher than both outer neighbours: neither is a strict
+                    // local maximum, so no peak is reported there, while the fp64 reference (whose magnitudes differ in
+                    // the bits fp32 drops) reports one of them.  The window is flagged so the caller can re-run it in fp64.
+                    if (sizeof(T) == 4 && j >= 1 && j + 1 <= HALF - 1 && e[u] == mags[P::addr(j + 1)] &&
+                        e[u] > mags[P::addr(j - 1)] && (j + 2 > HALF - 1 || e[u] > mags[P::addr(j + 2)]))
+                        tie = true;
                 }
             }
         }
@@ -422,7 +430,7 @@ __device__ __forceinline__ void k3_tail(T *mags, SlotT<T> *slots, const int slot
         return;
     }
     const int nslot = nslot_raw;
-    const int status = 0;
+    const int status = (sizeof(T) == 4 && __any_sync(0xffffffffu, tie_lane)) ? APDA_STATUS_FP32_TIE : 0;
 
     int na = 0;
     if (FLEX) {

@@ -214,9 +214,8 @@ template <typename T>
 __global__ void __launch_bounds__(1024)
 pick_flexible_kernel(const T *__restrict__ mags, const T *__restrict__ bmax, const T *__restrict__ bmin, int64_t n,
                      int half, double fs_all, const double *__restrict__ fs_ptr, int k, int rec_cap, LargeState *st, const int *__restrict__ cand,
-                     Found *__restrict__ found, int cap, unsigned char *__restrict__ rec) {
+                     Found *__restrict__ found, int cap, int *__restrict__ acc_slot, unsigned char *__restrict__ rec) {
     __shared__ int nfound_s;
-    __shared__ int acc_slot[APDA_MAX_REC_CAP];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ncand = min(st->ncand, cap);
     const double fs = fs_ptr ? *fs_ptr : fs_all;
@@ -336,11 +335,10 @@ pick_flexible_kernel(const T *__restrict__ mags, const T *__restrict__ bmax, con
 template <typename T>
 __global__ void __launch_bounds__(1024)
 pick_rigid_kernel(T *__restrict__ mags, int64_t n, int half, double fs_all, const double *__restrict__ fs_ptr, int k, int rec_cap, LargeState *st,
-                  const int *__restrict__ cand, int cap, unsigned char *__restrict__ rec) {
+                  const int *__restrict__ cand, int cap, int *__restrict__ acc_idx, unsigned char *__restrict__ rec) {
     __shared__ double best_m[32];
     __shared__ int best_j[32];
     __shared__ int ctl[4];
-    __shared__ int acc_idx[APDA_MAX_REC_CAP];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nhot = min(st->ncand, cap);
     const double thr = st->thr;
@@ -423,7 +421,7 @@ pick_rigid_kernel(T *__restrict__ mags, int64_t n, int half, double fs_all, cons
 }
 
 struct LargeLayout {
-    size_t mags, bmax, bmin, part, state, cand, found, bytes;
+    size_t mags, bmax, bmin, part, state, cand, found, acc, bytes;
     int cap, nblk;
 };
 template <typename T>
@@ -444,6 +442,7 @@ LargeLayout large_layout(int64_t half) {
     l.state = take(sizeof(LargeState));
     l.cand = take((size_t)l.cap * sizeof(int));
     l.found = take((size_t)l.cap * sizeof(Found));
+    l.acc = take((size_t)l.cap * sizeof(int));  // accepted peaks (any k up to cap)
     l.bytes = o;
     return l;
 }
@@ -473,6 +472,7 @@ int launch_peaks_large(apda_ctx *ctx, cudaStream_t st, const T *d_spec, int64_t 
     LargeState *state = reinterpret_cast<LargeState *>(base + l.state);
     int *cand = reinterpret_cast<int *>(base + l.cand);
     Found *found = reinterpret_cast<Found *>(base + l.found);
+    int *acc = reinterpret_cast<int *>(base + l.acc);
     for (int64_t w = 0; w < batch; ++w) {
         const V2 *spec = reinterpret_cast<const V2 *>(d_spec) + w * n;
         unsigned char *rec = reinterpret_cast<unsigned char *>(d_rec) + w * APDA_REC_BYTES(rec_cap);
@@ -482,10 +482,10 @@ int launch_peaks_large(apda_ctx *ctx, cudaStream_t st, const T *d_spec, int64_t 
         if (flexible) {
             hot_kernel<T, true><<<l.nblk, 256, 0, st>>>(mags, bmax, (int)half, state, cand, l.cap);
             pick_flexible_kernel<T><<<1, 1024, 0, st>>>(mags, bmax, bmin, n, (int)half, fs, fs_ptr, k, rec_cap, state, cand, found,
-                                                        l.cap, rec);
+                                                        l.cap, acc, rec);
         } else {
             hot_kernel<T, false><<<l.nblk, 256, 0, st>>>(mags, bmax, (int)half, state, cand, l.cap);
-            pick_rigid_kernel<T><<<1, 1024, 0, st>>>(mags, n, (int)half, fs, fs_ptr, k, rec_cap, state, cand, l.cap, rec);
+            pick_rigid_kernel<T><<<1, 1024, 0, st>>>(mags, n, (int)half, fs, fs_ptr, k, rec_cap, state, cand, l.cap, acc, rec);
         }
         ctx->launches += 4;
     }

@@ -99,35 +99,52 @@ class RecordGatherer:
 class PeerRecordTable:
     """The fleet's record table in the destination rank's HBM, mapped into every rank (CUDA IPC over NVLink).
 
-    Rank ``dst`` allocates ``world * per`` records; the others open the allocation and hand
-    ``table + rank * per * rec_bytes`` to the pickers as their record pointer, so the K3 kernels' own 128-byte epilogue
-    stores land in the owner's memory: the gather of SURVEY 8(e) fused into the producing kernel, with no collective,
-    no staging copy and no SM time.  ``torch.distributed`` only carries the 64-byte handle and the barriers.
+    Rank ``dst`` allocates ``buffers`` tables of ``world * per`` records; the others open the allocation and hand
+    ``table(step) + rank * per * rec_bytes`` to the pickers as their record pointer, so the K3 kernels' own 128-byte
+    epilogue stores land in the owner's memory: the gather of SURVEY 8(e) fused into the producing kernel, with no
+    collective, no staging copy and no SM time.  ``torch.distributed`` only carries the 64-byte handle and barriers.
+
+    Steps are numbered 1, 2, ...; step s uses table ``s % buffers``.  Flow control is on the device timelines in both
+    directions: a producer publishes ``s`` after its pickers (``signal``), the owner's stream holds until every rank
+    published ``s`` (``wait``), and once the owner has consumed the table it acknowledges ``s`` (``release``); a
+    producer about to write step ``s`` first holds its stream until step ``s - buffers`` is acknowledged (``begin``),
+    so it can never overwrite rows the owner is still reading.
 
         t = PeerRecordTable(analyzer.ctx, per, 128, device)       # once (collective: every rank calls it)
-        ... an.peaks_device(..., d_rec=t.local_ptr, ...) ...      # every step, any number of launches
-        table = t.complete()                                      # stream sync + barrier; rank dst: uint8 [world*per, rec_bytes]
+        for s in 1, 2, ...:
+            ptr = t.begin(s)                                      # every rank: back-pressure, then this step's rows
+            ... an.peaks_device(..., d_rec=ptr, ...) ...          # any number of launches
+            t.signal(s)
+            if t.owner:
+                table = t.wait(s)                                 # uint8 [world*per, rec_bytes], valid until release(s)
+                ... consume on the same stream ...
+                t.release(s)
         t.close()
     """
 
-    def __init__(self, ctx, per: int, rec_bytes: int, device, dst: int = 0, group=None):
+    def __init__(self, ctx, per: int, rec_bytes: int, device, dst: int = 0, group=None, buffers: int = 2):
         import ctypes
 
         import torch
         import torch.distributed as dist
         self.ctx, self.per, self.rec_bytes, self.dst, self.group = ctx, per, rec_bytes, dst, group
         self.device = device
+        self.buffers = max(1, int(buffers))
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.owner = self.rank == dst
-        self.nbytes = self.world * per * rec_bytes
-        self.flags_off = (self.nbytes + 255) & ~255          # one uint32 step counter per rank, then a time-out word
+        self.nbytes = self.world * per * rec_bytes                      # one table
+        self.stride = (self.nbytes + 255) & ~255
+        # control words behind the tables: [0, 4*world) step counters, +128 owner's time-out word, +132 acknowledged step,
+        # +256 + 4*rank the producers' own time-out words
+        self.flags_off = self.stride * self.buffers
+        self.ctl_bytes = 512
         base = ctypes.c_void_p()
         handle = (ctypes.c_ubyte * 64)()
         err = None
         if self.owner:
             try:
-                ctx.call("apda_peer_table_create", ctypes.c_int64(self.flags_off + 256), ctypes.byref(base), handle)
+                ctx.call("apda_peer_table_create", ctypes.c_int64(self.flags_off + self.ctl_bytes), ctypes.byref(base), handle)
             except Exception as exc:  # noqa: BLE001 - reported after the collective steps below, never before
                 err = exc
         if self.world > 1:
@@ -151,18 +168,21 @@ class PeerRecordTable:
         elif err:
             raise err
         self.base = int(base.value)
-        self.local_ptr = self.base + self.rank * per * rec_bytes
+        self.local_ptr = self.base + self.rank * per * rec_bytes        # rows of this rank in table 0
         self._closed = False
         if self.owner:  # counters start at 0
-            view = self._raw(self.flags_off, 256)
+            view = self._raw(self.flags_off, self.ctl_bytes)
             view.zero_()
             torch.cuda.synchronize(device)
         if self.world > 1:
             dist.barrier(group=group)
 
-    def row_ptr(self, row: int) -> int:
-        """Device pointer of local row ``row`` (for sub-batch launches)."""
-        return self.local_ptr + row * self.rec_bytes
+    def table_ptr(self, step: int) -> int:
+        return self.base + (int(step) % self.buffers) * self.stride
+
+    def row_ptr(self, row: int, step: int = 0) -> int:
+        """Device pointer of local row ``row`` in the table of ``step`` (for sub-batch launches)."""
+        return self.table_ptr(step) + (self.rank * self.per + row) * self.rec_bytes
 
     def _raw(self, offset: int, nbytes: int):
         import torch
@@ -174,8 +194,18 @@ class PeerRecordTable:
                                       "version": 3, "strides": None}
         return torch.as_tensor(m, device=self.device)
 
-    def _tensor(self):
-        return self._raw(0, self.nbytes).view(self.world * self.per, self.rec_bytes)
+    def _tensor(self, step: int = 0):
+        return self._raw((int(step) % self.buffers) * self.stride, self.nbytes).view(self.world * self.per, self.rec_bytes)
+
+    def begin(self, step: int, timeout_s: float = 5.0) -> int:
+        """Every rank, before the first launch that writes step ``step``: hold this rank's stream until the owner has
+        acknowledged step ``step - buffers`` (whose table is about to be overwritten); returns this rank's row pointer."""
+        import ctypes
+        if step > self.buffers:
+            self.ctx.call("apda_peer_wait", ctypes.c_void_p(self.base + self.flags_off + 132), 1,
+                          (int(step) - self.buffers) & 0xffffffff, float(timeout_s),
+                          ctypes.c_void_p(self.base + self.flags_off + 256 + 4 * self.rank))
+        return self.row_ptr(0, step)
 
     def signal(self, step: int):
         """Enqueue (after this rank's pickers, same stream): publish `step` - my rows of this step are in the table."""
@@ -183,25 +213,34 @@ class PeerRecordTable:
         self.ctx.call("apda_peer_signal", ctypes.c_void_p(self.base + self.flags_off + 4 * self.rank), int(step) & 0xffffffff)
 
     def wait(self, step: int, timeout_s: float = 5.0):
-        """Owner only: hold the stream until every rank has published `step`; returns the table view."""
+        """Owner only: hold the stream until every rank has published `step`; returns that step's table view, valid
+        until ``release(step)``."""
         import ctypes
         assert self.owner
         self.ctx.call("apda_peer_wait", ctypes.c_void_p(self.base + self.flags_off), self.world, int(step) & 0xffffffff,
                       float(timeout_s), ctypes.c_void_p(self.base + self.flags_off + 128))
-        return self._tensor()
+        return self._tensor(step)
+
+    def release(self, step: int):
+        """Owner only, enqueued after the consumer of ``wait(step)``'s table on the same stream: the table of ``step`` may
+        be overwritten (by step ``step + buffers``)."""
+        import ctypes
+        assert self.owner
+        self.ctx.call("apda_peer_signal", ctypes.c_void_p(self.base + self.flags_off + 132), int(step) & 0xffffffff)
 
     def timed_out(self) -> bool:
-        """Owner only (synchronises): did any wait give up?"""
-        return bool(self._raw(self.flags_off + 128, 4).view(-1).cpu().numpy().view("int32")[0])
+        """Owner only (synchronises): did the LAST wait of the owner, or the last back-pressure wait of any producer, give up?"""
+        words = self._raw(self.flags_off, self.ctl_bytes).cpu().numpy().view("int32")
+        return bool(words[32] != 0 or (words[64:64 + self.world] != 0).any())
 
-    def complete(self):
+    def complete(self, step: int = 0):
         """Every rank: wait for the local stream's kernels, then a process barrier; the owner gets the table view."""
         import torch
         import torch.distributed as dist
         torch.cuda.synchronize(self.device)
         if self.world > 1:
             dist.barrier(group=self.group)
-        return self._tensor() if self.owner else None
+        return self._tensor(step) if self.owner else None
 
     def close(self):
         import ctypes

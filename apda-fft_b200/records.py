@@ -71,16 +71,19 @@ def upload_metrics(summary: dict, axis: str, fft_entry: dict) -> dict:
     RMS-vector angles from the summary line, the axis' own RMS and the top-4 peak arrays of ``gateway_entry``
     (missing peaks are 0.0, as ``current_fft.get(..., 0.0)`` does there).  Pure host arithmetic, same operation order."""
     from math import acos, atan2, degrees
-    m1, m2, m3 = summary["rms_x"], summary["rms_y"], summary["rms_z"]
-    accrms = (m1 ** 2 + m2 ** 2 + m3 ** 2) ** 0.5
+    rms = {"X": summary["rms_x"], "Y": summary["rms_y"], "Z": summary["rms_z"]}
+    norm = (rms["X"] ** 2 + rms["Y"] ** 2 + rms["Z"] ** 2) ** 0.5          # length of the RMS vector
+    azimuth = degrees(atan2(rms["Y"], rms["X"]))
+    inclination = degrees(acos(rms["Z"] / norm)) if norm != 0 else 0
+    top4 = range(1, 5)
     return {
         "temp": summary["temperature"],
         "humidity": summary.get("humidity", 0.0),
-        "phi": degrees(atan2(m2, m1)),
-        "theta": degrees(acos(m3 / accrms)) if accrms != 0 else 0,
-        "rms_asse": {"X": m1, "Y": m2, "Z": m3}.get(axis, 0.0),
-        "fft_freqs": [fft_entry.get(f"peak_freq_{i}", 0.0) for i in range(1, 5)],
-        "fft_mags": [fft_entry.get(f"max_mag_{i}", 0.0) for i in range(1, 5)],
+        "phi": azimuth,
+        "theta": inclination,
+        "rms_asse": rms.get(axis, 0.0),
+        "fft_freqs": [fft_entry.get(f"peak_freq_{i}", 0.0) for i in top4],
+        "fft_mags": [fft_entry.get(f"max_mag_{i}", 0.0) for i in top4],
     }
 
 

@@ -43,10 +43,12 @@ def get_top_peaks_prominence(res_fft, fs, k=4):
     n = len(res_fft)
     z = pack_spectrum(res_fft)
     want = max(int(k), 1)   # the reference tests len(final_peaks) >= k only after appending
-    if want > _cabi.MAX_REC_CAP:
-        raise ValueError(f"k={k} exceeds the record capacity {_cabi.MAX_REC_CAP}")
+    # any k, as in the reference: a window of n bins cannot hold more than n/8 + 8 peaks (include/apda_b200.h
+    # APDA_MAX_PEAKS), so a larger k asks for "all of them" and the record is sized for that
+    want = min(want, _cabi.max_peaks(n))
     cap = max(5, want)
     rec = np.zeros(1, dtype=record_dtype(cap))
     _cabi.default_context().call("apda_peaks_prominence_f64_host", _p(z.ctypes.data), n, 1, float(fs), _p(0), want, cap,
                                  _p(rec.ctypes.data))
+    _cabi.check_record_status(rec)
     return prominence_dicts(rec[0], fs, n)

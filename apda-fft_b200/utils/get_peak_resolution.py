@@ -40,10 +40,10 @@ def get_top_peaks_resolution(fft_res, fs, k=5):
         # the reference never enters its loop; it still evaluates the statistics first
         _cabi.check(_cabi.ERR_STATS_MEAN if n // 2 < 1 else _cabi.ERR_STATS_STDEV if n // 2 < 2 else _cabi.OK)
         return []
-    if k > _cabi.MAX_REC_CAP:
-        raise ValueError(f"k={k} exceeds the record capacity {_cabi.MAX_REC_CAP}")
-    cap = max(5, int(k))
+    want = min(int(k), _cabi.max_peaks(n))   # any k, as in the reference (see get_peak_prominence.py)
+    cap = max(5, want)
     rec = np.zeros(1, dtype=record_dtype(cap))
-    _cabi.default_context().call("apda_peaks_resolution_f64_host", _p(z.ctypes.data), n, 1, float(fs), _p(0), int(k), cap,
+    _cabi.default_context().call("apda_peaks_resolution_f64_host", _p(z.ctypes.data), n, 1, float(fs), _p(0), want, cap,
                                  _p(rec.ctypes.data))
+    _cabi.check_record_status(rec)
     return resolution_dicts(rec[0], fs, n)

@@ -51,12 +51,23 @@ typedef struct apda_peak {
  * same header.  Peaks are in the reference's output order (flexible: descending rounded magnitude; rigid: discovery). */
 typedef struct apda_peak_rec {
     int32_t count;  /* peaks found (<= k) */
-    int32_t status; /* 0 ok; bit0: internal candidate list overflowed (result truncated) */
+    int32_t status; /* 0 ok, else a set of APDA_STATUS_* bits: the record is not (known to be) reference-equivalent */
     apda_peak pk[5];
 } apda_peak_rec;
 
+#define APDA_STATUS_TRUNCATED 1     /* internal candidate list overflowed (result truncated; unreachable by Cantelli's bound) */
+#define APDA_STATUS_OTHER_LENGTH 4  /* ragged batch: the window's own padded length differs from N */
+#define APDA_STATUS_EMPTY 8         /* ragged batch: empty window (the reference's pickers raise StatisticsError) */
+#define APDA_STATUS_FP32_TIE 16     /* fp32 pickers (N <= 2^15): two adjacent bins above the threshold are equal in fp32 and form
+                                     * the top of a peak; the strict local-maximum test reports no peak there, the fp64
+                                     * reference (whose magnitudes differ below fp32 resolution) reports one: re-run the
+                                     * window through the fp64 entry points (apda-fft_b200/batch.py does) */
 #define APDA_REC_BYTES(rec_cap) (8 + 24 * (int64_t)(rec_cap))
 #define APDA_MAX_REC_CAP 64
+/* Most peaks one window of n bins can report (candidates are strict local maxima above mean + 2 sigma of the half
+ * spectrum: fewer than 20 % of its bins): the reference accepts any k (utils/get_peak_prominence.py:149,223,
+ * utils/get_peak_resolution.py:80,94), so records may be as wide as max(APDA_MAX_REC_CAP, APDA_MAX_PEAKS(n)). */
+#define APDA_MAX_PEAKS(n) ((int64_t)(n) / 8 + 8)
 
 typedef struct apda_ctx apda_ctx;
 
@@ -95,7 +106,8 @@ int apda_center_f64_host(apda_ctx *ctx, const double *h_in, int64_t n, double *h
 
 /* ---- K3: peak pickers --------------------------------------------------------------------------------------
  * n = bins per window in the spectrum (the pickers read bins [0, n/2)); fs: one value for all windows when
- * d_fs/h_fs is NULL.  k <= rec_cap <= APDA_MAX_REC_CAP; out: batch records of APDA_REC_BYTES(rec_cap).
+ * d_fs/h_fs is NULL.  k <= rec_cap <= max(APDA_MAX_REC_CAP, APDA_MAX_PEAKS(n)); out: batch records of
+ * APDA_REC_BYTES(rec_cap).
  * prominence: replaces utils/get_peak_prominence.py:149-226 get_top_peaks_prominence(res_fft, fs, k=4)
  * resolution: replaces utils/get_peak_resolution.py:80-128 get_top_peaks_resolution(fft_res, fs, k=5) */
 int apda_peaks_prominence_f64_dev(apda_ctx *ctx, const double *d_spec, int64_t n, int64_t batch, double fs,
@@ -223,7 +235,10 @@ int apda_peer_table_destroy(apda_ctx *ctx, void *d_table);  /* owner side */
 /* Completion on the device timelines: every rank owns one uint32 step counter in the owner's memory (the caller
  * reserves them, e.g. behind the rows).  apda_peer_signal (producer, after its pickers, same stream) publishes
  * `value` with release semantics at system scope; apda_peer_wait (owner) holds the stream until all `world` counters
- * have reached `value` (acquire), or sets *d_timed_out = 1 after timeout_s seconds instead of hanging. */
+ * have reached `value` (acquire); *d_timed_out is 0 afterwards, or 1 if the wait gave up after timeout_s seconds instead
+ * of hanging.  The same pair serves the back-pressure direction: the owner signals an "acknowledged step" counter once it
+ * has consumed a step's table, and a producer waits on it (world = 1) before it overwrites rows the owner may still be
+ * reading (apda-fft_b200/fleet.py: PeerRecordTable double-buffers the table by step parity). */
 int apda_peer_signal(apda_ctx *ctx, void *d_flag, uint32_t value);
 int apda_peer_wait(apda_ctx *ctx, const void *d_flags, int world, uint32_t value, double timeout_s, int *d_timed_out);
 

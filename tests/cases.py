@@ -234,3 +234,16 @@ def approx_rel(a: float, b: float) -> float:
 
 def isclose_rel(a, b, tol):
     return approx_rel(float(a), float(b)) <= tol or (math.isnan(a) and math.isnan(b))
+
+
+def write_sensor_log(path, samples, fs: float, axis: str, per_line: int = 60, missing_marker_at: int | None = None) -> None:
+    """A sensor .log as the gateway writes it (GT_FFT_v5.py:380-395 header lines, protocol_decoder.py:174 "%8.6f"
+    samples, ';'-separated): what utils/load_data.py:29-82 parses."""
+    rows = [f"2_11_22_18_20_32;2 g;{fs} Hz;{axis} axis;", "Synced;", "25.010;-0.0222;0.0110;0.9981;85.0;",
+            "0.268262;0.0;1.0;"]
+    vals = ["%8.6f" % v for v in samples]
+    rows += [";".join(vals[i:i + per_line]) + ";" for i in range(0, len(vals), per_line)]
+    if missing_marker_at is not None:
+        rows.insert(missing_marker_at, "* MISSING PACKETS 3-4 *")
+    with open(path, "w") as fh:
+        fh.write("\n".join(rows) + "\n")

@@ -126,31 +126,48 @@ def test_cfg4_large_transform_f64_bit_exact(log2n, env):
 
 def test_cfg5_1m_windows_n4096_f32_fleet(env):
     """The headline workload: 1M x 4096 fp32, flexible picker.  Ground truth of the generator on every window,
-    exact x4 scaling and determinism on the full batch, oracle (fp64) index lists on a sample of the resident buffers."""
+    exact x4 scaling and determinism on the full batch, oracle (fp64) index lists on the SURVEY 8(c) sample of the
+    resident buffers: the first and last 256 windows of the shard plus 512 random ones (1 024 windows).  The only
+    windows the fp32 path answers differently from the fp64 reference are fp32 ties at a peak top (about one in 10^6):
+    they must carry APDA_STATUS_FP32_TIE, and re-running them in fp64 must give the oracle's answer."""
     an, dev, torch = env
+    from apda_fft_b200 import _cabi
     b, n = 1_000_000, 4096
     d_x = torch.empty((b, n), dtype=torch.float32, device=dev)
     an.synth_device(0, b, n, "f32", d_x.data_ptr())
     recs, d_spec = _records(an, torch, dev, d_x, n, "f32", True)
-    assert (recs["status"] == 0).all()
-    assert (recs["count"] == 3).mean() >= 0.99999       # a tone exactly between two bins ties in fp32 (DESIGN.md 5)
+    assert ((recs["status"] == 0) | (recs["status"] == _cabi.STATUS_FP32_TIE)).all()
+    tied = np.flatnonzero(recs["status"] == _cabi.STATUS_FP32_TIE)
+    assert tied.size <= 20
     ok = recs["count"] == 3
+    assert set(np.flatnonzero(~ok)) <= set(tied), (np.flatnonzero(~ok)[:10], tied[:10])   # every miss is a flagged tie
     first = 200_000
     tones = _tone_bins(0, first, n)
     idx = np.sort(recs["pk"]["idx"][:first, :3], axis=1)
     assert (np.abs(idx - tones)[ok[:first]] <= 1.0).all()
     mags = recs["pk"]["mag"][ok][:, :3]
     assert (mags[:, 0] >= mags[:, 1]).all() and (mags[:, 1] >= mags[:, 2]).all()       # descending magnitude
-    pick = list(range(0, 16)) + list(range(b - 16, b)) + list(range(31_337, b, 99_991))
+    rng = np.random.default_rng(2024)
+    pick = sorted(set(range(0, 256)) | set(range(b - 256, b)) | set(rng.choice(b, 512, replace=False).tolist())
+                  | set(tied.tolist()))
+    assert len(pick) >= 1000
     xs = d_x[pick].cpu().numpy().astype(np.float64)
     want = c_oracle.start_fft_batch(xs)
+    refs = {}
     for i, w in enumerate(pick):
-        ref = ref_port.top_peaks_prominence(want[i].tolist(), 125.0)
+        ref = refs[w] = ref_port.top_peaks_prominence(want[i].tolist(), 125.0)
+        if recs[w]["status"] == _cabi.STATUS_FP32_TIE:
+            continue
         got = _dicts(recs[w], n, True)
         assert [p["idx"] for p in got] == [p["idx"] for p in ref], w
         for g, r in zip(got, ref):
             assert abs(g["prominence"] - r["prominence"]) <= 1e-5 * r["prominence"]
             assert abs(g["mag"] - r["mag"]) <= 1e-4 + 1e-5 * r["mag"]
+    if tied.size:       # the flagged windows, re-run through the fp64 kernels on the same samples: exactly the oracle
+        d_t = d_x[torch.as_tensor(tied, device=dev)].double().contiguous()
+        r64, _ = _records(an, torch, dev, d_t, n, "f64", True)
+        for i, w in enumerate(tied):
+            assert _dicts(r64[i], n, True) == refs[int(w)], w
     d_x *= 4.0
     recs4, _ = _records(an, torch, dev, d_x, n, "f32", True, d_spec)
     assert np.array_equal(recs4["pk"]["idx"], recs["pk"]["idx"]) and np.array_equal(recs4["count"], recs["count"])

@@ -618,6 +618,10 @@ def test_text_ingest_matches_load_sensor(golden, tmp_path, an):
 
 
 def _peer_worker(rank, world, port, tmp):
+    """Six steps with DIFFERENT windows per step; the owner lags (it sleeps on its stream before consuming), so the
+    producers run ahead as far as the flow control lets them.  Every step's table, snapshotted by the owner between
+    wait() and release(), must equal the NCCL gather of that step's records - with a single table and no
+    acknowledgement a fast producer would have overwritten rows the owner had not read yet."""
     import torch
     import torch.distributed as dist
     import apda_fft_b200
@@ -627,24 +631,35 @@ def _peer_worker(rank, world, port, tmp):
     dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=dev)
     an = apda_fft_b200.Analyzer(rank)
     an.use_stream(torch.cuda.current_stream(dev).cuda_stream)
-    per, n = 3000, 4096
-    x = torch.empty((per, n), dtype=torch.float32, device=dev)
+    per, n, steps = 3000, 4096, 6
+    x = torch.empty((steps + 1, per, n), dtype=torch.float32, device=dev)
     spec = torch.empty((per, n, 2), dtype=torch.float32, device=dev)
     rec = torch.zeros((per, 128), dtype=torch.uint8, device=dev)
-    an.synth_device(rank * per, per, n, "f32", x.data_ptr())
+    for s in range(1, steps + 1):
+        an.synth_device((s * world + rank) * per, per, n, "f32", x[s].data_ptr())
     table = PeerRecordTable(an.ctx, per, 128, dev)
-    for step in (1, 2):
-        an.fft_device(x.data_ptr(), per, n, n, "f32", spec.data_ptr())
-        an.peaks_device(spec.data_ptr(), per, n, "f32", 125.0, table.local_ptr)
+    snaps = {}
+    for step in range(1, steps + 1):
+        ptr = table.begin(step)
+        an.fft_device(x[step].data_ptr(), per, n, n, "f32", spec.data_ptr())
+        an.peaks_device(spec.data_ptr(), per, n, "f32", 125.0, ptr)
         table.signal(step)
         if table.owner:
-            table.wait(step)
-    got = table.complete()
-    an.peaks_device(spec.data_ptr(), per, n, "f32", 125.0, rec.data_ptr())
-    want = gather_records(rec, per * world, dst=0)
+            torch.cuda._sleep(20_000_000)          # ~10 ms: the consumer is slower than the producers
+            snaps[step] = table.wait(step).clone()
+            table.release(step)
+    table.complete()
+    ok = True
+    for step in range(1, steps + 1):
+        an.fft_device(x[step].data_ptr(), per, n, n, "f32", spec.data_ptr())
+        an.peaks_device(spec.data_ptr(), per, n, "f32", 125.0, rec.data_ptr())
+        want = gather_records(rec, per * world, dst=0)
+        if rank == 0:
+            ok = ok and bool(torch.equal(snaps[step], want))
     if rank == 0:
         assert not table.timed_out()
-        assert torch.equal(got, want)
+        assert ok
+        assert not torch.equal(snaps[1], snaps[2])      # the steps really carried different data
         open(os.path.join(tmp, "ok"), "w").write("1")
     dist.barrier()
     table.close()
@@ -653,7 +668,9 @@ def _peer_worker(rank, world, port, tmp):
 
 def test_peer_record_table_equals_nccl_gather(tmp_path):
     """N>1 on GPUs: K3 storing its records into rank 0's table over NVLink peer memory (CUDA IPC + device-side step
-    counters) gives the table an NCCL gather gives, byte for byte.  Needs two GPUs (skipped on a single-GPU box)."""
+    counters, double-buffered with an owner->producer acknowledgement) gives the table an NCCL gather gives, byte for
+    byte, on every one of several steps with different data.  Needs two GPUs (skipped on a single-GPU box; bench.py
+    repeats the equality check as a hard failure on every multi-GPU run)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")

@@ -1,0 +1,351 @@
+"""T2, second round: the parity holes the round-1 review listed (needs a B200: -m gpu).
+
+  * the UNMODIFIED reference call site Gateway.work_flow_fft on the drop-in modules,
+  * multi-chunk host pipelines with pinned buffers where both pipeline streams use the device-side window lists
+    (repair list of the fast pickers, ragged list of the ingest paths) at the same time,
+  * record status bits on every ragged path, any k through the drop-ins, the fp32 tie flag,
+  * fp32 K2 (N = 2^20 .. 2^24) against the C oracle,
+  * result packing from a record table produced on the GPU.
+"""
+import ctypes
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import cases
+from oracle import c_oracle, ref_copy, ref_port
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_p = ctypes.c_void_p
+
+
+@pytest.fixture(scope="module")
+def an():
+    import apda_fft_b200
+    return apda_fft_b200.Analyzer(0)
+
+
+def _dicts(rec, fs, n, flexible):
+    from apda_fft_b200.records import prominence_dicts, resolution_dicts
+    return prominence_dicts(rec, fs, n) if flexible else resolution_dicts(rec, fs, n)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a12: the reference's own caller, unmodified, on the drop-ins
+# ---------------------------------------------------------------------------------------------------------------
+TIMING_KEYS = ("process_time", "wall_time", "percentage_cpu", "memrss")
+
+
+def _replay(mode, flexible, mac, paths):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "gateway_replay.py"), mode, str(int(flexible)), mac, *paths],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "[ERROR]" not in out.stdout, out.stdout[-2000:]          # work_flow_fft's broad except only prints
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+@pytest.mark.parametrize("flexible", [True, False])
+def test_gateway_work_flow_fft_unmodified_call_site(flexible, tmp_path, golden):
+    """GT_FFT_v5.py:620-680 from the build-time copy of the reference (oracle/_ref), digidevice stubbed, run once on
+    the reference's own hot-path modules and once with apda-fft_b200/ ahead on sys.path: the fft_dict
+    entries must be the same Python objects (every key but the caller's own timing fields), for both values of
+    is_flexibile_structure, on KAT-A/B/C logs (one file per axis, one of them with a MISSING PACKETS marker)."""
+    if not ref_copy.available(call_site=True):
+        pytest.skip("oracle/_ref is not populated (built only where /root/reference exists)")
+    mac = "0013a20041e7f6b7"
+    paths = []
+    for axis, cid, marker in (("X", "katA", 9), ("Y", "katB", None), ("Z", "katC", 30)):
+        x, fs = cases.build_samples(golden["cases"][cid]["spec"])
+        path = tmp_path / f"{mac}_{axis}axis.log"
+        cases.write_sensor_log(path, x, fs, axis, missing_marker_at=marker)
+        paths.append(str(path))
+    ref = _replay("ref", flexible, mac, paths)
+    new = _replay("dropin", flexible, mac, paths)
+    assert ref["gateway"] == new["gateway"] == "oracle/_ref/GT_FFT_v5.py"
+    assert ref["bound"] == "oracle/_ref/metrics/fft_iterativa.py"
+    assert new["bound"] == "apda-fft_b200/metrics/fft_iterativa.py"
+    assert set(new["fft_dict"][mac]) == {"X", "Y", "Z"}
+    for axis in "XYZ":
+        a, b = ref["fft_dict"][mac][axis], new["fft_dict"][mac][axis]
+        assert set(a) == set(b)
+        for key in a:
+            if key not in TIMING_KEYS:
+                assert a[key] == b[key], (axis, key, a[key], b[key])
+        assert b["peak_freq"] != -1 and "peak_freq_3" in b
+    want = golden["cases"]["katA"]["prominence" if flexible else "resolution"]["ok"]
+    assert new["fft_dict"][mac]["X"]["peak_freq_1"] == want[0]["freq"]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# device-side window lists are per stream
+# ---------------------------------------------------------------------------------------------------------------
+def test_multichunk_pinned_noise_spectra_repair_list_per_stream(an):
+    """More than three chunks of N = 8192 noise spectra in PINNED memory (so the two pipeline streams really overlap):
+    every window has ~150 bins above mean + 2 sigma, more than the fast picker's 96 on-chip slots, so every window goes
+    through the device-side repair list and the general kernel.  With one list per context, the next chunk's
+    memset / appends on the other stream raced with this chunk's; now every record must equal, byte for byte, what the
+    general kernel alone produces (apda_ctx_set_generic_only), and the oracle on a sample."""
+    import torch
+    from apda_fft_b200.records import record_dtype
+    n, b = 8192, 3 * 1536 + 200
+    rng = np.random.default_rng(77)
+    z = torch.empty((b, n, 2), dtype=torch.float32).pin_memory()
+    zn = z.numpy()
+    zn[:] = rng.standard_normal((b, n, 2), dtype=np.float32)
+    zn[:, 0, :] = 0
+    for flexible in (True, False):
+        name = "apda_peaks_prominence_f32_host" if flexible else "apda_peaks_resolution_f32_host"
+        k = 4 if flexible else 5
+        fast = torch.zeros((b, 128), dtype=torch.uint8).pin_memory()
+        slow = torch.zeros((b, 128), dtype=torch.uint8).pin_memory()
+        an.ctx.call(name, _p(z.data_ptr()), n, b, 125.0, _p(0), k, 5, _p(fast.data_ptr()))
+        an.ctx.set_generic_only(True)
+        try:
+            an.ctx.call(name, _p(z.data_ptr()), n, b, 125.0, _p(0), k, 5, _p(slow.data_ptr()))
+        finally:
+            an.ctx.set_generic_only(False)
+        f, s = fast.numpy().view(record_dtype(5)).reshape(-1), slow.numpy().view(record_dtype(5)).reshape(-1)
+        bad = np.flatnonzero((fast.numpy() != slow.numpy()).any(axis=1))
+        assert bad.size == 0, (flexible, bad[:10], f[bad[:3]], s[bad[:3]])
+        assert (f["status"] & 1 == 0).all()
+        for w in (0, 1535, 1536, 1537, 3071, 3072, b - 1):
+            zl = (zn[w, :, 0].astype(np.float64) + 1j * zn[w, :, 1].astype(np.float64)).tolist()
+            want = ref_port.top_peaks_prominence(zl, 125.0) if flexible else ref_port.top_peaks_resolution(zl, 125.0)
+            got = _dicts(f[w], 125.0, n, flexible)
+            assert [p["idx"] for p in got] == [p["idx"] for p in want], (flexible, w)
+
+
+def _wire_rows(rng, b, n, ragged_every):
+    """uint8[b, 2n] wire payloads of finite random words; every `ragged_every`-th window loses samples to inf/nan words."""
+    words = rng.integers(0, 1 << 16, size=(b, n), dtype=np.uint16) & np.uint16(0xBFFF)
+    lost = np.zeros(b, dtype=np.int64)
+    for w in range(0, b, ragged_every):
+        kind = (w // ragged_every) % 4
+        cnt = {0: 7, 1: n // 2 + 5, 2: n, 3: 1}[kind]          # a few, more than half (other padded length), all, one
+        pos = rng.choice(n, size=cnt, replace=False)
+        words[w, pos] = np.where(rng.random(cnt) < 0.5, 0x7C00, 0x7E01).astype(np.uint16)
+        lost[w] = cnt
+    pay = np.empty((b, 2 * n), dtype=np.uint8)
+    pay[:, 0::2] = (words >> 8).astype(np.uint8)
+    pay[:, 1::2] = (words & 0xFF).astype(np.uint8)
+    return pay, lost
+
+
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+def test_multichunk_wire16_ragged_list_per_stream(dtype, an):
+    """apda_analyze_wire16_*_host over several chunks (pinned payload) with ragged windows in every chunk: the records
+    must equal those of the same call made slice by slice (each slice a single chunk on one stream), and the status
+    bits must follow the per-window sample counts."""
+    import torch
+    from apda_fft_b200.records import record_dtype
+    n = 4096
+    chunk = (96 << 20) // (n * 2 * (4 if dtype == "f32" else 8))
+    b = 2 * chunk + chunk // 2 + 37
+    rng = np.random.default_rng(5)
+    pay_np, lost = _wire_rows(rng, b, n, ragged_every=11)
+    pay = torch.from_numpy(pay_np).pin_memory()
+    fv = torch.from_numpy(rng.uniform(-1, 1, b)).pin_memory()
+    whole = torch.zeros((b, 128), dtype=torch.uint8).pin_memory()
+    parts = torch.zeros((b, 128), dtype=torch.uint8).pin_memory()
+
+    def run(lo, hi, out):
+        an.ctx.call(f"apda_analyze_wire16_{dtype}_host", _p(pay.data_ptr() + lo * 2 * n), n, 2 * n, hi - lo,
+                    _p(fv.data_ptr() + 8 * lo), n, 0, 1, 125.0, _p(0), 4, 5, _p(out.data_ptr() + 128 * lo))
+
+    run(0, b, whole)
+    step = chunk // 3
+    for lo in range(0, b, step):
+        run(lo, min(b, lo + step), parts)
+    bad = np.flatnonzero((whole.numpy() != parts.numpy()).any(axis=1))
+    assert bad.size == 0, bad[:10]
+    recs = whole.numpy().view(record_dtype(5)).reshape(-1)
+    nv = n - lost
+    assert ((recs["status"] & 8 != 0) == (nv == 0)).all()
+    other = np.array([v > 0 and c_oracle.padded_len(int(v)) != n for v in nv])
+    assert ((recs["status"] & 4 != 0) == other).all()
+    assert (recs["status"][lost == 0] & ~16 == 0).all()
+
+
+def test_ragged_status_bits_on_general_kernel_sizes(an):
+    """Status bits 2 / 3 are written on every ragged path, not only where a specialised FFT kernel ran: N = 512 and
+    N = 16384 have none, and generic_only bypasses them at N = 4096."""
+    import torch
+    from apda_fft_b200.records import record_dtype
+    dev = torch.device("cuda:0")
+    an.use_stream(torch.cuda.current_stream(dev).cuda_stream)
+    try:
+        for n, generic in ((512, False), (16384, False), (4096, True)):
+            counts = [n, n // 2 - 3, 0, n - 1, n // 2 + 1, 1]
+            x = torch.randn((len(counts), n), dtype=torch.float64, device=dev)
+            d_nv = torch.tensor(counts, dtype=torch.int32, device=dev)
+            d_rec = torch.zeros((len(counts), 128), dtype=torch.uint8, device=dev)
+            an.ctx.set_generic_only(generic)
+            try:
+                an.ctx.call("apda_analyze_ragged_f64_dev", _p(x.data_ptr()), _p(d_nv.data_ptr()), n, n, len(counts), n, 0, 1,
+                            125.0, _p(0), 4, 5, _p(0), _p(d_rec.data_ptr()))
+                torch.cuda.synchronize()
+            finally:
+                an.ctx.set_generic_only(False)
+            recs = d_rec.cpu().numpy().view(record_dtype(5)).reshape(-1)
+            assert [int(s) & 12 for s in recs["status"]] == [0, 4, 8, 0, 0, 4], (n, recs["status"])
+            assert recs["count"][2] == 0
+    finally:
+        an.use_stream(None)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# any k (reference: get_peak_prominence.py:149,223; get_peak_resolution.py:80,94)
+# ---------------------------------------------------------------------------------------------------------------
+def test_dropins_accept_any_k():
+    sys.path.insert(0, os.path.join(ROOT, "apda-fft_b200"))
+    from utils.get_peak_prominence import get_top_peaks_prominence
+    from utils.get_peak_resolution import get_top_peaks_resolution
+    rng = np.random.default_rng(11)
+    for n in (256, 4096, 1 << 17):
+        z = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).tolist()
+        z[0] = 0
+        for k in (65, 100, 5000, 10 ** 6):
+            if n > 4096 and k > 100:
+                continue
+            got = get_top_peaks_prominence(z, 125.0, k)
+            want = ref_port.top_peaks_prominence(z, 125.0, k)
+            assert got == want, (n, k, len(got), len(want))
+            got = get_top_peaks_resolution(z, 125.0, k)
+            want = ref_port.top_peaks_resolution(z, 125.0, k)
+            assert got == want, (n, k, len(got), len(want))
+        assert len(get_top_peaks_resolution(z, 125.0, 100)) > 5      # the wide records were really needed
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fp32 ties (two equal magnitudes at a peak top)
+# ---------------------------------------------------------------------------------------------------------------
+def test_fp32_tie_is_flagged_and_resolved_in_fp64(an):
+    """A tone exactly half-way between two bins gives two magnitudes that differ only below fp32 resolution.  The fp32
+    pickers (strict local maxima, like the reference) then see a plateau and report no peak there; the record carries
+    APDA_STATUS_FP32_TIE and Analyzer.analyze re-runs such windows in fp64, which reports what the reference reports."""
+    from apda_fft_b200 import _cabi
+    n = 4096
+    z = np.zeros((3, n), dtype=np.complex64)
+    rng = np.random.default_rng(3)
+    z[:, 1: n // 2] = (0.01 * (rng.standard_normal((3, n // 2 - 1)) + 1j * rng.standard_normal((3, n // 2 - 1)))).astype(np.complex64)
+    for w in range(3):
+        z[w, 300] = 40.0
+        z[w, 900] = 25.0
+    z[1, 500] = z[1, 501] = 30.0 + 0j          # exact tie, higher than the neighbours
+    z[2, 500], z[2, 501] = 30.0, 29.0
+    for flexible in (True, False):
+        recs = an.peaks(z, 125.0, flexible=flexible)
+        assert [int(s) for s in recs["status"]] == [0, _cabi.STATUS_FP32_TIE, 0], recs["status"]
+        assert 500 not in list(recs[1]["pk"]["idx"]) and 501 not in list(recs[1]["pk"]["idx"])
+        assert 500 in list(recs[2]["pk"]["idx"])
+        an.ctx.set_generic_only(True)
+        try:
+            slow = an.peaks(z, 125.0, flexible=flexible)
+        finally:
+            an.ctx.set_generic_only(False)
+        assert [int(s) for s in slow["status"]] == [0, _cabi.STATUS_FP32_TIE, 0]
+    # through the sample path: a window whose fp32 spectrum ties is re-run in fp64 by Analyzer.analyze
+    i = np.arange(n)
+    x = (0.5 * np.sin(2 * np.pi * 200.5 * i / n) + 0.2 * np.sin(2 * np.pi * 611.0 * i / n + 1.0)).astype(np.float32)[None, :]
+    raw = an.analyze(x, 125.0, flexible=True, resolve_ties=False)[0]
+    fixed = an.analyze(x, 125.0, flexible=True)[0]
+    want = c_oracle.peaks_prominence(c_oracle.start_fft_batch(x.astype(np.float64))[0], 125.0)
+    if raw["status"] & _cabi.STATUS_FP32_TIE:       # whether fp32 ties here depends on rounding; if it does, it must be resolved
+        assert fixed["status"] == 0
+    assert [p["idx"] for p in _dicts(fixed, 125.0, n, True)] == [p["idx"] for p in want]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# K2 fp32 against the oracle at the cfg4 sizes
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("log2n", [20, 22, 24])
+def test_cfg4_large_transform_f32_vs_oracle(log2n):
+    """fp32 K2 (2-pass plan up to 2^22, 3-pass at 2^24 for fp32 tiles) against the bit-faithful C oracle run on the very
+    same (fp32-quantised) samples: every bin within 1e-5 of the window's largest magnitude, peak magnitudes within
+    rel 1e-5, peak index lists identical for both pickers."""
+    import torch
+    import apda_fft_b200
+    from apda_fft_b200.records import record_dtype
+    dev = torch.device("cuda:0")
+    an = apda_fft_b200.Analyzer(0)
+    an.use_stream(torch.cuda.current_stream(dev).cuda_stream)
+    n = 1 << log2n
+    i = np.arange(n, dtype=np.float64)
+    x = np.round(0.5 * np.sin(2 * np.pi * 101.6 * i / n) + 0.3 * np.sin(2 * np.pi * 252.4 * i / n + 0.3)
+                 + 0.2 * np.sin(2 * np.pi * 498.0 * i / n + 1.1) + 0.01 * np.cos(i * 0.37) + 0.125, 6).astype(np.float32)
+    d_x = torch.from_numpy(x[None, :]).to(dev)
+    d_spec = torch.empty((1, n, 2), dtype=torch.float32, device=dev)
+    an.fft_device(d_x.data_ptr(), 1, n, n, "f32", d_spec.data_ptr())
+    recs = {}
+    for flexible in (True, False):
+        d_rec = torch.zeros((1, 128), dtype=torch.uint8, device=dev)
+        an.peaks_device(d_spec.data_ptr(), 1, n, "f32", 125.0, d_rec.data_ptr(), flexible=flexible, k=4 if flexible else 5)
+        torch.cuda.synchronize()
+        recs[flexible] = d_rec.cpu().numpy().view(record_dtype(5)).reshape(-1)[0]
+    got = d_spec.cpu().numpy().view(np.complex64).reshape(n).astype(np.complex128)
+    want = c_oracle.start_fft_batch(x.astype(np.float64)[None, :])[0]
+    top = np.abs(want).max()
+    assert np.abs(got - want).max() <= 1e-5 * top, np.abs(got - want).max() / top
+    ref_p = ref_port.top_peaks_prominence(want.tolist(), 125.0)
+    ref_r = ref_port.top_peaks_resolution(want.tolist(), 125.0)
+    for flexible, ref in ((True, ref_p), (False, ref_r)):
+        mine = _dicts(recs[flexible], 125.0, n, flexible)
+        assert [p["idx"] for p in mine] == [p["idx"] for p in ref], (flexible, mine, ref)
+        for g, r in zip(mine, ref):
+            assert abs(g["mag"] - r["mag"]) <= 1e-4 + 1e-5 * r["mag"]
+            if flexible:
+                assert abs(g["prominence"] - r["prominence"]) <= 1e-5 * r["prominence"]
+    assert [p["idx"] for p in ref_p] == [102, 252, 498]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# (f4) result packing from a table produced on the GPU
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("flexible", [True, False])
+def test_result_packing_from_gpu_record_table(flexible, tmp_path, an):
+    """Records of a fleet batch computed on the GPU -> columnar Arrow table / JSONL / per-window gateway entries and
+    uploader blocks, compared with what the reference's caller (GT_FFT_v5.py:644-659) and uploader
+    (utils/fastapi_manager.py:37-47) build from the ORACLE's peaks of the same windows."""
+    import apda_fft_b200.synth as synth
+    from apda_fft_b200 import records
+    b, n, fs, k = 96, 4096, 125.0, 4
+    x = synth.fleet_windows(5_000, b, n)
+    recs = an.analyze(x, fs, flexible=flexible, k=k)
+    spectra = c_oracle.start_fft_batch(x)
+    oracle_peaks = [(ref_port.top_peaks_prominence if flexible else ref_port.top_peaks_resolution)(spectra[w].tolist(), fs, k)
+                    for w in range(b)]
+    table = records.fleet_arrow(recs, fs, n, flexible=flexible, k=k, first_window=5_000)
+    assert table.num_rows == b and table.column("window").to_pylist() == list(range(5_000, 5_000 + b))
+    idx_col, freq_col, mag_col = (table.column(c).to_pylist() for c in ("idx", "freq", "mag"))
+    path = tmp_path / "fleet.jsonl"
+    assert records.write_fleet_jsonl(path, recs, fs, n, flexible=flexible, k=k, first_window=5_000) == b
+    rows = [json.loads(line) for line in open(path)]
+    summary = {"rms_x": 0.011, "rms_y": -0.0222, "rms_z": 0.9981, "temperature": 25.01, "humidity": 85.0}
+    for w in range(b):
+        want = oracle_peaks[w]
+        assert idx_col[w] == [p["idx"] for p in want]
+        assert freq_col[w] == [p["idx"] * (fs / n) for p in want]
+        if flexible:
+            assert [round(m, 4) for m in mag_col[w]] == [p["mag"] for p in want]
+        else:
+            assert mag_col[w] == [p["mag"] for p in want]
+        # the reference caller's dict, built from the oracle's list vs from the GPU record
+        ref_entry = {"peak_freq": -1, "max_mag": -1}
+        if want:
+            ref_entry["peak_freq"], ref_entry["max_mag"] = want[0]["freq"], want[0]["mag"]
+            for i, pk in enumerate(want):
+                ref_entry[f"peak_freq_{i + 1}"], ref_entry[f"max_mag_{i + 1}"] = pk["freq"], pk["mag"]
+        entry = records.gateway_entry(_dicts(recs[w], fs, n, flexible))
+        assert entry == ref_entry, w
+        up = records.upload_metrics(summary, "Z", entry)
+        assert up["fft_freqs"] == [ref_entry.get(f"peak_freq_{i}", 0.0) for i in range(1, 5)]
+        assert up["fft_mags"] == [ref_entry.get(f"max_mag_{i}", 0.0) for i in range(1, 5)]
+        assert rows[w]["window"] == 5_000 + w
+        assert rows[w]["fft_freqs"] == ([p["freq"] for p in want] + [0.0] * k)[:k]
+        assert rows[w]["fft_mags"] == ([p["mag"] for p in want] + [0.0] * k)[:k]

@@ -201,3 +201,33 @@ def test_port_fuzz_against_live_reference():
             _run(ref_port.top_peaks_prominence, list(spec), fs, k)
         assert _run(ref["get_peak_resolution"].get_top_peaks_resolution, list(spec), fs, k) == \
             _run(ref_port.top_peaks_resolution, list(spec), fs, k)
+
+
+def test_reference_copy_and_gateway_replay_reference_mode(golden, tmp_path):
+    """oracle/_ref (build-time copy of the unmodified reference; only where /root/reference exists): the hot-path
+    functions loaded from it reproduce the goldens, and the real call site Gateway.work_flow_fft runs on a KAT-A log with
+    digidevice stubbed - the CPU half of tests/test_gpu_round2.py's drop-in replay."""
+    import json
+    import subprocess
+    import sys
+    from oracle import ref_copy
+    if ref_copy.build_ref() is None or not ref_copy.available(call_site=True):
+        pytest.skip("no reference checkout and no oracle/_ref copy")
+    ref = ref_copy.RefModules()
+    g = golden["cases"]["katA"]
+    x, fs = cases.build_samples(g["spec"])
+    spec = ref.start_fft(x.tolist(), fs)
+    assert cases.spectrum_sha16(spec) == g["spectrum_sha"]
+    assert ref.get_top_peaks_prominence(spec, fs) == g["prominence"]["ok"]
+    assert ref.get_top_peaks_resolution(spec, fs) == g["resolution"]["ok"]
+    path = tmp_path / "0013a2_Xaxis.log"
+    cases.write_sensor_log(path, x, fs, "X", missing_marker_at=9)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for flexible, key in ((1, "prominence"), (0, "resolution")):
+        out = subprocess.run([sys.executable, os.path.join(root, "tests", "gateway_replay.py"), "ref", str(flexible), "0013a2",
+                              str(path)], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stderr
+        entry = json.loads(out.stdout.strip().splitlines()[-1])["fft_dict"]["0013a2"]["X"]
+        want = g[key]["ok"]
+        assert entry["peak_freq"] == want[0]["freq"] and entry["max_mag"] == want[0]["mag"]
+        assert [entry[f"peak_freq_{i + 1}"] for i in range(len(want))] == [p["freq"] for p in want]
