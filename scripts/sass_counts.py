@@ -43,7 +43,7 @@ def main():
             continue
         if name is None:
             continue
-        counts[name]["instructions"] += bool(re.search(r"/\*[0-9a-f]{4}\*/", line))
+        counts[name]["instructions"] += bool(re.search(r"/\*[0-9a-f]{4,5}\*/", line))
         for pat in PATTERNS:
             if re.search(r"\b" + re.escape(pat), line):
                 counts[name][pat] += 1

@@ -173,14 +173,14 @@ def test_multichunk_wire16_ragged_list_per_stream(dtype, an):
 
 
 def test_ragged_status_bits_on_general_kernel_sizes(an):
-    """Status bits 2 / 3 are written on every ragged path, not only where a specialised FFT kernel ran: N = 512 and
-    N = 16384 have none, and generic_only bypasses them at N = 4096."""
+    """Status bits 2 / 3 are written on every ragged path, not only where a specialised FFT kernel ran: N = 256 and
+    N = 512 have none, and generic_only bypasses them at N = 4096."""
     import torch
     from apda_fft_b200.records import record_dtype
     dev = torch.device("cuda:0")
     an.use_stream(torch.cuda.current_stream(dev).cuda_stream)
     try:
-        for n, generic in ((512, False), (16384, False), (4096, True)):
+        for n, generic in ((512, False), (256, False), (4096, True)):
             counts = [n, n // 2 - 3, 0, n - 1, n // 2 + 1, 1]
             x = torch.randn((len(counts), n), dtype=torch.float64, device=dev)
             d_nv = torch.tensor(counts, dtype=torch.int32, device=dev)
