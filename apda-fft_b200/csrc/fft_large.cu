@@ -17,6 +17,8 @@
 // 1e-12: the reference's own twiddle drift reaches 3e-10 at N = 2^24).  fp32 runs the same passes on the rounded table.
 // The exact median of up to 2^30 samples is a multi-CTA radix select (histogram passes over HBM).
 #include <cuda.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -24,7 +26,7 @@
 
 namespace {
 
-constexpr int kThreads = 512;
+constexpr int kThreads = 512;  // default CTA size; the pass kernels are templated on it (NT)
 
 template <typename T>
 __device__ __forceinline__ void butterfly(typename vec2<T>::type &u, typename vec2<T>::type &v,
@@ -46,13 +48,13 @@ __device__ __forceinline__ void butterfly(typename vec2<T>::type &u, typename ve
 // Element (row r, column c) of the pass's working set lives at tile[r * rs + c * cs]; rows r = (hi << (t0+QR)) + (k << t0) + jr.
 // Twiddle of stage t for row r: T_{s0+t}[((r mod 2^(t-1)) << s0) + lo0 + c]  (head pass: s0 = 0 and no column term - its
 // columns are independent sub-transforms).  Same dataflow graph and individually rounded operations as before.
-template <typename T, int QR, bool HEAD>
+template <typename T, int QR, bool HEAD, int NT>
 __device__ __forceinline__ void stage_round(typename vec2<T>::type *tile, int rs, int cs, int logC, int q, int t0,
                                             const typename vec2<T>::type *__restrict__ tw, int s0, int64_t lo0, int tid) {
     using V2 = typename vec2<T>::type;
     constexpr int R = 1 << QR;
     const int items = 1 << (logC + q - QR);
-    for (int item = tid; item < items; item += kThreads) {
+    for (int item = tid; item < items; item += NT) {
         const int c = item & ((1 << logC) - 1), rest = item >> logC;
         const int jr = rest & ((1 << t0) - 1), hi = rest >> t0;
         V2 *p = tile + (size_t)(((hi << (t0 + QR)) + jr)) * rs + (size_t)c * cs;
@@ -77,24 +79,24 @@ __device__ __forceinline__ void stage_round(typename vec2<T>::type *tile, int rs
 }
 
 // all q stages of a pass, three at a time (the remainder as 2+2, 2 or 1), one barrier per round
-template <typename T, bool HEAD>
+template <typename T, bool HEAD, int NT>
 __device__ __forceinline__ void run_stages(typename vec2<T>::type *tile, int rs, int cs, int logC, int q,
                                            const typename vec2<T>::type *__restrict__ tw, int s0, int64_t lo0, int tid) {
     int t0 = 0;
     while (t0 < q) {
         const int left = q - t0;
         const int qr = left > 4 ? 3 : (left == 4 ? 2 : left);
-        if (qr == 3) stage_round<T, 3, HEAD>(tile, rs, cs, logC, q, t0, tw, s0, lo0, tid);
-        else if (qr == 2) stage_round<T, 2, HEAD>(tile, rs, cs, logC, q, t0, tw, s0, lo0, tid);
-        else stage_round<T, 1, HEAD>(tile, rs, cs, logC, q, t0, tw, s0, lo0, tid);
+        if (qr == 3) stage_round<T, 3, HEAD, NT>(tile, rs, cs, logC, q, t0, tw, s0, lo0, tid);
+        else if (qr == 2) stage_round<T, 2, HEAD, NT>(tile, rs, cs, logC, q, t0, tw, s0, lo0, tid);
+        else stage_round<T, 1, HEAD, NT>(tile, rs, cs, logC, q, t0, tw, s0, lo0, tid);
         __syncthreads();
         t0 += qr;
     }
 }
 
 // ---- head pass ------------------------------------------------------------------------------------------------------
-template <typename T, bool COMPLEX_IN>
-__global__ void __launch_bounds__(kThreads)
+template <typename T, bool COMPLEX_IN, int NT>
+__global__ void __launch_bounds__(NT)
 large_head_kernel(const T *__restrict__ samples, int64_t n_samples, int64_t ld, int n, int q, int C,
                   const typename vec2<T>::type *__restrict__ tw, typename vec2<T>::type *__restrict__ spec,
                   const T *__restrict__ med_ptr) {
@@ -110,7 +112,7 @@ large_head_kernel(const T *__restrict__ samples, int64_t n_samples, int64_t ld, 
     const int rows = 1 << q;
 
     const int logC = 31 - __clz(C);  // C is a power of two
-    for (int e = tid; e < (C << q); e += kThreads) {
+    for (int e = tid; e < (C << q); e += NT) {
         const int c = e & (C - 1), jh = e >> logC;
         const int64_t j = ((int64_t)jh << (n - q)) + lo0 + c;
         V2 val;
@@ -125,10 +127,10 @@ large_head_kernel(const T *__restrict__ samples, int64_t n_samples, int64_t ld, 
     }
     __syncthreads();
 
-    run_stages<T, true>(work, 1, LDW, logC, q, tw, 0, 0, tid);
+    run_stages<T, true, NT>(work, 1, LDW, logC, q, tw, 0, 0, tid);
 
     V2 *out = spec + win * N;
-    for (int e = tid; e < (C << q); e += kThreads) {
+    for (int e = tid; e < (C << q); e += NT) {
         const int c = e >> q, il = e & (rows - 1);
         const int64_t ih = (int64_t)(__brev((unsigned)(lo0 + c)) >> (32 - (n - q)));
         out[(ih << q) + il] = work[c * LDW + il];
@@ -159,7 +161,7 @@ large_tail_kernel(typename vec2<T>::type *__restrict__ spec, int n, int s0, int 
     }
     __syncthreads();
 
-    run_stages<T, false>(tile, LD, 1, logC, q, tw, s0, lo0, tid);
+    run_stages<T, false, kThreads>(tile, LD, 1, logC, q, tw, s0, lo0, tid);
 
     for (int e = tid; e < (C << q); e += kThreads) {
         const int c = e & (C - 1), r = e >> logC;
@@ -177,8 +179,10 @@ large_tail_kernel(typename vec2<T>::type *__restrict__ spec, int n, int s0, int 
 // (innermost dimension counted in scalars: 2 per complex value).
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <typename T>
-__global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 3 : 1)  // fp32: 3 tiles per SM in flight (load / compute / store)
+// NT threads, MINB resident CTAs per SM: several tiles per SM in flight are what overlaps the bulk load of one tile with
+// the butterflies of another and the bulk store of a third (a CTA alone runs load -> compute -> store back to back)
+template <typename T, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 large_tail_tma_kernel(const __grid_constant__ CUtensorMap tmap, int n, int s0, int q, int C,
                       const typename vec2<T>::type *__restrict__ tw, int zero_dc) {
     using V2 = typename vec2<T>::type;
@@ -223,7 +227,7 @@ large_tail_tma_kernel(const __grid_constant__ CUtensorMap tmap, int n, int s0, i
         }
     }
 
-    run_stages<T, false>(tile, C, 1, 31 - __clz(C), q, tw, s0, lo0, tid);
+    run_stages<T, false, NT>(tile, C, 1, 31 - __clz(C), q, tw, s0, lo0, tid);
     if (zero_dc && hi == 0 && lo0 == 0 && tid == 0) tile[0].x = tile[0].y = T(0);  // reference: res[0] = 0
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk store
     __syncthreads();
@@ -388,131 +392,480 @@ __global__ void select_prepare_upper_kernel(SelectState *st) {
     st->mask = ~0ull;
 }
 
-// After two digit passes the bucket of the median holds a small fraction of the window (sensor samples: a few percent).
-// One more pass over the window copies that bucket out (warp-aggregated append) and records the smallest key of the
-// buckets above it; everything else runs on the copy, in one CTA.
+// ---- exact median of one long window: sampled bracket + linear buckets (2 passes over the window) -----------------------
+// The MSB digits of floating-point keys are a poor histogram (sign and exponent: nearly every sample of a sensor window
+// falls into two or three of the 256 bins, and the shared-memory atomics serialise).  Instead:
+//   sample   one CTA draws 1024 stratified pseudo-random samples and takes, from a linear histogram of them, a value
+//            bracket [lo, hi) around the sample median that is ~16 sigma of the sampling error wide (about a quarter of
+//            the window), or the single plateau value if the middle of the sample is one repeated value;
+//   count    one pass over the window (128-bit loads): samples below the bracket are counted, samples inside it go
+//            into 4096 LINEAR buckets (a monotone map, so buckets are ordered like the values);
+//   compact  every CTA first re-derives, from the bucket counts, the bucket (or the region below / above the bracket,
+//            should the sample have missed) that holds the lower middle order statistic and its rank inside; the
+//            second pass then copies that bucket out (warp-aggregated append; typically a few hundred values) and
+//            records the smallest value after it;
+//   finish   one CTA ranks the copy (directly when it is small, else by an 8-bit radix select on the keys; immediate
+//            when all copied values are equal), finds the upper middle value (same key if duplicated across the
+//            midpoint, else the next key, inside the copy or after it) and writes statistics.median.
+// Exact for any input: the bracket only steers where the resolution goes.
+constexpr int kBrBuckets = 4096;
+constexpr int kBrSample = 1024;
+constexpr int kBrThreads = 256;
+
 template <typename T>
-__global__ void __launch_bounds__(256) select_compact_kernel(const T *__restrict__ x, int64_t n, SelectState *st,
-                                                             T *__restrict__ bucket) {
-    using K = typename KeyT<T>::type;
-    __shared__ unsigned long long blk_min[8];
-    const K prefix = (K)st->prefix, mask = (K)st->mask;
-    const int lane = threadIdx.x & 31;
-    unsigned long long above = ~0ull;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t rounds = (n + stride - 1) / stride;
-    for (int64_t it = 0; it < rounds; ++it) {
-        const int64_t i = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        const bool valid = i < n;
-        const T v = valid ? x[i] : T(0);
-        const K k = ordered_key(v);
-        const bool in = valid && (k & mask) == prefix;
-        if (valid && (k & mask) > prefix && (unsigned long long)k < above) above = (unsigned long long)k;
-        const unsigned hit = __ballot_sync(0xffffffffu, in);
-        if (hit) {
-            unsigned long long base = 0;
-            if (lane == __ffs(hit) - 1) base = atomicAdd(&st->m, (unsigned long long)__popc(hit));
-            base = __shfl_sync(0xffffffffu, base, __ffs(hit) - 1);
-            if (in) bucket[base + __popc(hit & ((1u << lane) - 1u))] = v;
+struct BracketState {  // device resident, one per stream
+    T lo, hi, scale;            // bracket [lo, hi), scale = buckets / (hi - lo)
+    int mode;                   // winning region: -1 below the bracket, 0..B-1 a bucket, B at or above hi
+    long long rank;             // rank of the lower middle order statistic inside the winning region
+    unsigned long long below;   // samples < lo
+    unsigned long long m;       // samples copied out
+    unsigned long long above_min, kmin, kmax;  // smallest key after the region; smallest / largest key copied
+    unsigned hist[kBrBuckets];
+};
+
+template <typename T>
+__device__ __forceinline__ int br_bucket(T x, T lo, T scale) {  // for lo <= x < hi
+    const int b = (int)(sub_rn(x, lo) * scale);  // monotone in x; NaN -> 0
+    return b < 0 ? 0 : (b >= kBrBuckets ? kBrBuckets - 1 : b);
+}
+template <typename T>
+__device__ __forceinline__ T next_above_t(T v) {
+    T n = key_value(ordered_key(v) + 1, T(0));
+    if (!(n > v)) n = key_value(ordered_key(v) + 2, T(0));  // -0.0 -> +0.0 compares equal
+    return n;
+}
+__device__ __forceinline__ unsigned block_scan_incl_1024(unsigned v, unsigned *warp_tot /* 32 */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    if (lane == 31) warp_tot[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned w = warp_tot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += t;
         }
+        warp_tot[lane] = w;
+    }
+    __syncthreads();
+    return v + (warp ? warp_tot[warp - 1] : 0u);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024) br_sample_kernel(const T *__restrict__ x, int64_t n, BracketState<T> *st) {
+    __shared__ unsigned bins[1024];
+    __shared__ unsigned wt[32];
+    __shared__ T red_min[32], red_max[32];
+    __shared__ int s_a, s_b;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int S = (int)(n < kBrSample ? n : kBrSample);
+    const int64_t g = n / S;  // stratum size (>= 1)
+    T v = T(0), mn = CUDART_INF, mx = -CUDART_INF;
+    if (tid < S) {
+        unsigned h = (unsigned)tid * 2654435761u;  // position inside the stratum: a hash, so periodic signals cannot alias
+        h ^= h >> 15;
+        h *= 2246822519u;
+        h ^= h >> 13;
+        v = x[(int64_t)tid * g + (int64_t)(h % (unsigned long long)g)];
+        mn = mx = v;
+    }
+    bins[tid] = 0;
+    for (int i = tid; i < kBrBuckets; i += 1024) st->hist[i] = 0;
+    if (tid == 0) {
+        s_a = 0;
+        s_b = 1023;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, above, o);
-        above = other < above ? other : above;
+        const T a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
     }
-    if (lane == 0) blk_min[threadIdx.x >> 5] = above;
+    if (lane == 0) {
+        red_min[warp] = mn;
+        red_max[warp] = mx;
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; ++w) above = blk_min[w] < above ? blk_min[w] : above;
-        if (above != ~0ull) atomicMin(&st->above_min, above);
+    for (int w = 0; w < 32; ++w) {
+        mn = red_min[w] < mn ? red_min[w] : mn;
+        mx = red_max[w] > mx ? red_max[w] : mx;
+    }
+    const T width = sub_rn(mx, mn);
+    const bool flat = !(width > T(0)) || !(width < CUDART_INF);  // one value (or no finite range): bracket = that value
+    const T sc = flat ? T(0) : T(1024) / width;
+    if (!flat && tid < S) {
+        int b = (int)(sub_rn(v, mn) * sc);
+        b = b < 0 ? 0 : (b > 1023 ? 1023 : b);
+        atomicAdd(&bins[b], 1u);
+    }
+    __syncthreads();
+    // sample ranks S/2 -+ S/8: the population rank of a sample order statistic is off by ~N/(2 sqrt(S)) = N/64
+    const unsigned mine = bins[tid];
+    const unsigned cum = block_scan_incl_1024(mine, wt);
+    const unsigned r0 = (unsigned)(S / 2 - S / 8), r1 = (unsigned)(S / 2 + S / 8);
+    if (mine && cum - mine <= r0 && r0 < cum) s_a = tid;
+    if (mine && cum - mine <= r1 && r1 < cum) s_b = tid;
+    __syncthreads();
+    if (tid == 0) {
+        T lo = mn, hi = next_above_t(mn);
+        if (!flat) {
+            const int a = s_a, b = s_b;
+            lo = add_rn(mn, (T)a * (width / T(1024)));
+            hi = add_rn(mn, (T)(b + 1) * (width / T(1024)));
+            if (a == 0) lo = mn;
+            if (!(hi > lo)) hi = next_above_t(lo);
+        }
+        const T w2 = sub_rn(hi, lo);
+        st->lo = lo;
+        st->hi = hi;
+        st->scale = (w2 > T(0) && (T)kBrBuckets / w2 < CUDART_INF) ? (T)kBrBuckets / w2 : T(0);  // 0: everything inside -> bucket 0
+        st->mode = 0;
+        st->rank = 0;
+        st->below = 0;
+        st->m = 0;
+        st->above_min = ~0ull;
+        st->kmin = ~0ull;
+        st->kmax = 0ull;
     }
 }
 
-// the remaining digits, the upper middle value and statistics.median itself, on the copied bucket, one CTA
-template <typename T>
-__global__ void __launch_bounds__(1024) select_small_kernel(const T *__restrict__ bucket, SelectState *st, int64_t n,
-                                                             int first_shift, T *med_out) {
-    using K = typename KeyT<T>::type;
-    __shared__ unsigned h[256];
-    __shared__ unsigned long long s_prefix, s_mask, s_le, s_above;
-    __shared__ long long s_rank;
-    const long long m = (long long)st->m;
-    if (threadIdx.x == 0) {
-        s_prefix = st->prefix;
-        s_mask = st->mask;
-        s_rank = st->rank;  // rank of the lower middle inside the bucket
-        s_le = 0;
-        s_above = ~0ull;
-    }
-    for (int shift = first_shift; shift >= 0; shift -= 8) {
-        if (threadIdx.x < 256) h[threadIdx.x] = 0;
-        __syncthreads();
-        const K prefix = (K)s_prefix, mask = (K)s_mask;
-        for (long long i = threadIdx.x; i < m; i += blockDim.x) {
-            const K k = ordered_key(bucket[i]);
-            if ((k & mask) == prefix) atomicAdd(&h[(unsigned)(k >> shift) & 255u], 1u);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            long long rank = s_rank;
-            unsigned long long acc = 0;
-            int digit = 255;
-            for (int d = 0; d < 256; ++d) {
-                if (rank < (long long)(acc + h[d])) {
-                    digit = d;
-                    break;
-                }
-                acc += h[d];
+// One pass over x[0, n) with 128-bit loads, four in flight per thread: body(e, valid) sees E = 4 * 16/sizeof(T) elements
+// per call (bit u of `valid`: e[u] is a sample).  Warp-uniform trip count (the bodies use warp collectives); the
+// few samples before the first / after the last aligned 16-byte vector go through the same body, one per lane.
+template <typename T, typename Body>
+__device__ __forceinline__ void br_stream(const T *__restrict__ x, int64_t n, Body body) {
+    constexpr int VEC = 16 / (int)sizeof(T), UNR = 4, E = VEC * UNR;
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(x);
+    int64_t a0 = (int64_t)(((16 - (addr & 15)) & 15) / sizeof(T));  // first element on a 16-byte boundary
+    if (a0 > n) a0 = n;
+    const int64_t nvec = (n - a0) / VEC;
+    const int4 *xv = reinterpret_cast<const int4 *>(x + a0);
+    const int64_t per_it = (int64_t)gridDim.x * kBrThreads * UNR;
+    for (int64_t it0 = 0; it0 < nvec; it0 += per_it) {
+        T e[E];
+        unsigned valid = 0;
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int64_t iv = it0 + ((int64_t)blockIdx.x * UNR + u) * kBrThreads + threadIdx.x;
+            int4 raw = make_int4(0, 0, 0, 0);
+            if (iv < nvec) {
+                raw = __ldg(xv + iv);
+                valid |= ((1u << VEC) - 1u) << (u * VEC);
             }
-            s_rank = rank - (long long)acc;
-            s_prefix |= (unsigned long long)digit << shift;
-            s_mask |= 255ull << shift;
+            const T *p = reinterpret_cast<const T *>(&raw);
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) e[u * VEC + q] = p[q];
+        }
+        body(e, valid);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 32) {  // leftovers: < VEC in front, < VEC behind
+        const int64_t tail0 = a0 + nvec * VEC;
+        const int64_t left = a0 + (n - tail0);
+        T e[E];
+#pragma unroll
+        for (int u = 0; u < E; ++u) e[u] = T(0);
+        unsigned valid = 0;
+        if ((int64_t)threadIdx.x < left) {
+            const int64_t i = (int64_t)threadIdx.x < a0 ? (int64_t)threadIdx.x : tail0 + ((int64_t)threadIdx.x - a0);
+            e[0] = x[i];
+            valid = 1u;
+        }
+        body(e, valid);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBrThreads) br_count_kernel(const T *__restrict__ x, int64_t n, BracketState<T> *st) {
+    constexpr int E = 4 * 16 / (int)sizeof(T);
+    __shared__ unsigned h[kBrBuckets];
+    for (int i = threadIdx.x; i < kBrBuckets; i += kBrThreads) h[i] = 0;
+    __syncthreads();
+    const T lo = st->lo, hi = st->hi, scale = st->scale;
+    unsigned below = 0;
+    br_stream<T>(x, n, [&](const T (&e)[E], unsigned valid) {
+        int cur = -1;  // run of equal buckets among this thread's consecutive samples: one atomic per run
+        unsigned run = 0;
+#pragma unroll
+        for (int u = 0; u < E; ++u) {
+            const bool ok = (valid >> u) & 1u;
+            below += ok && e[u] < lo;
+            if (ok && !(e[u] < lo) && !(e[u] >= hi)) {
+                const int b = br_bucket<T>(e[u], lo, scale);
+                if (b == cur) {
+                    ++run;
+                } else {
+                    if (run) atomicAdd(&h[cur], run);
+                    cur = b;
+                    run = 1;
+                }
+            }
+        }
+        if (run) atomicAdd(&h[cur], run);
+    });
+    below = __reduce_add_sync(0xffffffffu, below);
+    if ((threadIdx.x & 31) == 0 && below) atomicAdd(&st->below, (unsigned long long)below);
+    __syncthreads();
+    for (int b = threadIdx.x; b < kBrBuckets; b += kBrThreads)
+        if (h[b]) atomicAdd(&st->hist[b], h[b]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBrThreads) br_compact_kernel(const T *__restrict__ x, int64_t n, BracketState<T> *st,
+                                                               T *__restrict__ bucket) {
+    constexpr int E = 4 * 16 / (int)sizeof(T);
+    constexpr int PER = kBrBuckets / kBrThreads;
+    __shared__ unsigned long long wsum[kBrThreads / 32];
+    __shared__ int s_mode;
+    __shared__ long long s_rank;
+    __shared__ unsigned long long blk[3][kBrThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // ---- pick: which region holds rank (n-1)/2, and the rank inside it (every CTA derives the same answer) ----------
+    {
+        unsigned long long mine = 0;
+        unsigned cnt[PER];
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            cnt[u] = st->hist[threadIdx.x * PER + u];
+            mine += cnt[u];
+        }
+        unsigned long long incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        unsigned long long ahead = 0, inside = 0;
+        for (int w = 0; w < kBrThreads / 32; ++w) {
+            if (w < warp) ahead += wsum[w];
+            inside += wsum[w];
+        }
+        const long long r_lo = (long long)((n - 1) / 2), below = (long long)st->below;
+        if (threadIdx.x == 0) {
+            if (r_lo < below) {
+                s_mode = -1;
+                s_rank = r_lo;
+            } else if (r_lo >= below + (long long)inside) {
+                s_mode = kBrBuckets;
+                s_rank = r_lo - below - (long long)inside;
+            }
+        }
+        long long acc = below + (long long)(ahead + incl - mine);  // samples ahead of this thread's first bucket
+        if (r_lo >= acc && r_lo < acc + (long long)mine) {
+#pragma unroll
+            for (int u = 0; u < PER; ++u) {
+                if (r_lo >= acc && r_lo < acc + (long long)cnt[u]) {
+                    s_mode = threadIdx.x * PER + u;
+                    s_rank = r_lo - acc;
+                }
+                acc += cnt[u];
+            }
         }
         __syncthreads();
     }
-    // lower middle = s_prefix.  Upper middle: the same key if its duplicates reach across the midpoint, else the smallest
-    // key above it (inside the bucket, or the smallest key of the buckets above)
-    const K lo = (K)s_prefix;
-    unsigned long long le = 0, above = ~0ull;
-    for (long long i = threadIdx.x; i < m; i += blockDim.x) {
-        const K k = ordered_key(bucket[i]);
-        le += (k <= lo);
-        if (k > lo && (unsigned long long)k < above) above = (unsigned long long)k;
+    const int mode = s_mode;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->mode = mode;
+        st->rank = s_rank;
     }
+    // ---- compact ---------------------------------------------------------------------------------------------------
+    const T lo = st->lo, hi = st->hi, scale = st->scale;
+    T amin = CUDART_INF;                       // smallest value after the region
+    unsigned long long kmin = ~0ull, kmax = 0ull;  // key range of the copied values
+    br_stream<T>(x, n, [&](const T (&e)[E], unsigned valid) {
+        unsigned take = 0;
+#pragma unroll
+        for (int u = 0; u < E; ++u) {
+            if (!((valid >> u) & 1u)) continue;
+            const int r = e[u] < lo ? -1 : (e[u] >= hi ? kBrBuckets : br_bucket<T>(e[u], lo, scale));
+            if (r == mode) take |= 1u << u;
+            else if (r > mode && e[u] < amin) amin = e[u];
+        }
+        if (!__any_sync(0xffffffffu, take != 0)) return;
+        unsigned incl = (unsigned)__popc(take);  // offsets inside the warp's append
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&st->m, (unsigned long long)total);
+        base = __shfl_sync(0xffffffffu, base, 0) + (incl - (unsigned)__popc(take));
+#pragma unroll
+        for (int u = 0; u < E; ++u) {
+            if ((take >> u) & 1u) {
+                bucket[base++] = e[u];
+                const unsigned long long k = (unsigned long long)ordered_key(e[u]);
+                kmin = k < kmin ? k : kmin;
+                kmax = k > kmax ? k : kmax;
+            }
+        }
+    });
+    unsigned long long above = amin < CUDART_INF ? (unsigned long long)ordered_key(amin) : ~0ull;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        le += __shfl_xor_sync(0xffffffffu, le, o);
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, above, o);
-        above = other < above ? other : above;
+        const unsigned long long a = __shfl_xor_sync(0xffffffffu, above, o), b = __shfl_xor_sync(0xffffffffu, kmin, o),
+                                 c = __shfl_xor_sync(0xffffffffu, kmax, o);
+        above = a < above ? a : above;
+        kmin = b < kmin ? b : kmin;
+        kmax = c > kmax ? c : kmax;
     }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&s_le, le);
-        atomicMin(&s_above, above);
+    if (lane == 0) {
+        blk[0][warp] = above;
+        blk[1][warp] = kmin;
+        blk[2][warp] = kmax;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        // elements below the bucket: the rank the search started with minus the rank left when the bucket was fixed
-        const long long below = (long long)((n - 1) / 2) - st->rank;
+        for (int w = 1; w < kBrThreads / 32; ++w) {
+            above = blk[0][w] < above ? blk[0][w] : above;
+            kmin = blk[1][w] < kmin ? blk[1][w] : kmin;
+            kmax = blk[2][w] > kmax ? blk[2][w] : kmax;
+        }
+        if (above != ~0ull) atomicMin(&st->above_min, above);
+        if (kmin != ~0ull) atomicMin(&st->kmin, kmin);
+        if (kmax != 0ull) atomicMax(&st->kmax, kmax);
+    }
+}
+
+// rank `st->rank` of the copied region, the upper middle value and statistics.median itself, one CTA
+template <typename T>
+__global__ void __launch_bounds__(1024) br_finish_kernel(const T *__restrict__ bucket, BracketState<T> *st, int64_t n,
+                                                          T *med_out) {
+    using K = typename KeyT<T>::type;
+    constexpr int kDirect = 256;  // copies up to this size are ranked directly (m^2 comparisons)
+    __shared__ K keys[kDirect];
+    __shared__ unsigned h[256];
+    __shared__ unsigned wt[32];
+    __shared__ unsigned long long s_prefix, s_mask, s_le, s_above, s_lo;
+    __shared__ long long s_rank;
+    const long long m = (long long)st->m;
+    const long long rank0 = st->rank;
+    if (threadIdx.x == 0) {
+        s_prefix = 0;
+        s_mask = 0;
+        s_rank = rank0;
+        s_le = 0;
+        s_above = ~0ull;
+        s_lo = 0;
+    }
+    __syncthreads();
+    K lo_key;
+    if (st->kmin == st->kmax) {  // every copied value is the same (plateaus, constant windows)
+        lo_key = (K)st->kmin;
+        if (threadIdx.x == 0) s_le = (unsigned long long)m;
+        __syncthreads();
+    } else if (m <= kDirect) {
+        // direct ranking: thread i counts the keys below its own (ties by position); two keys per thread
+        for (int i = threadIdx.x; i < (int)m; i += 1024) keys[i] = ordered_key(bucket[i]);
+        __syncthreads();
+        for (int i = threadIdx.x; i < (int)m; i += 1024) {
+            const K mine = keys[i];
+            int below = 0, le = 0;
+            K next = ~(K)0;
+            for (int j = 0; j < (int)m; ++j) {
+                const K o = keys[j];
+                below += (o < mine) || (o == mine && j < i);
+                le += o <= mine;
+                if (o > mine && o < next) next = o;
+            }
+            if (below == (int)rank0) {  // exactly one thread: ranks with the position tie-break are a permutation
+                s_lo = (unsigned long long)mine;
+                s_le = (unsigned long long)le;
+                s_above = next == ~(K)0 ? ~0ull : (unsigned long long)next;
+            }
+        }
+        __syncthreads();
+        lo_key = (K)s_lo;
+    } else {
+        // the copied keys agree in every bit above the highest one in which the smallest and largest differ: the digit
+        // passes start at that byte
+        const int top = 63 - __clzll((long long)(st->kmin ^ st->kmax));
+        const int shift0 = (top / 8) * 8;
+        if (threadIdx.x == 0) {
+            const unsigned long long keep = shift0 + 8 >= 64 ? 0ull : ~((1ull << (shift0 + 8)) - 1ull);
+            s_prefix = st->kmin & keep;
+            s_mask = keep;
+        }
+        __syncthreads();
+        for (int shift = shift0; shift >= 0; shift -= 8) {
+            if (threadIdx.x < 256) h[threadIdx.x] = 0;
+            __syncthreads();
+            const K prefix = (K)s_prefix, mask = (K)s_mask;
+            int cur = -1;
+            unsigned run = 0;
+            for (long long i = threadIdx.x; i < m; i += blockDim.x) {
+                const K k = ordered_key(bucket[i]);
+                if ((k & mask) == prefix) {
+                    const int d = (int)((k >> shift) & 255u);
+                    if (d == cur) {
+                        ++run;
+                    } else {
+                        if (run) atomicAdd(&h[cur], run);
+                        cur = d;
+                        run = 1;
+                    }
+                }
+            }
+            if (run) atomicAdd(&h[cur], run);
+            __syncthreads();
+            const unsigned mine = threadIdx.x < 256 ? h[threadIdx.x] : 0u;
+            const unsigned cum = block_scan_incl_1024(mine, wt);
+            const long long rank = s_rank;
+            __syncthreads();
+            if (threadIdx.x < 256 && mine && rank >= (long long)(cum - mine) && rank < (long long)cum) {
+                s_rank = rank - (long long)(cum - mine);
+                s_prefix |= (unsigned long long)threadIdx.x << shift;
+                s_mask |= 255ull << shift;
+            }
+            __syncthreads();
+        }
+        lo_key = (K)s_prefix;
+        unsigned long long le = 0, above = ~0ull;
+        for (long long i = threadIdx.x; i < m; i += blockDim.x) {
+            const K k = ordered_key(bucket[i]);
+            le += (k <= lo_key);
+            if (k > lo_key && (unsigned long long)k < above) above = (unsigned long long)k;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            le += __shfl_xor_sync(0xffffffffu, le, o);
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, above, o);
+            above = other < above ? other : above;
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&s_le, le);
+            atomicMin(&s_above, above);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        // samples ahead of the copied region: the lower middle's global rank minus its rank inside the region
+        const long long before = (long long)((n - 1) / 2) - rank0;
         const unsigned long long up = s_above < st->above_min ? s_above : st->above_min;
-        const K hi = (below + (long long)s_le >= (long long)(n / 2 + 1)) ? lo : (K)up;
-        const T a = key_value(lo, T(0)), b = key_value(hi, T(0));
+        const K hi_key = (before + (long long)s_le >= (long long)(n / 2 + 1)) ? lo_key : (K)up;
+        const T a = key_value(lo_key, T(0)), b = key_value(hi_key, T(0));
         *med_out = div_rn(add_rn(a, b), T(2));  // statistics.median: middle value, or (a + b) / 2 for even n
     }
 }
 
 template <typename T>
-int large_median(apda_ctx *ctx, cudaStream_t st, const T *d_x, int64_t n, SelectState *state, T *d_med, T *d_bucket) {
-    const int bits = (int)sizeof(T) * 8;
-    const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8);
-    select_reset_kernel<<<1, 256, 0, st>>>(state, (long long)((n - 1) / 2));
-    for (int shift = bits - 8; shift >= bits - 16; shift -= 8) {  // two most significant digits on the whole window
-        select_hist_kernel<T><<<grid, 256, 0, st>>>(d_x, n, shift, state);
-        select_pick_kernel<<<1, 256, 0, st>>>(state, shift, 0, 0);
-    }
-    select_compact_kernel<T><<<grid, 256, 0, st>>>(d_x, n, state, d_bucket);
-    select_small_kernel<T><<<1, 1024, 0, st>>>(d_bucket, state, n, bits - 24, d_med);
-    ctx->launches += 7;
+int large_median(apda_ctx *ctx, cudaStream_t st, const T *d_x, int64_t n, void *state_raw, T *d_med, T *d_bucket) {
+    BracketState<T> *state = reinterpret_cast<BracketState<T> *>(state_raw);
+    constexpr int64_t per_cta = (int64_t)kBrThreads * 4 * (16 / (int)sizeof(T));  // samples per CTA and trip
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + per_cta - 1) / per_cta, (int64_t)ctx->sm_count * 8));
+    br_sample_kernel<T><<<1, 1024, 0, st>>>(d_x, n, state);
+    br_count_kernel<T><<<grid, kBrThreads, 0, st>>>(d_x, n, state);
+    br_compact_kernel<T><<<grid, kBrThreads, 0, st>>>(d_x, n, state, d_bucket);
+    br_finish_kernel<T><<<1, 1024, 0, st>>>(d_bucket, state, n, d_med);
+    ctx->launches += 4;
     APDA_CUDA(cudaGetLastError());
     return APDA_OK;
 }
@@ -550,6 +903,57 @@ static PassPlan make_plan(int n, int qmax) {
     return p;
 }
 
+// Tuning of the pass structure.  Defaults are the measured best on B200; the environment variables exist
+// for same-box A/B runs (scripts/k2_ab.py) and are read once per process.
+//   qmax      most radix-2 stages per pass (tile rows = 2^q)
+//   max_tile  complex elements per shared-memory tile (rows * columns)
+//   nt        threads per CTA of the tail passes;  minb: resident CTAs per SM the kernel is compiled for
+struct K2Tune {
+    int qmax, max_tile, nt, minb;
+};
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+template <typename T>
+static K2Tune k2_tune() {
+    static const K2Tune t = [] {
+        K2Tune d;
+        d.qmax = sizeof(T) == 8 ? 10 : 11;
+        d.max_tile = sizeof(T) == 8 ? 4096 : 8192;  // 64 KB tiles
+        d.nt = sizeof(T) == 8 ? 256 : 512;
+        d.minb = 3;
+        const char *sfx = sizeof(T) == 8 ? "64" : "32";
+        char name[32];
+        snprintf(name, sizeof(name), "APDA_K2_QMAX%s", sfx);
+        d.qmax = env_int(name, d.qmax);
+        snprintf(name, sizeof(name), "APDA_K2_TILE%s", sfx);
+        d.max_tile = env_int(name, d.max_tile);
+        snprintf(name, sizeof(name), "APDA_K2_NT%s", sfx);
+        d.nt = env_int(name, d.nt);
+        snprintf(name, sizeof(name), "APDA_K2_MINB%s", sfx);
+        d.minb = env_int(name, d.minb);
+        return d;
+    }();
+    return t;
+}
+
+template <typename T, int NT, int MINB>
+static int launch_tail_tma(cudaStream_t st, dim3 grid, size_t smem, const CUtensorMap &tm, int n, int s0, int q, int C,
+                           const typename vec2<T>::type *twp, int zero_dc) {
+    APDA_CUDA(cudaFuncSetAttribute(large_tail_tma_kernel<T, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    large_tail_tma_kernel<T, NT, MINB><<<grid, NT, smem, st>>>(tm, n, s0, q, C, twp, zero_dc);
+    return APDA_OK;
+}
+
+template <typename T, bool CPLX, int NT>
+static int launch_head(cudaStream_t st, dim3 grid, size_t smem, const T *d_samples, int64_t n_samples, int64_t ld, int n, int q,
+                       int C, const typename vec2<T>::type *twp, typename vec2<T>::type *spec, const T *d_med) {
+    APDA_CUDA(cudaFuncSetAttribute(large_head_kernel<T, CPLX, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    large_head_kernel<T, CPLX, NT><<<grid, NT, smem, st>>>(d_samples, n_samples, ld, n, q, C, twp, spec, d_med);
+    return APDA_OK;
+}
+
 }  // namespace
 
 template <typename T>
@@ -564,38 +968,46 @@ int launch_fft_large(apda_ctx *ctx, cudaStream_t st, const T *d_samples, int64_t
     TwiddleTables tw;
     APDA_TRY(apda_get_twiddles(ctx, N, &tw));
     const V2 *twp = sizeof(T) == 8 ? reinterpret_cast<const V2 *>(tw.d64) : reinterpret_cast<const V2 *>(tw.d32);
-    const int max_tile = sizeof(T) == 8 ? 4096 : 8192;  // complex elements per 64 KB tile: 3 CTAs per SM overlap load, compute and store
-    const PassPlan plan = make_plan(n, sizeof(T) == 8 ? 10 : 11);
+    const K2Tune tune = k2_tune<T>();
+    const int max_tile = tune.max_tile;  // complex elements per tile: 64 KB tiles let 3 CTAs per SM overlap load, compute and store
+    const PassPlan plan = make_plan(n, tune.qmax);
 
     // centring constant per window
     T *d_med = nullptr;
     if (!complex_input && flags != APDA_CENTER_NONE) {
         // per-stream scratch: the two host-pipeline streams may run long transforms concurrently
         const size_t med_bytes = ((size_t)batch * sizeof(T) + 255) & ~(size_t)255;
-        const size_t need = 2048 + med_bytes + (size_t)n_samples * sizeof(T);  // state, medians, bucket copy (worst case: all samples)
+        constexpr size_t kStateBytes = (sizeof(BracketState<T>) + sizeof(SelectState) + 255) & ~(size_t)255;
+        const size_t need = kStateBytes + med_bytes + (size_t)n_samples * sizeof(T);  // state, medians, bucket copy (worst case: all samples)
         auto &slot = ctx->stream_scratch[st];
         if (need > slot.second) {
             APDA_CUDA(cudaStreamSynchronize(st));
             APDA_TRY(apda_reserve(&slot.first, &slot.second, need));
         }
         SelectState *state = reinterpret_cast<SelectState *>(slot.first);
-        d_med = reinterpret_cast<T *>(reinterpret_cast<char *>(slot.first) + 2048);
-        T *d_bucket = reinterpret_cast<T *>(reinterpret_cast<char *>(slot.first) + 2048 + med_bytes);
+        d_med = reinterpret_cast<T *>(reinterpret_cast<char *>(slot.first) + kStateBytes);
+        T *d_bucket = reinterpret_cast<T *>(reinterpret_cast<char *>(slot.first) + kStateBytes + med_bytes);
         for (int64_t w = 0; w < batch; ++w) {
             if (ctx->generic_only) APDA_TRY(large_median_passes<T>(ctx, st, d_samples + w * ld, n_samples, state, d_med + w));
-            else APDA_TRY(large_median<T>(ctx, st, d_samples + w * ld, n_samples, state, d_med + w, d_bucket));
+            else APDA_TRY(large_median<T>(ctx, st, d_samples + w * ld, n_samples, slot.first, d_med + w, d_bucket));
         }
     }
 
     {  // head pass
         const int q = plan.q[0];
         const int64_t cols = (int64_t)1 << (n - q);
-        const int C = (int)std::min<int64_t>(std::min<int64_t>(max_tile >> q, 64), cols);
+        const int C = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(max_tile >> q, 64), cols));
         const size_t smem = (size_t)C * ((1u << q) + 1) * sizeof(V2);
-        auto kern = complex_input ? large_head_kernel<T, true> : large_head_kernel<T, false>;
-        APDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid((unsigned)(cols / C), (unsigned)batch);
-        kern<<<grid, kThreads, smem, st>>>(d_samples, n_samples, ld, n, q, C, twp, reinterpret_cast<V2 *>(d_spec), d_med);
+        V2 *spec = reinterpret_cast<V2 *>(d_spec);
+        const int hnt = smem > (96u << 10) ? 1024 : 512;  // a tile that leaves room for one CTA per SM gets the most threads
+        if (complex_input) {
+            if (hnt == 1024) APDA_TRY((launch_head<T, true, 1024>(st, grid, smem, d_samples, n_samples, ld, n, q, C, twp, spec, d_med)));
+            else APDA_TRY((launch_head<T, true, 512>(st, grid, smem, d_samples, n_samples, ld, n, q, C, twp, spec, d_med)));
+        } else {
+            if (hnt == 1024) APDA_TRY((launch_head<T, false, 1024>(st, grid, smem, d_samples, n_samples, ld, n, q, C, twp, spec, d_med)));
+            else APDA_TRY((launch_head<T, false, 512>(st, grid, smem, d_samples, n_samples, ld, n, q, C, twp, spec, d_med)));
+        }
         ctx->launches++;
         APDA_CUDA(cudaGetLastError());
     }
@@ -603,17 +1015,28 @@ int launch_fft_large(apda_ctx *ctx, cudaStream_t st, const T *d_samples, int64_t
     for (int p = 1; p < plan.npass; ++p) {
         const int q = plan.q[p];
         const int64_t cols = (int64_t)1 << s0;
-        const int C = (int)std::min<int64_t>(std::min<int64_t>(max_tile >> q, 64), cols);
+        const int C = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(max_tile >> q, 64), cols));
         const int64_t tiles = (cols / C) * ((int64_t)1 << (n - s0 - q));
         dim3 grid((unsigned)tiles, (unsigned)batch);
         const int zero_dc = (!complex_input && p == plan.npass - 1) ? 1 : 0;
         CUtensorMap tm;
-        if (!ctx->generic_only && make_tail_tmap<T>(&tm, d_spec, n, s0, q, C, batch)) {
-            const size_t smem = (size_t)C * (1u << q) * sizeof(V2) + 128;
-            APDA_CUDA(cudaFuncSetAttribute(large_tail_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            large_tail_tma_kernel<T><<<grid, kThreads, smem, st>>>(tm, n, s0, q, C, twp, zero_dc);
+        const size_t tma_smem = (size_t)C * (1u << q) * sizeof(V2) + 128;
+        if (!ctx->generic_only && C * sizeof(V2) >= 16 && tma_smem <= (size_t)ctx->smem_optin &&
+            make_tail_tmap<T>(&tm, d_spec, n, s0, q, C, batch)) {
+            const bool one_per_sm = tma_smem > (size_t)ctx->smem_optin / 2;
+            const int nt = one_per_sm ? std::max(tune.nt, 512) : tune.nt;
+            if (nt >= 1024) APDA_TRY((launch_tail_tma<T, 1024, 1>(st, grid, tma_smem, tm, n, s0, q, C, twp, zero_dc)));
+            else if (nt >= 512 && (one_per_sm || tune.minb <= 1)) APDA_TRY((launch_tail_tma<T, 512, 1>(st, grid, tma_smem, tm, n, s0, q, C, twp, zero_dc)));
+            else if (nt >= 512 && tune.minb == 2) APDA_TRY((launch_tail_tma<T, 512, 2>(st, grid, tma_smem, tm, n, s0, q, C, twp, zero_dc)));
+            else if (nt >= 512) APDA_TRY((launch_tail_tma<T, 512, 3>(st, grid, tma_smem, tm, n, s0, q, C, twp, zero_dc)));
+            else if (tune.minb <= 2) APDA_TRY((launch_tail_tma<T, 256, 2>(st, grid, tma_smem, tm, n, s0, q, C, twp, zero_dc)));
+            else APDA_TRY((launch_tail_tma<T, 256, 3>(st, grid, tma_smem, tm, n, s0, q, C, twp, zero_dc)));
         } else {
             const size_t smem = (size_t)(C + 1) * (1u << q) * sizeof(V2);
+            if (smem > (size_t)ctx->smem_optin) {
+                apda_set_error("fft_large: tile of 2^%d x %d does not fit shared memory", q, C);
+                return APDA_ERR_UNSUPPORTED;
+            }
             APDA_CUDA(cudaFuncSetAttribute(large_tail_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             large_tail_kernel<T><<<grid, kThreads, smem, st>>>(reinterpret_cast<V2 *>(d_spec), n, s0, q, C, twp, zero_dc);
         }
