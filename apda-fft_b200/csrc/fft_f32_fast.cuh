@@ -193,35 +193,56 @@ __device__ float select_median(const float2 (&v2)[16], int n_valid, uint32_t *sh
     const int r_lo = (n_valid - 1) >> 1, r_hi = n_valid >> 1;  // 0-based ranks of the two middle order statistics
     float *shf = reinterpret_cast<float *>(sh);
 
-    // mean and standard deviation only steer the first two pivots: warp 0's quarter of the window (every 4th block of
-    // 64 samples) is a good enough estimate, the other warps skip the pass
-    if (warp == 0) {
+    // Shared-memory words: [0, 32) the survivors of the final gather (first the per-warp partial sums of the prologue,
+    // or the even-n temporaries: never live at the same time), [32, 48) two banks of per-warp round counts, 48 the gather
+    // counter, 49 the result.
+    //
+    // Mean and standard deviation only steer the first two pivots: every thread contributes 8 of its 32 values (slots
+    // 0, 4, 8, 12: samples spread over the whole window), every warp reduces its own share, and all threads combine the
+    // NW partial sums after ONE barrier - no warp idles while another one prepares the estimate.
+    {
         float s1 = 0.f, s2 = 0.f;
         int cntv = 0;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const bool ok = FULL || VAL(i) < CUDART_INF_F;
-            const float x = ok ? VAL(i) : 0.f;
-            s1 += x;
-            s2 = fmaf(x, x, s2);
-            cntv += ok;
+        for (int c = 0; c < 16; c += 4) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float raw = h ? v2[c].y : v2[c].x;
+                const bool ok = FULL || raw < CUDART_INF_F;
+                const float x = ok ? raw : 0.f;
+                s1 += x;
+                s2 = fmaf(x, x, s2);
+                cntv += ok;
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             s1 += __shfl_xor_sync(0xffffffffu, s1, o);
             s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-            cntv += __shfl_xor_sync(0xffffffffu, cntv, o);
         }
+        if (!FULL) cntv = __reduce_add_sync(0xffffffffu, cntv);
         if (lane == 0) {
-            const float nv = (float)max(cntv, 1);
-            const float m = s1 / nv;
-            shf[0] = m;
-            shf[1] = sqrtf(fmaxf(s2 / nv - m * m, 0.f));
+            shf[warp] = s1;
+            shf[8 + warp] = s2;
+            if (!FULL) sh[16 + warp] = (uint32_t)cntv;
         }
+        if (t == 0) sh[48] = 0;  // gather counter, used after the last round
     }
     group_sync<T>(slot);
-    const float mean = shf[0], sd = shf[1];
-    group_sync<T>(slot);
+    float mean, sd;
+    {
+        float s1 = 0.f, s2 = 0.f;
+        int cntv = FULL ? 8 * T : 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            s1 += shf[w];
+            s2 += shf[8 + w];
+            if (!FULL) cntv += (int)sh[16 + w];
+        }
+        const float inv = 1.f / (float)max(cntv, 1);
+        mean = s1 * inv;
+        sd = sqrtf(fmaxf(fmaf(-mean, mean, s2 * inv), 0.f));
+    }
     const float density = (float)n_valid / fmaxf(2.5f * sd, 1e-30f);  // values per unit near the centre
 
     float lo = -CUDART_INF_F, hi = CUDART_INF_F;  // bracket [lo, hi): c_lo = #(v < lo) <= r_lo, c_hi = #(v < hi) > r_hi
@@ -267,7 +288,7 @@ __device__ float select_median(const float2 (&v2)[16], int n_valid, uint32_t *sh
         int cnt = __popc(signs);
         cnt = __reduce_add_sync(0xffffffffu, cnt);  // REDUX: one instruction instead of a shuffle tree
         // one barrier per round: the per-warp partial counts alternate between two banks of slots
-        uint32_t *cslot = sh + 40 + 8 * (round & 1);
+        uint32_t *cslot = sh + 32 + 8 * (round & 1);
         if (lane == 0) cslot[warp] = (uint32_t)cnt;
         group_sync<T>(slot);
         int tot = 0;
@@ -308,26 +329,25 @@ __device__ float select_median(const float2 (&v2)[16], int n_valid, uint32_t *sh
             return (below + above) * 0.5f;
         }
     }
-    // <= 32 values in [lo, hi), or one distinct value: gather and rank inside each warp (every warp computes the same)
-    if (t == 0) sh[16] = 0;
-    group_sync<T>(slot);
+    // <= 32 values in [lo, hi), or one distinct value: gather (the counter was zeroed in the prologue; the list area
+    // [0, 32) was last read before the first round's barrier) and rank
     for (unsigned inb = ~mask_lo & mask_hi; inb; ) {  // at most 32 bits in the whole window (or one repeated value)
         const int q = __clz(inb);
         inb &= ~(0x80000000u >> q);
-        const uint32_t pos = atomicAdd(&sh[16], 1u);
-        if (pos < 32u) shf[32 + pos] = reload(q);
+        const uint32_t pos = atomicAdd(&sh[48], 1u);
+        if (pos < 32u) shf[pos] = reload(q);
     }
     group_sync<T>(slot);
-    const int cnt = (int)sh[16];
+    const int cnt = (int)sh[48];
     if (warp == 0) {
         float med;
         if (cnt > 32) {
             med = lo;  // every value in the bracket equals lo
         } else {
-            const float mine = lane < cnt ? shf[32 + lane] : CUDART_INF_F;
+            const float mine = lane < cnt ? shf[lane] : CUDART_INF_F;
             int rank = 0;
             for (int j = 0; j < cnt; ++j) {
-                const float other = shf[32 + j];
+                const float other = shf[j];
                 rank += (other < mine) || (other == mine && j < lane);
             }
             const uint32_t m_lo = __ballot_sync(0xffffffffu, lane < cnt && rank == r_lo - c_lo);
@@ -336,12 +356,10 @@ __device__ float select_median(const float2 (&v2)[16], int n_valid, uint32_t *sh
             const float b = __shfl_sync(0xffffffffu, mine, __ffs(m_hi) - 1);
             med = (a + b) * 0.5f;
         }
-        if (lane == 0) shf[17] = med;
+        if (lane == 0) shf[49] = med;
     }
     group_sync<T>(slot);
-    const float med = shf[17];
-    group_sync<T>(slot);
-    return med;
+    return shf[49];  // nothing writes these words again before the window is done
 }
 #undef VAL
 

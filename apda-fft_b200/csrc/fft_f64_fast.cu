@@ -41,16 +41,22 @@ __device__ __forceinline__ int pad16(int idx) { return idx + (idx >> 4); }
 
 // exact statistics.median of the window; every thread holds 16 of its values (invalid slots: +inf)
 template <int T>
-__device__ double select_median_f64(const double (&val)[16], int n_valid, double *shd /* 64 doubles */, int tid) {
+__device__ double select_median_f64(const double (&val)[16], int n_valid, double *shd /* 72 doubles */, int tid) {
     constexpr int NW = T / 32 > 0 ? T / 32 : 1;
     const int lane = tid & 31, warp = tid >> 5;
     const int r_lo = (n_valid - 1) >> 1, r_hi = n_valid >> 1;
     unsigned *shu = reinterpret_cast<unsigned *>(shd + 48);
-    if (warp == 0) {
+    // mean / standard deviation only steer the first two pivots: every thread contributes 4 of its 16 values, every warp
+    // reduces its share and all threads combine the partial sums after one barrier (no warp idles during the estimate).
+    // shd: [2, 34) gather list (first: partial sums / even-n temporaries), 40 result, 41 gather counter, [48, 64) the two
+    // banks of per-warp round counts, [64, 72) the warps' valid-sample counts of the prologue
+    unsigned *gather_cnt = reinterpret_cast<unsigned *>(shd + 41);
+    unsigned *cnt_part = reinterpret_cast<unsigned *>(shd + 64);
+    {
         double s1 = 0.0, s2 = 0.0;
         int cv = 0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 16; i += 4) {
             const bool ok = val[i] < CUDART_INF;
             const double x = ok ? val[i] : 0.0;
             s1 += x;
@@ -61,17 +67,30 @@ __device__ double select_median_f64(const double (&val)[16], int n_valid, double
         for (int o = 16; o > 0; o >>= 1) {
             s1 += __shfl_xor_sync(0xffffffffu, s1, o);
             s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-            cv += __shfl_xor_sync(0xffffffffu, cv, o);
         }
+        cv = __reduce_add_sync(0xffffffffu, cv);
         if (lane == 0) {
-            const double nv = (double)max(cv, 1), m = s1 / nv;
-            shd[0] = m;
-            shd[1] = sqrt(fmax(s2 / nv - m * m, 0.0));
+            shd[2 + warp] = s1;
+            shd[2 + 16 + warp] = s2;
+            cnt_part[warp] = (unsigned)cv;
         }
+        if (tid == 0) *gather_cnt = 0;
     }
     __syncthreads();
-    const double mean = shd[0], sd = shd[1];
-    __syncthreads();
+    double mean, sd;
+    {
+        double s1 = 0.0, s2 = 0.0;
+        int cv = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            s1 += shd[2 + w];
+            s2 += shd[2 + 16 + w];
+            cv += (int)cnt_part[w];
+        }
+        const double nv = (double)max(cv, 1);
+        mean = s1 / nv;
+        sd = sqrt(fmax(s2 / nv - mean * mean, 0.0));
+    }
     const double density = (double)n_valid / fmax(2.5 * sd, 1e-300);
     double lo = -CUDART_INF, hi = CUDART_INF;  // bracket [lo, hi): c_lo = #(v < lo) <= r_lo, c_hi = #(v < hi) > r_hi
     int c_lo = 0, c_hi = n_valid;
@@ -141,11 +160,8 @@ __device__ double select_median_f64(const double (&val)[16], int n_valid, double
             return div_rn(add_rn(below, above), 2.0);
         }
     }
-    unsigned *gather_cnt = reinterpret_cast<unsigned *>(shd + 41);
-    if (tid == 0) *gather_cnt = 0;
-    __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < 16; ++i) {  // the counter was zeroed in the prologue; the list area was last read before round 0's barrier
         if (val[i] >= lo && val[i] < hi) {
             const unsigned pos = atomicAdd(gather_cnt, 1u);
             if (pos < 32u) shd[2 + pos] = val[i];
@@ -173,9 +189,7 @@ __device__ double select_median_f64(const double (&val)[16], int n_valid, double
         if (lane == 0) shd[40] = med;
     }
     __syncthreads();
-    const double med = shd[40];
-    __syncthreads();
-    return med;
+    return shd[40];  // nothing writes this word again before the window is done
 }
 
 // q radix-2 stages on 2^q register values of one work item (stride 2^s0, low index bits `lo`)
@@ -230,7 +244,7 @@ fft_f64_fast_kernel(const double *__restrict__ samples, int n_samples, int64_t l
     using PL = Plan64<LOGN>;
     constexpr int N = PL::N, T = PL::T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ double shd[64];
+    __shared__ double shd[72];
     double2 *s = reinterpret_cast<double2 *>(smem_raw);
     double *raw = reinterpret_cast<double *>(smem_raw);  // staging of the real samples (padded by i>>3), aliases s
     const int t = threadIdx.x;

@@ -919,7 +919,7 @@ template <typename T>
 static K2Tune k2_tune() {
     static const K2Tune t = [] {
         K2Tune d;
-        d.qmax = sizeof(T) == 8 ? 10 : 11;
+        d.qmax = 10;  // fp32 could hold 2^11-row tiles, but 2^22 runs 22 % faster as (8, 7, 7) than as (11, 11)
         d.max_tile = sizeof(T) == 8 ? 4096 : 8192;  // 64 KB tiles
         d.nt = sizeof(T) == 8 ? 256 : 512;
         d.minb = 3;
