@@ -193,6 +193,39 @@ __device__ __forceinline__ double magnitude(double re, double im) {
 }
 __device__ __forceinline__ float magnitude(float re, float im) { return sqrtf(fmaf(re, re, im * im)); }
 
+// Blackwell packed fp32 arithmetic (FADD2 / FMUL2 / FFMA2): one instruction per (re, im) pair.  ptxas folds a pair made of
+// one register twice, (a, a), into the scalar-broadcast operand form, so a complex product is two packed instructions.
+__device__ __forceinline__ unsigned long long f2bits(float2 v) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y));
+    return r;
+}
+__device__ __forceinline__ float2 f2from(unsigned long long b) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(b));
+    return r;
+}
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2bits(a)), "l"(f2bits(b)));
+    return f2from(r);
+}
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2bits(a)), "l"(f2bits(b)));
+    return f2from(r);
+}
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2bits(a)), "l"(f2bits(b)));
+    return f2from(r);
+}
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2bits(a)), "l"(f2bits(b)), "l"(f2bits(c)));
+    return f2from(r);
+}
+
 // order-preserving integer keys of IEEE values (radix select)
 __device__ __forceinline__ uint64_t ordered_key(double v) {
     uint64_t b = (uint64_t)__double_as_longlong(v);

@@ -43,11 +43,21 @@ __device__ __forceinline__ void butterfly(typename vec2<T>::type &u, typename ve
     v = b;
 }
 
+// fp32 butterfly (tolerance path, not bit-exact): packed arithmetic, the product v*w as two packed instructions
+//   v*w = v.x * (w.x, w.y) + v.y * (-w.y, w.x);   wr = (-w.y, w.x) is prepared once per twiddle
+__device__ __forceinline__ void butterfly_f32(float2 &u, float2 &v, const float2 w, const float2 wr) {
+    const float2 vw = f2fma(make_float2(v.y, v.y), wr, f2mul(make_float2(v.x, v.x), w));
+    const float2 a = f2add(u, vw), b = f2sub(u, vw);
+    u = a;
+    v = b;
+}
+
 // QR radix-2 stages (t0+1 .. t0+QR of this pass) on 2^QR register-resident values per work item: one shared-memory round
 // trip and one barrier per QR stages instead of per stage, 2^QR - 1 twiddle loads per QR * 2^(QR-1) butterflies.
 // Element (row r, column c) of the pass's working set lives at tile[r * rs + c * cs]; rows r = (hi << (t0+QR)) + (k << t0) + jr.
 // Twiddle of stage t for row r: T_{s0+t}[((r mod 2^(t-1)) << s0) + lo0 + c]  (head pass: s0 = 0 and no column term - its
-// columns are independent sub-transforms).  Same dataflow graph and individually rounded operations as before.
+// columns are independent sub-transforms).  fp64: the reference's dataflow graph with individually rounded operations
+// (bit-exact); fp32: the same graph with packed arithmetic.
 template <typename T, int QR, bool HEAD, int NT>
 __device__ __forceinline__ void stage_round(typename vec2<T>::type *tile, int rs, int cs, int logC, int q, int t0,
                                             const typename vec2<T>::type *__restrict__ tw, int s0, int64_t lo0, int tid) {
@@ -69,26 +79,41 @@ __device__ __forceinline__ void stage_round(typename vec2<T>::type *tile, int rs
             V2 w[R / 2];
 #pragma unroll
             for (int m = 0; m < (1 << (u - 1)); ++m) w[m] = __ldg(tab + ((int64_t)(jr + (m << t0)) << s0));
+            if constexpr (sizeof(T) == 4) {
+                V2 wr[R / 2];
 #pragma unroll
-            for (int k = 0; k < R; ++k)
-                if ((k & (1 << (u - 1))) == 0) butterfly<T>(v[k], v[k + (1 << (u - 1))], w[k & ((1 << (u - 1)) - 1)]);
+                for (int m = 0; m < (1 << (u - 1)); ++m) wr[m] = make_float2(-w[m].y, w[m].x);
+#pragma unroll
+                for (int k = 0; k < R; ++k)
+                    if ((k & (1 << (u - 1))) == 0)
+                        butterfly_f32(v[k], v[k + (1 << (u - 1))], w[k & ((1 << (u - 1)) - 1)], wr[k & ((1 << (u - 1)) - 1)]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < R; ++k)
+                    if ((k & (1 << (u - 1))) == 0) butterfly<T>(v[k], v[k + (1 << (u - 1))], w[k & ((1 << (u - 1)) - 1)]);
+            }
         }
 #pragma unroll
         for (int k = 0; k < R; ++k) p[k * kstride] = v[k];
     }
 }
 
-// all q stages of a pass, three at a time (the remainder as 2+2, 2 or 1), one barrier per round
+// all q stages of a pass in ceil(q / QMAX) rounds of nearly equal size (QMAX = 3 stages on 8 values per thread in fp64,
+// 4 stages on 16 values in fp32, where the registers allow it), one barrier per round
 template <typename T, bool HEAD, int NT>
 __device__ __forceinline__ void run_stages(typename vec2<T>::type *tile, int rs, int cs, int logC, int q,
                                            const typename vec2<T>::type *__restrict__ tw, int s0, int64_t lo0, int tid) {
+    constexpr int QMAX = sizeof(T) == 4 ? 4 : 3;
+    const int rounds = (q + QMAX - 1) / QMAX, base = q / rounds, rem = q % rounds;
     int t0 = 0;
-    while (t0 < q) {
-        const int left = q - t0;
-        const int qr = left > 4 ? 3 : (left == 4 ? 2 : left);
+    for (int r = 0; r < rounds; ++r) {
+        const int qr = base + (r < rem ? 1 : 0);
+        if constexpr (sizeof(T) == 4) {
+            if (qr == 4) stage_round<T, 4, HEAD, NT>(tile, rs, cs, logC, q, t0, tw, s0, lo0, tid);
+        }
         if (qr == 3) stage_round<T, 3, HEAD, NT>(tile, rs, cs, logC, q, t0, tw, s0, lo0, tid);
         else if (qr == 2) stage_round<T, 2, HEAD, NT>(tile, rs, cs, logC, q, t0, tw, s0, lo0, tid);
-        else stage_round<T, 1, HEAD, NT>(tile, rs, cs, logC, q, t0, tw, s0, lo0, tid);
+        else if (qr == 1) stage_round<T, 1, HEAD, NT>(tile, rs, cs, logC, q, t0, tw, s0, lo0, tid);
         __syncthreads();
         t0 += qr;
     }
@@ -240,7 +265,9 @@ large_tail_tma_kernel(const __grid_constant__ CUtensorMap tmap, int n, int s0, i
                          : "memory");
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        // the CTA may retire as soon as the bulk store has READ the tile out of shared memory (its slot can then be handed to
+        // the next tile); the global writes themselves complete before the kernel does
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
 }
 
@@ -921,7 +948,7 @@ static K2Tune k2_tune() {
         K2Tune d;
         d.qmax = 10;  // fp32 could hold 2^11-row tiles, but 2^22 runs 22 % faster as (8, 7, 7) than as (11, 11)
         d.max_tile = sizeof(T) == 8 ? 4096 : 8192;  // 64 KB tiles
-        d.nt = sizeof(T) == 8 ? 256 : 512;
+        d.nt = 256;  // 3 CTAs x 256 threads leave 85 registers per thread: 8 complex fp64 / 16 complex fp32 values in flight
         d.minb = 3;
         const char *sfx = sizeof(T) == 8 ? "64" : "32";
         char name[32];
@@ -1000,13 +1027,15 @@ int launch_fft_large(apda_ctx *ctx, cudaStream_t st, const T *d_samples, int64_t
         const size_t smem = (size_t)C * ((1u << q) + 1) * sizeof(V2);
         dim3 grid((unsigned)(cols / C), (unsigned)batch);
         V2 *spec = reinterpret_cast<V2 *>(d_spec);
-        const int hnt = smem > (96u << 10) ? 1024 : 512;  // a tile that leaves room for one CTA per SM gets the most threads
+        // a tile that leaves room for one CTA per SM gets the most threads; otherwise 256 threads, so that three CTAs per
+        // SM fit the register file (74 registers in fp32: 16 complex values per thread)
+        const int hnt = smem > (96u << 10) ? 1024 : 256;
         if (complex_input) {
             if (hnt == 1024) APDA_TRY((launch_head<T, true, 1024>(st, grid, smem, d_samples, n_samples, ld, n, q, C, twp, spec, d_med)));
-            else APDA_TRY((launch_head<T, true, 512>(st, grid, smem, d_samples, n_samples, ld, n, q, C, twp, spec, d_med)));
+            else APDA_TRY((launch_head<T, true, 256>(st, grid, smem, d_samples, n_samples, ld, n, q, C, twp, spec, d_med)));
         } else {
             if (hnt == 1024) APDA_TRY((launch_head<T, false, 1024>(st, grid, smem, d_samples, n_samples, ld, n, q, C, twp, spec, d_med)));
-            else APDA_TRY((launch_head<T, false, 512>(st, grid, smem, d_samples, n_samples, ld, n, q, C, twp, spec, d_med)));
+            else APDA_TRY((launch_head<T, false, 256>(st, grid, smem, d_samples, n_samples, ld, n, q, C, twp, spec, d_med)));
         }
         ctx->launches++;
         APDA_CUDA(cudaGetLastError());

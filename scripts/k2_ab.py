@@ -19,16 +19,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 VARIANTS = {
-    "r1 (512 thr, f64 1 CTA/SM)": {"APDA_K2_NT64": "512", "APDA_K2_MINB64": "1"},
     "default": {},
-    "f32 q8 64KB": {"APDA_K2_QMAX32": "8"},
-    "f32 q9 64KB": {"APDA_K2_QMAX32": "9"},
-    "f32 q9 32KB": {"APDA_K2_QMAX32": "9", "APDA_K2_TILE32": "4096"},
-    "f32 q10 64KB": {"APDA_K2_QMAX32": "10"},
-    "f64 q9 64KB": {"APDA_K2_QMAX64": "9"},
-    "f64 q7 64KB": {"APDA_K2_QMAX64": "7"},
-    "f64 q8 32KB": {"APDA_K2_QMAX64": "8", "APDA_K2_TILE64": "2048"},
-    "f64 q12 128KB": {"APDA_K2_QMAX64": "12", "APDA_K2_TILE64": "8192"},
+    "f64 512x1 (round 1)": {"APDA_K2_NT64": "512", "APDA_K2_MINB64": "1"},
+    "f32 256x2": {"APDA_K2_MINB32": "2"},
+    "f32 512x2": {"APDA_K2_NT32": "512", "APDA_K2_MINB32": "2"},
+    "f32 q8": {"APDA_K2_QMAX32": "8"},
+    "f32 q11": {"APDA_K2_QMAX32": "11"},
+    "f32 q12 128KB": {"APDA_K2_QMAX32": "12", "APDA_K2_TILE32": "16384"},
 }
 
 
