@@ -1,8 +1,9 @@
 // Fused window -> record kernel (fp32, N = 1024..8192): SURVEY 8(f) rank 1, the "B_min" variant.
 //
 // K1-fast's three register passes, then the split step keeps only the half spectrum the pickers read: bins k < N/2 go
-// straight from registers to magnitudes in shared memory (K3-fast's padded layout) and the window's Sum / Sum-of-squares
-// are reduced across the CTA; warp 0 then runs K3-fast's tail (hot list, picker, record).  HBM traffic per window is
+// straight from registers to magnitudes in shared memory and the window's Sum / Sum-of-squares are reduced across the
+// CTA; the picker tail then runs on ALL the CTA's warps (k3_tail_mw in peaks_fast.cuh: a 16-bin chunk per thread, the
+// candidates' prominence walks dealt out to the warps), so no FFT warp idles while the record is being made.  HBM traffic per window is
 // s*N bytes in and 128 bytes out (16 512 B at N = 4096) instead of the pipeline's 4*s*N + 128: the spectrum never exists
 // in memory.  This is a throughput variant: the drop-in start_fft contract (N bins materialised) stays with the
 // pipeline kernels, and results are reported under their own byte accounting (never mixed with B_alg numbers).
@@ -15,32 +16,42 @@ int fft_f32_fast_get_tables(apda_ctx *ctx, int64_t N, const float2 **tw1, const 
 
 namespace {
 
+template <int N>
+struct FusedLayout {
+    using P = Plan<N>;
+    static constexpr int M = N / 2, T = M / 16;
+    static constexpr int FFT_BYTES = (int)sizeof(float2) * P::R1 * (P::R2 * P::R3 + 16 / P::R1);
+    static constexpr int MAG_BYTES = K3M<M>::MAGW * (int)sizeof(float);
+    static constexpr int BYTES = FFT_BYTES + MAG_BYTES + 128;
+    static constexpr int SLOT_CAP = M / 5 + 8;  // bins above mean + 2 sigma are < 20 % of all bins: never overflows
+    // the FFT buffer is free once the magnitudes exist: chunk summaries and the slot list live there
+    static_assert(2 * T * (int)sizeof(float) + SLOT_CAP * (int)sizeof(Slot) <= FFT_BYTES, "tail scratch must fit the FFT buffer");
+};
+
 template <int N, int CENTER, bool FULL, bool FLEX>
 __global__ void __launch_bounds__(N / 32, (N == 4096 ? 8 : N < 4096 ? 1024 / (N / 32) / 2 : 2))
 fused_f32_kernel(const float *__restrict__ samples, int n_samples, int64_t ld, int64_t batch,
                  const float2 *__restrict__ tw1, const float2 *__restrict__ twu, double df_all,
-                 const double *__restrict__ d_fs, int k, unsigned char *__restrict__ recs, int *__restrict__ repair) {
-    using P = Plan<N>;
-    using Q = K3<float, N / 2>;
-    constexpr int M = N / 2, R1 = P::R1, R2 = P::R2, R3 = P::R3, T = M / 16;
-    constexpr int S1 = R2 * R3, LD = S1 + 16 / R1;
-    extern __shared__ __align__(16) unsigned char dyn_smem[];  // FFT buffer, then K3's per-window region
+                 const double *__restrict__ d_fs, int k, unsigned char *__restrict__ recs) {
+    using L = FusedLayout<N>;
+    using Q = K3M<N / 2>;
+    constexpr int M = N / 2, T = M / 16;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];  // FFT buffer, magnitudes, record
     float2 *s = reinterpret_cast<float2 *>(dyn_smem);
-    unsigned char *k3mem = dyn_smem + sizeof(float2) * R1 * LD;
+    float *mags = reinterpret_cast<float *>(dyn_smem + L::FFT_BYTES);
+    unsigned char *rec_s = dyn_smem + L::FFT_BYTES + L::MAG_BYTES;
     __shared__ uint32_t sel[64];
     __shared__ float red[8];
     __shared__ double stat[2 * (T / 32 > 0 ? T / 32 : 1)];
-    __shared__ int nslot_s;
+    __shared__ int ctl[2];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int64_t win = blockIdx.x;
     if (win >= batch) return;
+    if (t == 0) ctl[0] = ctl[1] = 0;  // slot count, tie flag (published by the barriers inside k1_forward)
 
     k1_forward<N, CENTER, FULL>(samples, n_samples, ld, win, tw1, s, sel, red, 0, t);
 
-    // split step, lower half only: X[k] = S/2 + Wt*D for k = 2p, 2p+1 -> magnitudes in K3's shared-memory layout
-    float *mags = reinterpret_cast<float *>(k3mem);
-    unsigned char *rec_s = k3mem + Q::REC_OFF;
-    if (t == 0) nslot_s = 0;
+    // split step, lower half only: X[k] = S/2 + Wt*D for k = 2p, 2p+1 -> magnitudes in the tail's shared-memory layout
     if (t < 16) reinterpret_cast<uint64_t *>(rec_s)[t] = (t % 3 == 1) ? 0x00000000ffffffffull : 0ull;
     const float4 *s4 = reinterpret_cast<const float4 *>(s);
     const float4 *twu4 = reinterpret_cast<const float4 *>(twu);
@@ -77,8 +88,7 @@ fused_f32_kernel(const float *__restrict__ samples, int n_samples, int64_t ld, i
         stat[warp] = S;
         stat[NW + warp] = Qs;
     }
-    group_sync<T>(0);
-    if (warp != 0) return;  // the picker tail is a one-warp job
+    group_sync<T>(0);  // magnitudes and partial sums complete; the FFT buffer is free
     S = 0.0;
     Qs = 0.0;
 #pragma unroll
@@ -93,12 +103,9 @@ fused_f32_kernel(const float *__restrict__ samples, int n_samples, int64_t ld, i
     const double thr = mean + 2.0 * sd;
     const float thr_f = __double2float_rd(thr);
     const double df = d_fs ? div_rn(d_fs[win], (double)N) : df_all;
-    // the FFT buffer is free now (every warp passed the barrier above): it holds the slot list, sized for the worst case
-    // (bins above mean + 2 sigma are < 20 % of all bins), so the fused kernel never needs the repair path
-    Slot *slots = reinterpret_cast<Slot *>(s);
-    constexpr int kSlotCap = M / 5 + 8;
-    static_assert(kSlotCap * sizeof(Slot) <= sizeof(float2) * R1 * LD, "slot list must fit the FFT buffer");
-    k3_tail<float, M, FLEX>(mags, slots, kSlotCap, rec_s, &nslot_s, sd, thr_f, df, k, lane, win, recs, repair);
+    float *cmaxs = reinterpret_cast<float *>(s), *cmins = cmaxs + T;
+    Slot *slots = reinterpret_cast<Slot *>(cmins + T);
+    k3_tail_mw<M, FLEX, T>(mags, cmaxs, cmins, slots, L::SLOT_CAP, ctl, rec_s, sd, thr_f, df, k, t, win, recs);
 }
 
 // this translation unit owns its own copy of the __constant__ pass-2 twiddles (anonymous namespace in the header)
@@ -132,12 +139,10 @@ int launch_fused_n(apda_ctx *ctx, cudaStream_t st, const float *d_samples, int64
     const float2 *tw1, *twu;
     APDA_TRY(fft_f32_fast_get_tables(ctx, N, &tw1, &twu));
     APDA_TRY(upload_tw2<N>(ctx->device));
-    int *repair = nullptr;  // never appended to (the slot list is sized for the worst case); k3_tail wants a valid pointer
-    APDA_TRY(apda_repair_list(ctx, st, batch, &repair));
     const bool full = n_samples == N && (reinterpret_cast<uintptr_t>(d_samples) & 7u) == 0 && (ld & 1) == 0;
     const bool med = flags == APDA_CENTER_MEDIAN;
     void (*kern)(const float *, int, int64_t, int64_t, const float2 *, const float2 *, double, const double *, int,
-                 unsigned char *, int *);
+                 unsigned char *);
 #define PICK(C, F, X) fused_f32_kernel<N, C, F, X>
     if (flexible) {
         kern = med ? (full ? PICK(APDA_CENTER_MEDIAN, true, true) : PICK(APDA_CENTER_MEDIAN, false, true))
@@ -147,11 +152,10 @@ int launch_fused_n(apda_ctx *ctx, cudaStream_t st, const float *d_samples, int64
                    : (full ? PICK(APDA_CENTER_MEAN, true, false) : PICK(APDA_CENTER_MEAN, false, false));
     }
 #undef PICK
-    using P = Plan<N>;
-    const size_t smem = sizeof(float2) * P::R1 * (P::R2 * P::R3 + 16 / P::R1) + K3<float, N / 2>::BYTES;
+    const size_t smem = FusedLayout<N>::BYTES;
     APDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)batch, N / 32, smem, st>>>(d_samples, (int)n_samples, ld, batch, tw1, twu, fs / (double)N, d_fs, k,
-                                            reinterpret_cast<unsigned char *>(d_rec), repair);
+                                            reinterpret_cast<unsigned char *>(d_rec));
     ctx->launches++;
     APDA_CUDA(cudaGetLastError());
     return APDA_OK;

@@ -192,39 +192,38 @@ __device__ T coop_prominence(const T *mags, int j, T cmax, T cmin, int lane) {
     return sub_rn(p, vmax(fl, fr));
 }
 
-template <typename T, int HALF>
+template <typename T, int HALF, typename P = K3<T, HALF>>
 __device__ __forceinline__ int half_power_bins_f(const T *mags, T prom, int j) {
-    const T top = mags[K3<T, HALF>::addr(j)];
+    const T top = mags[P::addr(j)];
     const T level = add_rn(sub_rn(top, prom), mul_rn(prom, (T)0.707));
     int lo = j;
-    while (lo > 0 && mags[K3<T, HALF>::addr(lo)] > level) {
-        if (mags[K3<T, HALF>::addr(lo)] > top) break;
+    while (lo > 0 && mags[P::addr(lo)] > level) {
+        if (mags[P::addr(lo)] > top) break;
         --lo;
     }
     int hi = j;
-    while (hi < HALF - 1 && mags[K3<T, HALF>::addr(hi)] > level) {
-        if (mags[K3<T, HALF>::addr(hi)] > top) break;
+    while (hi < HALF - 1 && mags[P::addr(hi)] > level) {
+        if (mags[P::addr(hi)] > top) break;
         ++hi;
     }
     const int w = hi - lo;
     return w > 1 ? w : 1;
 }
 
-template <typename T, int HALF>
+template <typename T, int HALF, typename P = K3<T, HALF>>
 __device__ __forceinline__ int half_height_bins_f(const T *mags, int j) {
-    const T level = mul_rn((T)0.707, mags[K3<T, HALF>::addr(j)]);
+    const T level = mul_rn((T)0.707, mags[P::addr(j)]);
     int lo = j;
-    while (lo > 0 && mags[K3<T, HALF>::addr(lo)] > level) --lo;
+    while (lo > 0 && mags[P::addr(lo)] > level) --lo;
     int hi = j;
-    while (hi < HALF && mags[K3<T, HALF>::addr(hi)] > level) ++hi;
+    while (hi < HALF && mags[P::addr(hi)] > level) ++hi;
     return hi - lo;
 }
 
 // width_half_magnitude with the whole warp (all lanes call it with the same j): 32 bins per side and step instead of a
 // serial walk - same result as half_height_bins_f (utils/get_peak_resolution.py:30-44)
-template <typename T, int HALF>
+template <typename T, int HALF, typename P = K3<T, HALF>>
 __device__ __forceinline__ int half_height_bins_warp(const T *mags, int j, int lane) {
-    using P = K3<T, HALF>;
     const T level = mul_rn((T)0.707, mags[P::addr(j)]);
     int lo = 0, hi = HALF;
     for (int base = j; base > 0; base -= 32) {  // left = first i <= j with mags[i] <= level, else 0 (bin 0 is never tested)
@@ -249,10 +248,9 @@ __device__ __forceinline__ int half_height_bins_warp(const T *mags, int j, int l
 // The reference sorts the gated candidates by round(mag, 4) descending (stable: ties keep ascending idx) and walks that
 // order with the greedy "hump" exclusion.  Each lane owns PER slots; a slot's place in the order is its rank (number of
 // passing slots that precede it), computed once with shuffles.  Accepted peaks go straight into the record.
-template <typename T, int HALF, int PER>
+template <typename T, int HALF, int PER, typename P = K3<T, HALF>>
 __device__ __forceinline__ int order_and_exclude(const SlotT<T> *slots, int nslot, const T *mags, unsigned char *rec_s,
                                                  double df, int k, int lane) {
-    using P = K3<T, HALF>;
     // each lane owns PER slots; the order is extracted one element at a time with a warp arg-max (REDUX on the key's
     // words: largest round(mag, 4), ties -> lowest idx), at most k + rejected times
     double key[PER];
@@ -315,10 +313,9 @@ __device__ __forceinline__ int order_and_exclude(const SlotT<T> *slots, int nslo
 
 // Same order / exclusion for any number of slots (only reached with > 96 gated candidates, i.e. noise-like windows in
 // the fused kernel, whose slot list lives in the free FFT buffer): extract the order one element at a time.
-template <typename T, int HALF>
+template <typename T, int HALF, typename P = K3<T, HALF>>
 __device__ int order_and_exclude_any(const SlotT<T> *slots, int nslot, const T *mags, unsigned char *rec_s, double df,
                                      int k, int lane) {
-    using P = K3<T, HALF>;
     double prev_key = CUDART_INF;
     int prev_idx = -1, na = 0;
     while (na < k) {
@@ -372,8 +369,105 @@ __device__ int order_and_exclude_any(const SlotT<T> *slots, int nslot, const T *
     return na;
 }
 
-// Everything after the magnitudes are in shared memory: hot-bin list, picker, record.  Shared by the pipeline kernel
-// (peaks_f32_fast.cu) and the fused window->record kernel (fused_f32.cu).  Runs on ONE warp.
+// Damping / width gates of one flexible-picker candidate (utils/get_peak_prominence.py:177-186): returns the half-power
+// width in bins if the candidate passes every gate, else 0.
+template <typename T, int HALF, typename P>
+__device__ __forceinline__ int k3_gate(const T *mags, int j, T prom, double half_sd, double df) {
+    if (!((double)prom > half_sd)) return 0;
+    const int bins = half_power_bins_f<T, HALF, P>(mags, prom, j);
+    const double width_hz = mul_rn((double)bins, df);
+    if (!(width_hz > 0.0)) return 0;
+    const double fn = mul_rn((double)j, df);
+    // 0.001 <= 1/(2*(fn/width_hz)) <= 0.07, decided by products unless within 1e-12 of a bound
+    const double lo_b = 0.002 * fn, hi_b = 0.14 * fn;
+    if (width_hz >= lo_b * (1.0 + 1e-12) && width_hz <= hi_b * (1.0 - 1e-12)) return bins;
+    if (!(width_hz < lo_b * (1.0 - 1e-12) || width_hz > hi_b * (1.0 + 1e-12))) {
+        const double q = div_rn(fn, width_hz);
+        const double damping = div_rn(1.0, mul_rn(2.0, q));
+        if (0.001 <= damping && damping <= 0.07) return bins;
+    }
+    return 0;
+}
+
+// Rigid picker on the hot list (utils/get_peak_resolution.py:94-126), one warp; returns the number of accepted peaks and
+// writes them into the record under construction.  Zeroes magnitudes in shared memory as the reference does.
+template <typename T, int HALF, typename P>
+__device__ __forceinline__ int k3_rigid(T *mags, const SlotT<T> *slots, int nslot, T thr_f, double df, int k, int lane,
+                                        unsigned char *rec_s) {
+    const double distance = sub_rn(mul_rn(2.0, df), mul_rn(1.0, df));
+    int acc_idx[5];
+#pragma unroll
+    for (int a = 0; a < 5; ++a) acc_idx[a] = -1;
+    int na = 0;
+    __syncwarp();
+    while (na < k) {
+        T bm = (T)-1;
+        int bj = -1;
+        for (int e = lane; e < nslot; e += 32) {
+            const int j = slots[e].idx;
+            const T m = mags[P::addr(j)];
+            if (j >= 1 && j <= HALF - 2 && m > thr_f && m > mags[P::addr(j - 1)] && m > mags[P::addr(j + 1)] &&
+                (m > bm || (m == bm && j < bj))) {
+                bm = m;
+                bj = j;
+            }
+        }
+        warp_argmax(bm, bj);
+        if (bj < 0) break;
+        const int w2 = half_height_bins_warp<T, HALF, P>(mags, bj, lane);
+        bool separated = true;
+#pragma unroll
+        for (int a = 0; a < 5; ++a) {
+            if (a < na && separated) {
+                // an accepted peak's own bin was zeroed when it was found, so its half-height width is 0 (the
+                // reference's resolution() degenerates to 1.18*dist/w_candidate); walk only if that ever fails
+                const int w1 = mags[P::addr(acc_idx[a])] == (T)0 ? 0 : half_height_bins_f<T, HALF, P>(mags, acc_idx[a]);
+                bool ok = false;
+                if (w1 + w2 != 0) {
+                    const double num = mul_rn(1.18, (double)abs(bj - acc_idx[a])), den = 1.5 * (double)(w1 + w2);
+                    if (num >= den * (1.0 + 1e-12)) ok = true;                       // rs >= 1.5 by a clear margin
+                    else if (!(num < den * (1.0 - 1e-12))) ok = div_rn(num, (double)(w1 + w2)) >= 1.5;
+                }
+                if (!ok) separated = false;
+            }
+        }
+        if (separated) {
+            if (lane == 0) {
+                unsigned char *pk = rec_s + 8 + 24 * na;
+                reinterpret_cast<int *>(pk)[0] = bj;
+                reinterpret_cast<int *>(pk)[1] = w2;
+                reinterpret_cast<double *>(pk + 8)[0] = (double)bm;
+            }
+#pragma unroll
+            for (int a = 0; a < 5; ++a)
+                if (a == na) acc_idx[a] = bj;
+            ++na;
+        }
+        // zeroing radius round((freq * 0.02) / (frequencies[2] - frequencies[1])): equals round-half-even(0.02 * idx)
+        // unless that product sits within 1e-6 of a tie; only then (or for a degenerate df) the exact expression runs
+        double reach_d;
+        {
+            const double x02 = 0.02 * (double)bj, fr = x02 - floor(x02);
+            if (df > 1e-300 && df < 1e300 && fabs(fr - 0.5) > 1e-6) {
+                reach_d = rint(x02);
+            } else {
+                const double f = mul_rn((double)bj, df);
+                reach_d = rint(div_rn(mul_rn(f, 0.02), distance));
+            }
+        }
+        if (!(reach_d >= 0.0)) reach_d = 0.0;
+        if (reach_d > (double)HALF) reach_d = (double)HALF;
+        const int reach = (int)reach_d;
+        const int z0 = max(0, bj - reach), z1 = min(HALF, bj + reach + 1);
+        __syncwarp();
+        for (int b = z0 + lane; b < z1; b += 32) mags[P::addr(b)] = (T)0;
+        __syncwarp();
+    }
+    return na;
+}
+
+// Everything after the magnitudes are in shared memory: hot-bin list, picker, record.  Shared by the pipeline kernels
+// (peaks_f32_fast.cu, peaks_f64_fast.cu).  Runs on ONE warp.
 // thr_f: largest T with  m > thr  <=>  m > thr_f  for every magnitude m (the threshold itself when T is double).
 template <typename T, int HALF, bool FLEX>
 __device__ __forceinline__ void k3_tail(T *mags, SlotT<T> *slots, const int slot_cap, unsigned char *rec_s,
@@ -443,115 +537,189 @@ __device__ __forceinline__ void k3_tail(T *mags, SlotT<T> *slots, const int slot
         __syncwarp();
         // ---- B: lane-parallel gates (one candidate per lane) ---------------------------------------------------------
         const double half_sd = mul_rn(0.5, sd);
-        for (int c = lane; c < nslot; c += 32) {
-            const int j = slots[c].idx;
-            const T prom = slots[c].prom;
-            int width = 0;
-            if ((double)prom > half_sd) {
-                const int bins = half_power_bins_f<T, HALF>(mags, prom, j);
-                const double width_hz = mul_rn((double)bins, df);
-                if (width_hz > 0.0) {
-                    const double fn = mul_rn((double)j, df);
-                    // 0.001 <= 1/(2*(fn/width_hz)) <= 0.07, decided by products unless within 1e-12 of a bound
-                    const double lo_b = 0.002 * fn, hi_b = 0.14 * fn;
-                    if (width_hz >= lo_b * (1.0 + 1e-12) && width_hz <= hi_b * (1.0 - 1e-12)) {
-                        width = bins;
-                    } else if (!(width_hz < lo_b * (1.0 - 1e-12) || width_hz > hi_b * (1.0 + 1e-12))) {
-                        const double q = div_rn(fn, width_hz);
-                        const double damping = div_rn(1.0, mul_rn(2.0, q));
-                        if (0.001 <= damping && damping <= 0.07) width = bins;
-                    }
-                }
-            }
-            slots[c].width = (uint16_t)width;
-        }
+        for (int c = lane; c < nslot; c += 32)
+            slots[c].width = (uint16_t)k3_gate<T, HALF, P>(mags, slots[c].idx, slots[c].prom, half_sd, df);
         __syncwarp();
         // ---- C: order "descending round(mag,4), ascending idx" (stable sort of the reference), greedy hump exclusion ------
         na = nslot <= 32   ? order_and_exclude<T, HALF, 1>(slots, nslot, mags, rec_s, df, k, lane)
              : nslot <= 96 ? order_and_exclude<T, HALF, 3>(slots, nslot, mags, rec_s, df, k, lane)
                            : order_and_exclude_any<T, HALF>(slots, nslot, mags, rec_s, df, k, lane);
-        if (lane == 0) {
-            reinterpret_cast<int *>(rec_s)[0] = na;
-            reinterpret_cast<int *>(rec_s)[1] = status;
-        }
     } else {
-        // ---- rigid picker on the hot list ---------------------------------------------------------------------------------
-        const double distance = sub_rn(mul_rn(2.0, df), mul_rn(1.0, df));
-        int acc_idx[5];
-#pragma unroll
-        for (int a = 0; a < 5; ++a) acc_idx[a] = -1;
-        __syncwarp();
-        while (na < k) {
-            T bm = (T)-1;
-            int bj = -1;
-            for (int e = lane; e < nslot; e += 32) {
-                const int j = slots[e].idx;
-                const T m = mags[P::addr(j)];
-                if (j >= 1 && j <= HALF - 2 && m > thr_f && m > mags[P::addr(j - 1)] && m > mags[P::addr(j + 1)] &&
-                    (m > bm || (m == bm && j < bj))) {
-                    bm = m;
-                    bj = j;
-                }
-            }
-            warp_argmax(bm, bj);
-            if (bj < 0) break;
-            const int w2 = half_height_bins_warp<T, HALF>(mags, bj, lane);
-            bool separated = true;
-#pragma unroll
-            for (int a = 0; a < 5; ++a) {
-                if (a < na && separated) {
-                    // an accepted peak's own bin was zeroed when it was found, so its half-height width is 0 (the
-                    // reference's resolution() degenerates to 1.18*dist/w_candidate); walk only if that ever fails
-                    const int w1 = mags[P::addr(acc_idx[a])] == (T)0 ? 0 : half_height_bins_f<T, HALF>(mags, acc_idx[a]);
-                    bool ok = false;
-                    if (w1 + w2 != 0) {
-                        const double num = mul_rn(1.18, (double)abs(bj - acc_idx[a])), den = 1.5 * (double)(w1 + w2);
-                        if (num >= den * (1.0 + 1e-12)) ok = true;                       // rs >= 1.5 by a clear margin
-                        else if (!(num < den * (1.0 - 1e-12))) ok = div_rn(num, (double)(w1 + w2)) >= 1.5;
-                    }
-                    if (!ok) separated = false;
-                }
-            }
-            if (separated) {
-                if (lane == 0) {
-                    unsigned char *pk = rec_s + 8 + 24 * na;
-                    reinterpret_cast<int *>(pk)[0] = bj;
-                    reinterpret_cast<int *>(pk)[1] = w2;
-                    reinterpret_cast<double *>(pk + 8)[0] = (double)bm;
-                }
-#pragma unroll
-                for (int a = 0; a < 5; ++a)
-                    if (a == na) acc_idx[a] = bj;
-                ++na;
-            }
-            // zeroing radius round((freq * 0.02) / (frequencies[2] - frequencies[1])): equals round-half-even(0.02 * idx)
-            // unless that product sits within 1e-6 of a tie; only then (or for a degenerate df) the exact expression runs
-            double reach_d;
-            {
-                const double x02 = 0.02 * (double)bj, fr = x02 - floor(x02);
-                if (df > 1e-300 && df < 1e300 && fabs(fr - 0.5) > 1e-6) {
-                    reach_d = rint(x02);
-                } else {
-                    const double f = mul_rn((double)bj, df);
-                    reach_d = rint(div_rn(mul_rn(f, 0.02), distance));
-                }
-            }
-            if (!(reach_d >= 0.0)) reach_d = 0.0;
-            if (reach_d > (double)HALF) reach_d = (double)HALF;
-            const int reach = (int)reach_d;
-            const int z0 = max(0, bj - reach), z1 = min(HALF, bj + reach + 1);
-            __syncwarp();
-            for (int b = z0 + lane; b < z1; b += 32) mags[P::addr(b)] = (T)0;
-            __syncwarp();
-        }
-        if (lane == 0) {
-            reinterpret_cast<int *>(rec_s)[0] = na;
-            reinterpret_cast<int *>(rec_s)[1] = status;
-        }
+        na = k3_rigid<T, HALF, P>(mags, slots, nslot, thr_f, df, k, lane, rec_s);
+    }
+    if (lane == 0) {
+        reinterpret_cast<int *>(rec_s)[0] = na;
+        reinterpret_cast<int *>(rec_s)[1] = status;
     }
     __syncwarp();
     if (lane < 16)  // one coalesced 128-byte store (local HBM, or the fleet table in a peer's HBM over NVLink)
         reinterpret_cast<uint64_t *>(recs + win * 128)[lane] = reinterpret_cast<const uint64_t *>(rec_s)[lane];
+}
+
+// ---- the same picker with the WHOLE CTA of the fused kernel (T threads = T/32 warps per window) ---------------------------
+// In the fused window->record kernel the CTA's FFT warps would idle while one warp runs the tail (and the CTA keeps its
+// registers and shared memory meanwhile); here every thread owns a chunk of 16 bins in phase 2, the candidates'
+// prominence walks are dealt out to the warps (chunk summaries in shared memory: whole chunks are skipped with ballots
+// over the 32 * W chunk maxima, only boundary chunks are scanned), the gates run thread-parallel, and only the short
+// ordering / record epilogue is left to warp 0.  Same decisions as k3_tail (tests compare the records).
+template <int NT>
+__device__ __forceinline__ void window_sync() {  // all NT threads that share the window (the whole CTA of the fused kernel)
+    if (NT == 32) __syncwarp();
+    else asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+}
+
+template <int HALF>
+struct K3M {  // magnitude layout of the multi-warp tail: chunks of 16 bins, 4-word pad per chunk (conflict-free LDS.128)
+    static constexpr int C = 16;
+    static constexpr int NCH = HALF / C;
+    static constexpr int MAGW = HALF + 4 * NCH;
+    __device__ static __forceinline__ int addr(int b) { return b + ((b >> 4) << 2); }
+};
+
+// prominence of bin j (utils/get_peak_prominence.py:32-54) on chunk summaries held in shared memory; one warp
+template <int HALF>
+__device__ float prominence_mw(const float *mags, const float *cmaxs, const float *cmins, int j, int lane) {
+    using P = K3M<HALF>;
+    constexpr int NW = P::NCH / 32;  // 32-chunk words
+    const float p = mags[P::addr(j)];
+    const int cj = j >> 4, jo = j & 15;
+    // own chunk: lanes 0..15 hold its bins
+    const float own = lane < 16 ? mags[P::addr(16 * cj + lane)] : p;
+    const unsigned hi_own = __ballot_sync(0xffffffffu, lane < 16 && own > p);
+    const unsigned left_hi = hi_own & ((1u << jo) - 1u);          // higher bins left of j in its chunk
+    const unsigned right_hi = hi_own & ~((2u << jo) - 1u) & 0xffffu;  // ... right of j
+    const int lstop = left_hi ? 31 - __clz(left_hi) : -1;         // walk covers (lstop, jo)
+    const int rstop = right_hi ? __ffs(right_hi) - 1 : 16;        // walk covers (jo, rstop)
+    float fl = p, fr = p;
+    if (lane < 16 && lane > lstop && lane < jo) fl = own;
+    if (lane < 16 && lane > jo && lane < rstop) fr = own;
+    // chunk maxima above p, NW words of 32 chunks
+    unsigned above[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) above[w] = __ballot_sync(0xffffffffu, cmaxs[32 * w + lane] > p);
+    if (!left_hi) {  // the walk leaves the chunk to the left: nearest chunk L < cj with a higher bin, else down to bin 0
+        int L = -1;
+#pragma unroll
+        for (int w = NW - 1; w >= 0; --w) {
+            if (L < 0 && 32 * w < cj) {
+                const unsigned m = 32 * w + 32 <= cj ? above[w] : (above[w] & ((1u << (cj - 32 * w)) - 1u));
+                if (m) L = 32 * w + 31 - __clz(m);
+            }
+        }
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {  // chunks strictly between L and cj are walked completely
+            const int id = 32 * w + lane;
+            if (id > L && id < cj) fl = fminf(fl, cmins[id]);
+        }
+        if (L >= 0) {  // inside L: bins right of its last higher bin
+            const float v = lane < 16 ? mags[P::addr(16 * L + lane)] : p;
+            const unsigned h = __ballot_sync(0xffffffffu, lane < 16 && v > p);
+            const int stop = 31 - __clz(h);  // h != 0: the chunk maximum is higher than p
+            if (lane < 16 && lane > stop) fl = fminf(fl, v);
+        }
+    }
+    if (!right_hi) {
+        int R = P::NCH;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            if (R == P::NCH && 32 * w + 31 > cj) {
+                const unsigned m = 32 * w > cj ? above[w] : (above[w] & ~((2u << (cj - 32 * w)) - 1u));
+                if (m) R = 32 * w + __ffs(m) - 1;
+            }
+        }
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const int id = 32 * w + lane;
+            if (id > cj && id < R) fr = fminf(fr, cmins[id]);
+        }
+        if (R < P::NCH) {
+            const float v = lane < 16 ? mags[P::addr(16 * R + lane)] : p;
+            const unsigned h = __ballot_sync(0xffffffffu, lane < 16 && v > p);
+            const int stop = __ffs(h) - 1;
+            if (lane < 16 && lane < stop) fr = fminf(fr, v);
+        }
+    }
+    fl = warp_min_nonneg(fl);
+    fr = warp_min_nonneg(fr);
+    return sub_rn(p, fmaxf(fl, fr));
+}
+
+// scratch: cmaxs[NCH], cmins[NCH] floats, then the slot list (slot_cap entries), then two ints (slot count, tie flag);
+// all threads of the window's CTA call this after the magnitudes are in shared memory (and a barrier)
+template <int HALF, bool FLEX, int NT>
+__device__ __forceinline__ void k3_tail_mw(float *mags, float *cmaxs, float *cmins, Slot *slots, const int slot_cap,
+                                           int *ctl /* [0] slots, [1] tie */, unsigned char *rec_s, const double sd,
+                                           const float thr_f, const double df, const int k, const int t, const int64_t win,
+                                           unsigned char *__restrict__ recs) {
+    using P = K3M<HALF>;
+    static_assert(P::NCH == NT, "one 16-bin chunk per thread");
+    const int lane = t & 31, warp = t >> 5;
+    constexpr int W = NT / 32;
+    // ---- phase 2: one 16-bin chunk per thread --------------------------------------------------------------------------
+    {
+        const float *ch = mags + P::addr(16 * t);
+        float cmax = -CUDART_INF_F, cmin = CUDART_INF_F;
+        unsigned hotq = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 v = *reinterpret_cast<const float4 *>(ch + 4 * q);
+            const float m4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+            cmax = fmaxf(cmax, m4);
+            cmin = fminf(cmin, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
+            if (m4 > thr_f) hotq |= 1u << q;
+        }
+        cmaxs[t] = cmax;
+        cmins[t] = cmin;
+        while (hotq) {
+            const int q = __ffs(hotq) - 1;
+            hotq &= hotq - 1;
+            const float4 v = *reinterpret_cast<const float4 *>(ch + 4 * q);
+            const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (e[u] > thr_f) {
+                    const int j = 16 * t + 4 * q + u;
+                    bool take = true;
+                    if (FLEX) take = j >= 1 && j <= HALF - 2 && e[u] > mags[P::addr(j - 1)] && e[u] > mags[P::addr(j + 1)];
+                    if (take) {
+                        const int pos = atomicAdd(&ctl[0], 1);
+                        if (pos < slot_cap) slots[pos].idx = (uint16_t)j;
+                    }
+                    if (j >= 1 && j + 1 <= HALF - 1 && e[u] == mags[P::addr(j + 1)] && e[u] > mags[P::addr(j - 1)] &&
+                        (j + 2 > HALF - 1 || e[u] > mags[P::addr(j + 2)]))
+                        ctl[1] = 1;  // APDA_STATUS_FP32_TIE, see k3_tail
+                }
+            }
+        }
+    }
+    window_sync<NT>();
+    const int nslot = min(ctl[0], slot_cap);
+    const int status = (ctl[0] > slot_cap ? APDA_STATUS_TRUNCATED : 0) | (ctl[1] ? APDA_STATUS_FP32_TIE : 0);
+    int na = 0;
+    if (FLEX) {
+        for (int c = warp; c < nslot; c += W) {  // A: the candidates' prominence walks, dealt out to the warps
+            const float prom = prominence_mw<HALF>(mags, cmaxs, cmins, slots[c].idx, lane);
+            if (lane == 0) slots[c].prom = prom;
+        }
+        window_sync<NT>();
+        const double half_sd = mul_rn(0.5, sd);
+        for (int c = t; c < nslot; c += NT)  // B: gates, one candidate per thread
+            slots[c].width = (uint16_t)k3_gate<float, HALF, P>(mags, slots[c].idx, slots[c].prom, half_sd, df);
+        window_sync<NT>();
+        if (warp != 0) return;
+        na = nslot <= 32   ? order_and_exclude<float, HALF, 1, P>(slots, nslot, mags, rec_s, df, k, lane)
+             : nslot <= 96 ? order_and_exclude<float, HALF, 3, P>(slots, nslot, mags, rec_s, df, k, lane)
+                           : order_and_exclude_any<float, HALF, P>(slots, nslot, mags, rec_s, df, k, lane);
+    } else {
+        if (warp != 0) return;
+        na = k3_rigid<float, HALF, P>(mags, slots, nslot, thr_f, df, k, lane, rec_s);
+    }
+    if (lane == 0) {
+        reinterpret_cast<int *>(rec_s)[0] = na;
+        reinterpret_cast<int *>(rec_s)[1] = status;
+    }
+    __syncwarp();
+    if (lane < 16) reinterpret_cast<uint64_t *>(recs + win * 128)[lane] = reinterpret_cast<const uint64_t *>(rec_s)[lane];
 }
 
 }  // namespace
