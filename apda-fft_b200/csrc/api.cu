@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -44,6 +45,17 @@ int apda_reserve(void **buf, size_t *have, size_t need) {
         return APDA_ERR_NOMEM;
     }
     *have = want;
+    return APDA_OK;
+}
+
+int apda_func_smem(const void *kernel, int device, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, size_t> done;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &have = done[std::make_pair(device, kernel)];
+    if (bytes <= have) return APDA_OK;
+    APDA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    have = bytes;
     return APDA_OK;
 }
 
@@ -99,6 +111,7 @@ extern "C" int apda_ctx_create(int device, apda_ctx **out) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    APDA_CUDA(cudaDeviceGetAttribute(&ctx->clock_khz, cudaDevAttrClockRate, device));
     APDA_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
     for (int i = 0; i < 2; ++i) {
@@ -1115,10 +1128,8 @@ extern "C" int apda_peer_wait(apda_ctx *ctx, const void *d_flags, int world, uin
                               int *d_timed_out) {
     if (!ctx || !d_flags || !d_timed_out || world < 1 || world > 32) return APDA_ERR_INVALID;
     APDA_CUDA(cudaSetDevice(ctx->device));
-    int khz = 0;
-    APDA_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device));
     peer_wait_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const unsigned *>(d_flags), world, value,
-                                               (long long)(timeout_s * 1e3 * (double)khz), d_timed_out);
+                                               (long long)(timeout_s * 1e3 * (double)ctx->clock_khz), d_timed_out);
     ctx->launches++;
     APDA_CUDA(cudaGetLastError());
     return APDA_OK;

@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <map>
+#include <mutex>
 #include <utility>
 #include <vector>
 #include <string>
@@ -23,6 +24,7 @@ struct apda_ctx {
     int device = 0;
     int sm_count = 0;
     int smem_optin = 0;
+    int clock_khz = 0;  // SM clock (cached: querying cudaDevAttrClockRate per call costs about a millisecond)
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;  // stream the _dev entry points enqueue on
     cudaStream_t pipe[2] = {nullptr, nullptr};
@@ -64,6 +66,10 @@ int apda_cuda_fail(cudaError_t e, const char *what);
 
 int apda_get_twiddles(apda_ctx *ctx, int64_t N, TwiddleTables *out);
 int apda_reserve(void **buf, size_t *have, size_t need);
+// cudaFuncAttributeMaxDynamicSharedMemorySize, set once per (device, kernel): the attribute call is a driver round trip that
+// a launch on the hot path (a few hundred microseconds of GPU work per step in the strong-scaled fleet sweep) should not pay
+int apda_func_smem(const void *kernel, int device, size_t bytes);
+#define APDA_FUNC_SMEM(ctx, kernel, bytes) APDA_TRY(apda_func_smem(reinterpret_cast<const void *>(kernel), (ctx)->device, (size_t)(bytes)))
 // per-stream window lists of `batch + 1` ints, zero count enqueued on `st` (see apda_ctx::stream_lists)
 int apda_repair_list(apda_ctx *ctx, cudaStream_t st, int64_t batch, int **out);
 int apda_ragged_list(apda_ctx *ctx, cudaStream_t st, int64_t batch, int **out);

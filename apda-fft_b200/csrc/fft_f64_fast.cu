@@ -303,7 +303,7 @@ int launch_n(apda_ctx *ctx, cudaStream_t st, const double *d_samples, int64_t n_
              int flags, const double2 *tw, double *d_spec, const int *d_nv) {
     using PL = Plan64<LOGN>;
     const size_t smem = (size_t)PL::SM_ELEMS * sizeof(double2);
-    APDA_CUDA(cudaFuncSetAttribute(fft_f64_fast_kernel<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    APDA_FUNC_SMEM(ctx, fft_f64_fast_kernel<LOGN>, smem);
     fft_f64_fast_kernel<LOGN><<<(unsigned)batch, PL::T, smem, st>>>(d_samples, (int)n_samples, ld, tw,
                                                                    reinterpret_cast<double2 *>(d_spec), flags, d_nv);
     ctx->launches++;

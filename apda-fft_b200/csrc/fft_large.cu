@@ -966,17 +966,17 @@ static K2Tune k2_tune() {
 }
 
 template <typename T, int NT, int MINB>
-static int launch_tail_tma(cudaStream_t st, dim3 grid, size_t smem, const CUtensorMap &tm, int n, int s0, int q, int C,
+static int launch_tail_tma(apda_ctx *ctx, cudaStream_t st, dim3 grid, size_t smem, const CUtensorMap &tm, int n, int s0, int q, int C,
                            const typename vec2<T>::type *twp, int zero_dc) {
-    APDA_CUDA(cudaFuncSetAttribute(large_tail_tma_kernel<T, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    APDA_FUNC_SMEM(ctx, (large_tail_tma_kernel<T, NT, MINB>), smem);
     large_tail_tma_kernel<T, NT, MINB><<<grid, NT, smem, st>>>(tm, n, s0, q, C, twp, zero_dc);
     return APDA_OK;
 }
 
 template <typename T, bool CPLX, int NT>
-static int launch_head(cudaStream_t st, dim3 grid, size_t smem, const T *d_samples, int64_t n_samples, int64_t ld, int n, int q,
+static int launch_head(apda_ctx *ctx, cudaStream_t st, dim3 grid, size_t smem, const T *d_samples, int64_t n_samples, int64_t ld, int n, int q,
                        int C, const typename vec2<T>::type *twp, typename vec2<T>::type *spec, const T *d_med) {
-    APDA_CUDA(cudaFuncSetAttribute(large_head_kernel<T, CPLX, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    APDA_FUNC_SMEM(ctx, (large_head_kernel<T, CPLX, NT>), smem);
     large_head_kernel<T, CPLX, NT><<<grid, NT, smem, st>>>(d_samples, n_samples, ld, n, q, C, twp, spec, d_med);
     return APDA_OK;
 }
@@ -1031,11 +1031,11 @@ int launch_fft_large(apda_ctx *ctx, cudaStream_t st, const T *d_samples, int64_t
         // SM fit the register file (74 registers in fp32: 16 complex values per thread)
         const int hnt = smem > (96u << 10) ? 1024 : 256;
         if (complex_input) {
-            if (hnt == 1024) APDA_TRY((launch_head<T, true, 1024>(st, grid, smem, d_samples, n_samples, ld, n, q, C, twp, spec, d_med)));
-            else APDA_TRY((launch_head<T, true, 256>(st, grid, smem, d_samples, n_samples, ld, n, q, C, twp, spec, d_med)));
+            if (hnt == 1024) APDA_TRY((launch_head<T, true, 1024>(ctx, st, grid, smem, d_samples, n_samples, ld, n, q, C, twp, spec, d_med)));
+            else APDA_TRY((launch_head<T, true, 256>(ctx, st, grid, smem, d_samples, n_samples, ld, n, q, C, twp, spec, d_med)));
         } else {
-            if (hnt == 1024) APDA_TRY((launch_head<T, false, 1024>(st, grid, smem, d_samples, n_samples, ld, n, q, C, twp, spec, d_med)));
-            else APDA_TRY((launch_head<T, false, 256>(st, grid, smem, d_samples, n_samples, ld, n, q, C, twp, spec, d_med)));
+            if (hnt == 1024) APDA_TRY((launch_head<T, false, 1024>(ctx, st, grid, smem, d_samples, n_samples, ld, n, q, C, twp, spec, d_med)));
+            else APDA_TRY((launch_head<T, false, 256>(ctx, st, grid, smem, d_samples, n_samples, ld, n, q, C, twp, spec, d_med)));
         }
         ctx->launches++;
         APDA_CUDA(cudaGetLastError());
@@ -1054,19 +1054,19 @@ int launch_fft_large(apda_ctx *ctx, cudaStream_t st, const T *d_samples, int64_t
             make_tail_tmap<T>(&tm, d_spec, n, s0, q, C, batch)) {
             const bool one_per_sm = tma_smem > (size_t)ctx->smem_optin / 2;
             const int nt = one_per_sm ? std::max(tune.nt, 512) : tune.nt;
-            if (nt >= 1024) APDA_TRY((launch_tail_tma<T, 1024, 1>(st, grid, tma_smem, tm, n, s0, q, C, twp, zero_dc)));
-            else if (nt >= 512 && (one_per_sm || tune.minb <= 1)) APDA_TRY((launch_tail_tma<T, 512, 1>(st, grid, tma_smem, tm, n, s0, q, C, twp, zero_dc)));
-            else if (nt >= 512 && tune.minb == 2) APDA_TRY((launch_tail_tma<T, 512, 2>(st, grid, tma_smem, tm, n, s0, q, C, twp, zero_dc)));
-            else if (nt >= 512) APDA_TRY((launch_tail_tma<T, 512, 3>(st, grid, tma_smem, tm, n, s0, q, C, twp, zero_dc)));
-            else if (tune.minb <= 2) APDA_TRY((launch_tail_tma<T, 256, 2>(st, grid, tma_smem, tm, n, s0, q, C, twp, zero_dc)));
-            else APDA_TRY((launch_tail_tma<T, 256, 3>(st, grid, tma_smem, tm, n, s0, q, C, twp, zero_dc)));
+            if (nt >= 1024) APDA_TRY((launch_tail_tma<T, 1024, 1>(ctx, st, grid, tma_smem, tm, n, s0, q, C, twp, zero_dc)));
+            else if (nt >= 512 && (one_per_sm || tune.minb <= 1)) APDA_TRY((launch_tail_tma<T, 512, 1>(ctx, st, grid, tma_smem, tm, n, s0, q, C, twp, zero_dc)));
+            else if (nt >= 512 && tune.minb == 2) APDA_TRY((launch_tail_tma<T, 512, 2>(ctx, st, grid, tma_smem, tm, n, s0, q, C, twp, zero_dc)));
+            else if (nt >= 512) APDA_TRY((launch_tail_tma<T, 512, 3>(ctx, st, grid, tma_smem, tm, n, s0, q, C, twp, zero_dc)));
+            else if (tune.minb <= 2) APDA_TRY((launch_tail_tma<T, 256, 2>(ctx, st, grid, tma_smem, tm, n, s0, q, C, twp, zero_dc)));
+            else APDA_TRY((launch_tail_tma<T, 256, 3>(ctx, st, grid, tma_smem, tm, n, s0, q, C, twp, zero_dc)));
         } else {
             const size_t smem = (size_t)(C + 1) * (1u << q) * sizeof(V2);
             if (smem > (size_t)ctx->smem_optin) {
                 apda_set_error("fft_large: tile of 2^%d x %d does not fit shared memory", q, C);
                 return APDA_ERR_UNSUPPORTED;
             }
-            APDA_CUDA(cudaFuncSetAttribute(large_tail_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            APDA_FUNC_SMEM(ctx, large_tail_kernel<T>, smem);
             large_tail_kernel<T><<<grid, kThreads, smem, st>>>(reinterpret_cast<V2 *>(d_spec), n, s0, q, C, twp, zero_dc);
         }
         ctx->launches++;

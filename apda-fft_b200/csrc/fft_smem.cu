@@ -260,7 +260,7 @@ int launch_fft_smem(apda_ctx *ctx, cudaStream_t st, const T *d_samples, int64_t 
     }
     constexpr bool kFaithful = sizeof(T) == 8;
     auto kern = complex_input ? fft_smem_kernel<T, kFaithful, true> : fft_smem_kernel<T, kFaithful, false>;
-    APDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    APDA_FUNC_SMEM(ctx, kern, smem);
     int logN = ilog2_i64(N);
     // grid.x is limited to 2^31-1 windows per launch, far above any batch that fits HBM
     const unsigned grid = d_list ? (unsigned)std::min<int64_t>(batch, 2 * (int64_t)ctx->sm_count) : (unsigned)batch;

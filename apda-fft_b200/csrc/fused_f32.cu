@@ -153,7 +153,7 @@ int launch_fused_n(apda_ctx *ctx, cudaStream_t st, const float *d_samples, int64
     }
 #undef PICK
     const size_t smem = FusedLayout<N>::BYTES;
-    APDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    APDA_FUNC_SMEM(ctx, kern, smem);
     kern<<<(unsigned)batch, N / 32, smem, st>>>(d_samples, (int)n_samples, ld, batch, tw1, twu, fs / (double)N, d_fs, k,
                                             reinterpret_cast<unsigned char *>(d_rec));
     ctx->launches++;

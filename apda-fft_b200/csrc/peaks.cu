@@ -347,7 +347,7 @@ static int launch_peaks_general(apda_ctx *ctx, cudaStream_t st, const T *d_spec,
     const unsigned grid = list ? (unsigned)std::min<int64_t>(batch, 2 * (int64_t)ctx->sm_count) : (unsigned)batch;
     if (in_smem) {
         auto kern = flexible ? peaks_kernel<T, true, true> : peaks_kernel<T, true, false>;
-        APDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.bytes));
+        APDA_FUNC_SMEM(ctx, kern, lay.bytes);
         kern<<<grid, 256, lay.bytes, st>>>(spec, n, half, batch, fs, d_fs, k, rec_cap, recs, nullptr, list);
     } else {
         if (!ws) {

@@ -71,7 +71,7 @@ int launch_half(apda_ctx *ctx, cudaStream_t st, const float *d_spec, int64_t bat
                 int k, int flexible, void *d_rec) {
     const int smem = kWPC * K3<float, HALF>::BYTES;
     auto kern = flexible ? peaks_f32_fast_kernel<HALF, true> : peaks_f32_fast_kernel<HALF, false>;
-    APDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    APDA_FUNC_SMEM(ctx, kern, smem);
     const int64_t blocks = (batch + kWPC - 1) / kWPC;
     // repair list: [0] = count, [1..] = windows whose candidate list did not fit on chip
     int *repair = nullptr;

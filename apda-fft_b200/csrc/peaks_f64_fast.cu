@@ -204,8 +204,17 @@ int launch_half64(apda_ctx *ctx, cudaStream_t st, const double *d_spec, int64_t 
                   int k, int flexible, void *d_rec) {
     const int smem = kWPC64 * K3<double, HALF>::BYTES;
     auto kern = flexible ? peaks_f64_fast_kernel<HALF, true> : peaks_f64_fast_kernel<HALF, false>;
-    APDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    APDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    {
+        static std::mutex mu;  // carve-out preference: once per (device, kernel), like the dynamic shared memory size
+        static std::map<std::pair<int, const void *>, bool> carved;
+        std::lock_guard<std::mutex> lock(mu);
+        bool &done = carved[std::make_pair(ctx->device, reinterpret_cast<const void *>(kern))];
+        if (!done) {
+            APDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            done = true;
+        }
+    }
+    APDA_FUNC_SMEM(ctx, kern, smem);
     const int64_t blocks = (batch + kWPC64 - 1) / kWPC64;
     int *repair = nullptr;  // repair list, see peaks_f32_fast.cu
     APDA_TRY(apda_repair_list(ctx, st, batch, &repair));
