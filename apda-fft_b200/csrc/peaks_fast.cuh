@@ -561,7 +561,9 @@ __device__ __forceinline__ void k3_tail(T *mags, SlotT<T> *slots, const int slot
 // registers and shared memory meanwhile); here every thread owns a chunk of 16 bins in phase 2, the candidates'
 // prominence walks are dealt out to the warps (chunk summaries in shared memory: whole chunks are skipped with ballots
 // over the 32 * W chunk maxima, only boundary chunks are scanned), the gates run thread-parallel, and only the short
-// ordering / record epilogue is left to warp 0.  Same decisions as k3_tail (tests compare the records).
+// ordering / record epilogue is left to warp 0.  Same decisions as k3_tail (tests compare the records).  (Measured and
+// rejected for the PIPELINE picker, where one warp per window hides the tail's latency behind other windows: a CTA per
+// window with this tail ran 4.5 instead of 3.3 ns per window.)
 template <int NT>
 __device__ __forceinline__ void window_sync() {  // all NT threads that share the window (the whole CTA of the fused kernel)
     if (NT == 32) __syncwarp();
