@@ -10,6 +10,6 @@ Layout
 """
 from . import records, synth  # noqa: F401
 from ._cabi import ApdaError, Context, default_context, load  # noqa: F401
-from .batch import Analyzer  # noqa: F401
+from .batch import Analyzer, multi_analyze  # noqa: F401
 
-__all__ = ["Analyzer", "ApdaError", "Context", "default_context", "load", "records", "synth"]
+__all__ = ["Analyzer", "multi_analyze", "ApdaError", "Context", "default_context", "load", "records", "synth"]

@@ -51,6 +51,8 @@ SIGNATURES = {
     "apda_analyze_f32_dev": (_int, [_p, _p, _i64, _i64, _i64, _i64, _int, _int, _dbl, _p, _int, _int, _p, _p]),
     "apda_analyze_f64_host": (_int, [_p, _p, _i64, _i64, _i64, _i64, _int, _int, _dbl, _p, _int, _int, _p]),
     "apda_analyze_f32_host": (_int, [_p, _p, _i64, _i64, _i64, _i64, _int, _int, _dbl, _p, _int, _int, _p]),
+    "apda_multi_analyze_f32_host": (_int, [_p, _int, _p, _i64, _i64, _i64, _i64, _int, _int, _dbl, _p, _int, _int, _p]),
+    "apda_multi_analyze_f64_host": (_int, [_p, _int, _p, _i64, _i64, _i64, _i64, _int, _int, _dbl, _p, _int, _int, _p]),
     "apda_fft_ragged_f64_dev": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _int, _p]),
     "apda_fft_ragged_f32_dev": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _int, _p]),
     "apda_analyze_ragged_f64_dev": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _int, _int, _dbl, _p, _int, _int, _p, _p]),

@@ -196,3 +196,24 @@ class Analyzer:
         if arr.shape != (batch,):
             raise ValueError(f"fs must be a scalar or have shape ({batch},)")
         return float(arr[0]) if batch else 0.0, arr
+
+
+def multi_analyze(contexts, samples: np.ndarray, fs, flexible: bool = True, k: int | None = None,
+                  n_fft: int | None = None, center: int = _cabi.CENTER_MEDIAN) -> np.ndarray:
+    """One process, several GPUs: [B, n_samples] host windows sharded contiguously over ``contexts`` (``_cabi.Context``
+    objects of different devices), every device writing its rows of the returned record table
+    (apda_multi_analyze_*_host: one host thread per context, no collective)."""
+    x = np.ascontiguousarray(np.atleast_2d(samples))
+    sfx = _suffix(x.dtype)
+    b, ns = x.shape
+    n = next_pow2(ns) if n_fft is None else int(n_fft)
+    k = (4 if flexible else 5) if k is None else int(k)
+    cap = max(5, k)
+    recs = np.zeros(b, dtype=record_dtype(cap))
+    fs_scalar, fs_arr = Analyzer._fs(fs, b)
+    handles = (ctypes.c_void_p * len(contexts))(*[c.handle for c in contexts])
+    fn = getattr(_cabi.load(), f"apda_multi_analyze_{sfx}_host")
+    _cabi.check(fn(handles, len(contexts), _p(x.ctypes.data), ns, ns, b, n, center, int(bool(flexible)), fs_scalar,
+                   _p(fs_arr.ctypes.data if fs_arr is not None else 0), k, cap, _p(recs.ctypes.data)))
+    return recs
+

@@ -6,6 +6,8 @@
 
 #include <algorithm>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -672,6 +674,67 @@ extern "C" int apda_analyze_f32_host(apda_ctx *ctx, const float *h_samples, int6
     APDA_TRY(check_peaks_args(ctx, h_samples, N, batch, k, rec_cap, h_rec));
     return host_pipeline<float>(ctx, kAnalyze, h_samples, n_samples, ld, batch, N, flags, flexible, fs, h_fs, k, rec_cap,
                                 false, nullptr, h_rec);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// one host process, several GPUs: the batch is sharded contiguously over the contexts (rank r of G owns
+// windows [r*ceil(B/G), ...)), one host thread per context runs the chunked host pipeline on its shard, and every
+// device copies its records straight into its rows of the caller's table - the "gather to rank 0" of a single-process
+// host needs no collective at all.  (Multi-process fleets use the peer record table below, or NCCL in the host language.)
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+static int multi_analyze_host(apda_ctx **ctxs, int n_ctx, const T *h_samples, int64_t n_samples, int64_t ld, int64_t batch,
+                              int64_t N, int flags, int flexible, double fs, const double *h_fs, int k, int rec_cap,
+                              void *h_rec) {
+    if (!ctxs || n_ctx < 1 || n_ctx > 64) {
+        apda_set_error("multi_analyze: need 1..64 contexts");
+        return APDA_ERR_INVALID;
+    }
+    for (int i = 0; i < n_ctx; ++i) {
+        if (!ctxs[i]) {
+            apda_set_error("multi_analyze: context %d is NULL", i);
+            return APDA_ERR_INVALID;
+        }
+        for (int j = 0; j < i; ++j)
+            if (ctxs[j] == ctxs[i]) {
+                apda_set_error("multi_analyze: context %d is listed twice (a context belongs to one thread)", i);
+                return APDA_ERR_INVALID;
+            }
+    }
+    APDA_TRY(check_fft_args(ctxs[0], h_samples, n_samples, ld, batch, N, flags, h_rec));
+    APDA_TRY(check_peaks_args(ctxs[0], h_samples, N, batch, k, rec_cap, h_rec));
+    const int64_t per = (batch + n_ctx - 1) / n_ctx;
+    const size_t rec_bytes = (size_t)APDA_REC_BYTES(rec_cap);
+    std::vector<int> status((size_t)n_ctx, APDA_OK);
+    std::vector<std::string> message((size_t)n_ctx);
+    std::vector<std::thread> workers;
+    for (int r = 0; r < n_ctx; ++r) {
+        const int64_t lo = std::min<int64_t>(batch, r * per), hi = std::min<int64_t>(batch, lo + per);
+        if (hi <= lo) continue;
+        workers.emplace_back([&, r, lo, hi] {
+            status[(size_t)r] = host_pipeline<T>(ctxs[r], kAnalyze, h_samples + (size_t)lo * (size_t)ld, n_samples, ld, hi - lo, N,
+                                                 flags, flexible, fs, h_fs ? h_fs + lo : nullptr, k, rec_cap, false, nullptr,
+                                                 (char *)h_rec + (size_t)lo * rec_bytes);
+            if (status[(size_t)r] != APDA_OK) message[(size_t)r] = apda_last_error();  // the worker's thread-local message
+        });
+    }
+    for (auto &w : workers) w.join();
+    for (int r = 0; r < n_ctx; ++r)
+        if (status[(size_t)r] != APDA_OK) {
+            apda_set_error("multi_analyze: context %d (device %d): %s", r, ctxs[r]->device, message[(size_t)r].c_str());
+            return status[(size_t)r];
+        }
+    return APDA_OK;
+}
+extern "C" int apda_multi_analyze_f32_host(apda_ctx **ctxs, int n_ctx, const float *h_samples, int64_t n_samples, int64_t ld,
+                                           int64_t batch, int64_t N, int flags, int flexible, double fs, const double *h_fs,
+                                           int k, int rec_cap, void *h_rec) {
+    return multi_analyze_host<float>(ctxs, n_ctx, h_samples, n_samples, ld, batch, N, flags, flexible, fs, h_fs, k, rec_cap, h_rec);
+}
+extern "C" int apda_multi_analyze_f64_host(apda_ctx **ctxs, int n_ctx, const double *h_samples, int64_t n_samples, int64_t ld,
+                                           int64_t batch, int64_t N, int flags, int flexible, double fs, const double *h_fs,
+                                           int k, int rec_cap, void *h_rec) {
+    return multi_analyze_host<double>(ctxs, n_ctx, h_samples, n_samples, ld, batch, N, flags, flexible, fs, h_fs, k, rec_cap, h_rec);
 }
 
 static int check_fused_args(int64_t N, int flags, int k, int rec_cap) {

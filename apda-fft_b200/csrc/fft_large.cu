@@ -67,18 +67,21 @@ __device__ __forceinline__ void stage_round(typename vec2<T>::type *tile, int rs
     for (int item = tid; item < items; item += NT) {
         const int c = item & ((1 << logC) - 1), rest = item >> logC;
         const int jr = rest & ((1 << t0) - 1), hi = rest >> t0;
-        V2 *p = tile + (size_t)(((hi << (t0 + QR)) + jr)) * rs + (size_t)c * cs;
+        V2 *p = tile + (((hi << (t0 + QR)) + jr) * rs + c * cs);  // a tile holds < 2^15 elements: 32-bit index arithmetic
         const int kstride = rs << t0;
         V2 v[R];
 #pragma unroll
         for (int k = 0; k < R; ++k) v[k] = p[k * kstride];
+        // twiddle indices fit 32 bits (the table of N <= 2^30 has N - 1 entries): one 64-bit pointer add per load
+        const unsigned tw_row = ((unsigned)jr << s0) + (HEAD ? 0u : (unsigned)lo0 + (unsigned)c);
+        const unsigned tw_step = 1u << (t0 + s0);
 #pragma unroll
         for (int u = 1; u <= QR; ++u) {
             const int t = t0 + u;  // stage of this pass (1-based): pairs rows that differ in bit t-1
-            const V2 *tab = tw + (((int64_t)1 << (s0 + t - 1)) - 1) + (HEAD ? 0 : lo0 + c);
+            const V2 *tab = tw + (((1u << (s0 + t - 1)) - 1u) + tw_row);
             V2 w[R / 2];
 #pragma unroll
-            for (int m = 0; m < (1 << (u - 1)); ++m) w[m] = __ldg(tab + ((int64_t)(jr + (m << t0)) << s0));
+            for (int m = 0; m < (1 << (u - 1)); ++m) w[m] = __ldg(tab + m * tw_step);
             if constexpr (sizeof(T) == 4) {
                 V2 wr[R / 2];
 #pragma unroll

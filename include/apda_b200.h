@@ -144,6 +144,18 @@ int apda_analyze_f32_host(apda_ctx *ctx, const float *h_samples, int64_t n_sampl
                           int64_t N, int flags, int flexible, double fs, const double *h_fs, int k, int rec_cap,
                           void *h_rec);
 
+/* One host process, several GPUs (nothing like it in the reference, which analyses one file at a time,
+ * GT_FFT_v5.py:466,620): ctxs[0..n_ctx) are contexts of different devices (or several contexts of one device), each owned
+ * by this call for its duration.  The batch is sharded contiguously (context r: windows [r*ceil(batch/n_ctx), ...)), one
+ * host thread per context runs the chunked pipeline of apda_analyze_*_host on its shard, and every device writes its
+ * records into its rows of h_rec - the table a gather to rank 0 would produce, in window order, with no collective. */
+int apda_multi_analyze_f32_host(apda_ctx **ctxs, int n_ctx, const float *h_samples, int64_t n_samples, int64_t ld,
+                                int64_t batch, int64_t N, int flags, int flexible, double fs, const double *h_fs, int k,
+                                int rec_cap, void *h_rec);
+int apda_multi_analyze_f64_host(apda_ctx **ctxs, int n_ctx, const double *h_samples, int64_t n_samples, int64_t ld,
+                                int64_t batch, int64_t N, int flags, int flexible, double fs, const double *h_fs, int k,
+                                int rec_cap, void *h_rec);
+
 /* Ragged batches: window b holds d_n_valid[b] <= n_max <= N samples (rows of ld reals); everything stays on the device
  * and nothing synchronises.  Windows of the common length n_max run on the specialised kernels, the others on the
  * general kernel with their own length.  Record status bit 2 (4): the window's own padded length differs from N (the

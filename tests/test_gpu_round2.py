@@ -350,3 +350,31 @@ def test_result_packing_from_gpu_record_table(flexible, tmp_path, an):
         assert rows[w]["window"] == 5_000 + w
         assert rows[w]["fft_freqs"] == ([p["freq"] for p in want] + [0.0] * k)[:k]
         assert rows[w]["fft_mags"] == ([p["mag"] for p in want] + [0.0] * k)[:k]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# one host process, several contexts / GPUs (C-ABI gather without a collective)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_multi_analyze_host_equals_single_context(dtype, an):
+    """apda_multi_analyze_*_host shards the batch over several contexts (every visible GPU, and two contexts per GPU so
+    that a one-GPU box exercises the sharding too): the table must equal the single-context call byte for byte, for a
+    batch that does not divide evenly, per-window sampling rates included."""
+    import torch
+    import apda_fft_b200
+    import apda_fft_b200.synth as synth
+    from apda_fft_b200 import _cabi
+    ndev = torch.cuda.device_count()
+    ctxs = [_cabi.Context(d) for d in range(ndev) for _ in range(2)]
+    b, n = 1003, 4096
+    x = synth.fleet_windows(77, b, n).astype(dtype)
+    x[5, :] = 0.25                                   # a constant window (no peaks) in the first shard
+    fs = np.linspace(100.0, 200.0, b)
+    for flexible in (True, False):
+        want = an.analyze(x, fs, flexible=flexible, resolve_ties=False)
+        got = apda_fft_b200.multi_analyze(ctxs, x, fs, flexible=flexible)
+        assert got.tobytes() == want.tobytes(), flexible
+    with pytest.raises(ValueError):
+        apda_fft_b200.multi_analyze([ctxs[0], ctxs[0]], x, 125.0)
+    for c in ctxs:
+        c.close()
