@@ -279,7 +279,7 @@ static int check_peaks_args(apda_ctx *ctx, const void *spec, int64_t n, int64_t 
 
 template <typename T>
 static int fft_dispatch(apda_ctx *ctx, cudaStream_t st, const T *d_samples, int64_t n_samples, int64_t ld,
-                        int64_t batch, int64_t N, int flags, T *d_spec, bool complex_in) {
+                        int64_t batch, int64_t N, int flags, T *d_spec, bool complex_in, bool half_out = false) {
     if (batch == 0) return APDA_OK;
     if (sizeof(T) == 8 && flags == APDA_CENTER_MEAN) {
         apda_set_error("fft: APDA_CENTER_MEAN is an fp32-only option; the fp64 path is bit-faithful to the reference");
@@ -287,7 +287,7 @@ static int fft_dispatch(apda_ctx *ctx, cudaStream_t st, const T *d_samples, int6
     }
     if (sizeof(T) == 4 && !complex_in && !ctx->generic_only && fft_f32_fast_supports(N))
         return launch_fft_f32_fast(ctx, st, reinterpret_cast<const float *>(d_samples), n_samples, ld, batch, N, flags,
-                                   reinterpret_cast<float *>(d_spec));
+                                   reinterpret_cast<float *>(d_spec), nullptr, half_out);
     if (sizeof(T) == 8 && !complex_in && !ctx->generic_only && fft_f64_fast_supports(N))
         return launch_fft_f64_fast(ctx, st, reinterpret_cast<const double *>(d_samples), n_samples, ld, batch, N, flags,
                                    reinterpret_cast<double *>(d_spec));
@@ -461,7 +461,9 @@ static int analyze_dev(apda_ctx *ctx, const T *d_samples, int64_t n_samples, int
         APDA_TRY(apda_reserve(&ctx->ws, &ctx->ws_bytes, spec_bytes + mag_bytes));
     }
     T *spec = d_spec_ws ? d_spec_ws : reinterpret_cast<T *>(ctx->ws);
-    APDA_TRY(fft_dispatch<T>(ctx, ctx->stream, d_samples, n_samples, ld, batch, N, flags, spec, false));
+    // the library's own workspace only ever feeds the picker: K1 skips the upper half of the spectrum there (a caller's
+    // d_spec_ws receives all N bins, as apda_fft_* would write them)
+    APDA_TRY(fft_dispatch<T>(ctx, ctx->stream, d_samples, n_samples, ld, batch, N, flags, spec, false, d_spec_ws == nullptr));
     return peaks_dispatch<T>(ctx, ctx->stream, spec, N, batch, fs, d_fs, k, rec_cap, flexible, d_rec, &ctx->ws,
                              &ctx->ws_bytes, spec_bytes);
 }
@@ -589,7 +591,8 @@ static int host_pipeline(apda_ctx *ctx, HostMode mode, const T *h_in, int64_t n_
             return APDA_OK;
         }
         if (mode != kPeaksOnly) {
-            APDA_TRY(fft_dispatch<T>(ctx, st, d_in, n_samples, (int64_t)in_elems, cnt, N, flags, d_spec, complex_in));
+            APDA_TRY(fft_dispatch<T>(ctx, st, d_in, n_samples, (int64_t)in_elems, cnt, N, flags, d_spec, complex_in,
+                                     mode == kAnalyze));
             spec_for_peaks = d_spec;
             if (mode == kFftOnly)
                 APDA_CUDA(cudaMemcpyAsync(h_spec_out + (size_t)done * spec_elems, d_spec, cnt * spec_elems * sizeof(T),

@@ -101,7 +101,7 @@ template <typename T>
 int64_t fft_smem_max_n(apda_ctx *ctx);
 bool fft_f32_fast_supports(int64_t N);
 int launch_fft_f32_fast(apda_ctx *ctx, cudaStream_t st, const float *d_samples, int64_t n_samples, int64_t ld,
-                        int64_t batch, int64_t N, int flags, float *d_spec, const int *d_nv = nullptr);
+                        int64_t batch, int64_t N, int flags, float *d_spec, const int *d_nv = nullptr, bool half_out = false);
 void fft_f32_fast_release(apda_ctx *ctx);
 int launch_fused_f32(apda_ctx *ctx, cudaStream_t st, const float *d_samples, int64_t n_samples, int64_t ld, int64_t batch,
                      int64_t N, int flags, int flexible, double fs, const double *d_fs, int k, void *d_rec);

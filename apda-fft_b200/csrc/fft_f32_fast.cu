@@ -5,7 +5,10 @@
 
 namespace {
 
-template <int N, int CENTER, bool FULL>
+// HALF_OUT: only bins [0, N/2) are written - all the pickers ever read (utils/get_peak_prominence.py:159,
+// utils/get_peak_resolution.py:84); used where the spectrum is an internal workspace of the pipeline (apda_analyze_*),
+// never where the caller receives the spectrum (start_fft materialises N bins).  SURVEY 8d "half-spectrum pipeline".
+template <int N, int CENTER, bool FULL, bool HALF_OUT>
 __global__ void __launch_bounds__(Plan<N>::WPB *(N / 32), Plan<N>::MINB)
 fft_f32_fast_kernel(const float *__restrict__ samples, int n_samples, int64_t ld, int64_t batch,
                     const float2 *__restrict__ tw1,  // [R1][S1]: W_M^{c*k1}
@@ -48,12 +51,13 @@ fft_f32_fast_kernel(const float *__restrict__ samples, int n_samples, int64_t ld
         const float2 s1 = pfma(zb, cj, zk1), d1 = pfma(zb, ncj, zk1);
         const float2 t0 = cmul(d0, make_float2(w.x, w.y)), t1 = cmul(d1, make_float2(w.z, w.w));
         const float2 x0 = pfma(s0, hf, t0), x1 = pfma(s1, hf, t1);
-        const float2 y0 = pfma(s0, hf, make_float2(-t0.x, -t0.y)), y1 = pfma(s1, hf, make_float2(-t1.x, -t1.y));
         float4 lo4 = make_float4(x0.x, x0.y, x1.x, x1.y);
-        float4 hi4 = make_float4(y0.x, y0.y, y1.x, y1.y);
         if (p == 0) lo4.x = lo4.y = 0.f;  // reference: res[0] = 0
         out[p] = lo4;
-        out[M / 2 + p] = hi4;
+        if (!HALF_OUT) {
+            const float2 y0 = pfma(s0, hf, make_float2(-t0.x, -t0.y)), y1 = pfma(s1, hf, make_float2(-t1.x, -t1.y));
+            out[M / 2 + p] = make_float4(y0.x, y0.y, y1.x, y1.y);
+        }
     }
 }
 
@@ -117,18 +121,19 @@ static int fast_tables(apda_ctx *ctx, FastTables *out) {
 
 template <int N>
 static int launch_fast_n(apda_ctx *ctx, cudaStream_t st, const float *d_samples, int64_t n_samples, int64_t ld,
-                         int64_t batch, int flags, float *d_spec, const int *d_nv) {
+                         int64_t batch, int flags, float *d_spec, const int *d_nv, bool half_out) {
     using P = Plan<N>;
     FastTables ft;
     APDA_TRY(fast_tables<N>(ctx, &ft));
     const int threads = P::WPB * (N / 32);
     const int64_t blocks = (batch + P::WPB - 1) / P::WPB;
     const bool full = n_samples == N && (reinterpret_cast<uintptr_t>(d_samples) & 7u) == 0 && (ld & 1) == 0;
-    auto kern = flags == APDA_CENTER_MEDIAN
-                    ? (full ? fft_f32_fast_kernel<N, APDA_CENTER_MEDIAN, true> : fft_f32_fast_kernel<N, APDA_CENTER_MEDIAN, false>)
-                : flags == APDA_CENTER_MEAN
-                    ? (full ? fft_f32_fast_kernel<N, APDA_CENTER_MEAN, true> : fft_f32_fast_kernel<N, APDA_CENTER_MEAN, false>)
-                    : (full ? fft_f32_fast_kernel<N, APDA_CENTER_NONE, true> : fft_f32_fast_kernel<N, APDA_CENTER_NONE, false>);
+    void (*kern)(const float *, int, int64_t, int64_t, const float2 *, const float2 *, float2 *, const int *);
+#define APDA_K1(C, F) (half_out ? fft_f32_fast_kernel<N, C, F, true> : fft_f32_fast_kernel<N, C, F, false>)
+    kern = flags == APDA_CENTER_MEDIAN ? (full ? APDA_K1(APDA_CENTER_MEDIAN, true) : APDA_K1(APDA_CENTER_MEDIAN, false))
+           : flags == APDA_CENTER_MEAN ? (full ? APDA_K1(APDA_CENTER_MEAN, true) : APDA_K1(APDA_CENTER_MEAN, false))
+                                       : (full ? APDA_K1(APDA_CENTER_NONE, true) : APDA_K1(APDA_CENTER_NONE, false));
+#undef APDA_K1
     kern<<<(unsigned)blocks, threads, 0, st>>>(d_samples, (int)n_samples, ld, batch, ft.tw1, ft.twu,
                                                reinterpret_cast<float2 *>(d_spec), d_nv);
     ctx->launches++;
@@ -154,12 +159,12 @@ int fft_f32_fast_get_tables(apda_ctx *ctx, int64_t N, const float2 **tw1, const 
 bool fft_f32_fast_supports(int64_t N) { return N == 1024 || N == 2048 || N == 4096 || N == 8192; }
 
 int launch_fft_f32_fast(apda_ctx *ctx, cudaStream_t st, const float *d_samples, int64_t n_samples, int64_t ld,
-                        int64_t batch, int64_t N, int flags, float *d_spec, const int *d_nv) {
+                        int64_t batch, int64_t N, int flags, float *d_spec, const int *d_nv, bool half_out) {
     switch (N) {
-        case 1024: return launch_fast_n<1024>(ctx, st, d_samples, n_samples, ld, batch, flags, d_spec, d_nv);
-        case 2048: return launch_fast_n<2048>(ctx, st, d_samples, n_samples, ld, batch, flags, d_spec, d_nv);
-        case 4096: return launch_fast_n<4096>(ctx, st, d_samples, n_samples, ld, batch, flags, d_spec, d_nv);
-        case 8192: return launch_fast_n<8192>(ctx, st, d_samples, n_samples, ld, batch, flags, d_spec, d_nv);
+        case 1024: return launch_fast_n<1024>(ctx, st, d_samples, n_samples, ld, batch, flags, d_spec, d_nv, half_out);
+        case 2048: return launch_fast_n<2048>(ctx, st, d_samples, n_samples, ld, batch, flags, d_spec, d_nv, half_out);
+        case 4096: return launch_fast_n<4096>(ctx, st, d_samples, n_samples, ld, batch, flags, d_spec, d_nv, half_out);
+        case 8192: return launch_fast_n<8192>(ctx, st, d_samples, n_samples, ld, batch, flags, d_spec, d_nv, half_out);
     }
     apda_set_error("fft_f32_fast: unsupported N=%lld", (long long)N);
     return APDA_ERR_UNSUPPORTED;

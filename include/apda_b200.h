@@ -130,7 +130,9 @@ int apda_peaks_resolution_f32_host(apda_ctx *ctx, const float *h_spec, int64_t n
 /* ---- pipeline: samples -> records, spectra never leave HBM -------------------------------------------------
  * replaces the body of GT_FFT_v5.py:635-642 (start_fft followed by the picker selected by is_flexibile_structure).
  * flexible != 0 -> prominence picker, else resolution picker.  d_spec_ws: caller-provided spectrum workspace of
- * batch*2*N reals, or NULL to use the context's own. */
+ * batch*2*N reals (it then holds the N-bin spectra apda_fft_* would write), or NULL to use the context's own - in which
+ * case the fp32 FFT kernel only writes the bins [0, N/2) the pickers read (SURVEY.md 8d "half-spectrum pipeline":
+ * 3*s*N + 128 bytes of HBM traffic per window instead of 4*s*N + 128; same records). */
 int apda_analyze_f64_dev(apda_ctx *ctx, const double *d_samples, int64_t n_samples, int64_t ld, int64_t batch,
                          int64_t N, int flags, int flexible, double fs, const double *d_fs, int k, int rec_cap,
                          double *d_spec_ws, void *d_rec);

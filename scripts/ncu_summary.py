@@ -2,7 +2,10 @@
 """Summarise an ncu report (ncu --set full) into profiles/: one markdown table of the metrics the roofline numbers
 come from, plus profiles/traffic.json (DRAM bytes per launch of each kernel, consumed by bench.py's roofline.traffic).
 
-    python scripts/ncu_summary.py gpurun_out/prof.ncu-rep profiles/ncu_r1 [--windows 200000]
+    python scripts/ncu_summary.py gpurun_out/prof.ncu-rep profiles/ncu_r1 [--windows 200000] [--w <name regex>=<windows> ...]
+
+--w gives the windows per launch of the kernels whose name matches the regex (reports that hold launches of different
+batch sizes); --windows is the default for the others.
 """
 import csv
 import io
@@ -28,12 +31,21 @@ METRICS = [
     ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem wavefronts"),
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts"),
     ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe % (expected 0)"),
+    ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "fp64 pipe busy %"),
+    ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "fma pipe busy %"),
+    ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "alu pipe busy %"),
 ]
 
 
 def main():
     rep, out_prefix = sys.argv[1], sys.argv[2]
-    windows = int(sys.argv[sys.argv.index("--windows") + 1]) if "--windows" in sys.argv else None
+    default_windows = int(sys.argv[sys.argv.index("--windows") + 1]) if "--windows" in sys.argv else None
+    import re
+    wmap = []
+    for i, a in enumerate(sys.argv):
+        if a == "--w":
+            rx, _, cnt = sys.argv[i + 1].rpartition("=")
+            wmap.append((re.compile(rx), int(cnt)))
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
@@ -43,6 +55,7 @@ def main():
     traffic = {}
     for r in rows[2:]:
         name = r[hdr.index("Kernel Name")]
+        windows = next((cnt for rx, cnt in wmap if rx.search(name)), default_windows)
         lines += [f"## `{name[:140]}`", "", "| metric | value | unit |", "|---|---|---|"]
         vals = {}
         for key, label in METRICS:
@@ -50,6 +63,17 @@ def main():
                 i = hdr.index(key)
                 vals[key] = r[i]
                 lines.append(f"| {label} (`{key}`) | {r[i]} | {units[i]} |")
+        stalls = sorted(((float(r[i] or 0), h) for i, h in enumerate(hdr)
+                         if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio")),
+                        reverse=True)[:5]
+        lines.append("| top stall reasons (warps per issue) | " + ", ".join(
+            f"{h[len('smsp__average_warps_issue_stalled_'):-len('_per_issue_active.ratio')]} {v:.2f}" for v, h in stalls) + " | |")
+        if windows:
+            lines.append(f"| windows per launch | {windows} | |")
+            try:
+                lines.append(f"| warp instructions per window | {float(vals['smsp__inst_executed.sum']) / windows:.0f} | |")
+            except Exception:  # noqa: BLE001
+                pass
         try:
             def to_bytes(v, u):
                 v = float(v.replace(",", ""))
@@ -59,7 +83,6 @@ def main():
             entry = {"dram_bytes_per_launch": rd + wr, "read": rd, "write": wr, "windows": windows}
             if windows:
                 entry["dram_bytes_per_window"] = (rd + wr) / windows
-            import re
             m = re.search(r"(fft_f32_fast|fft_f64_fast|peaks_f32_fast|peaks_f64_fast|fft_smem|peaks)_kernel<\(?(?:int\))?(\d+)", name)
             if m and m.group(1) == "fft_f64_fast":      # templated on log2(N)
                 key = f"k1_f64_n{1 << int(m.group(2))}"

@@ -378,3 +378,33 @@ def test_multi_analyze_host_equals_single_context(dtype, an):
         apda_fft_b200.multi_analyze([ctxs[0], ctxs[0]], x, 125.0)
     for c in ctxs:
         c.close()
+
+
+def test_half_spectrum_pipeline_equals_full_pipeline(an):
+    """apda_analyze_f32_dev with the library's own workspace (K1 writes only bins [0, N/2)) gives the records of
+    K1 (N bins) + K3, byte for byte; a caller-provided workspace still receives all N bins."""
+    import torch
+    dev = torch.device("cuda:0")
+    an.use_stream(torch.cuda.current_stream(dev).cuda_stream)
+    try:
+        for n in (1024, 2048, 4096, 8192):
+            b = 777
+            x = torch.empty((b, n), dtype=torch.float32, device=dev)
+            an.synth_device(123, b, n, "f32", x.data_ptr())
+            spec = torch.zeros((b, n, 2), dtype=torch.float32, device=dev)
+            ws = torch.zeros((b, n, 2), dtype=torch.float32, device=dev)
+            rec_full = torch.zeros((b, 128), dtype=torch.uint8, device=dev)
+            rec_half = torch.zeros((b, 128), dtype=torch.uint8, device=dev)
+            rec_ws = torch.zeros((b, 128), dtype=torch.uint8, device=dev)
+            for flexible in (True, False):
+                k = 4 if flexible else 5
+                an.fft_device(x.data_ptr(), b, n, n, "f32", spec.data_ptr())
+                an.peaks_device(spec.data_ptr(), b, n, "f32", 125.0, rec_full.data_ptr(), flexible=flexible, k=k)
+                an.analyze_device(x.data_ptr(), b, n, n, "f32", 125.0, rec_half.data_ptr(), flexible=flexible, k=k)
+                an.analyze_device(x.data_ptr(), b, n, n, "f32", 125.0, rec_ws.data_ptr(), flexible=flexible, k=k,
+                                  d_spec_ws=ws.data_ptr())
+                torch.cuda.synchronize()
+                assert torch.equal(rec_full, rec_half) and torch.equal(rec_full, rec_ws), (n, flexible)
+                assert torch.equal(ws, spec), n          # all N bins in the caller's workspace
+    finally:
+        an.use_stream(None)
