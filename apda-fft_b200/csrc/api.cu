@@ -118,7 +118,6 @@ extern "C" int apda_ctx_create(int device, apda_ctx **out) {
     ctx->stream = ctx->own_stream;
     for (int i = 0; i < 2; ++i) {
         APDA_CUDA(cudaStreamCreateWithFlags(&ctx->pipe[i], cudaStreamNonBlocking));
-        APDA_CUDA(cudaEventCreateWithFlags(&ctx->pipe_done[i], cudaEventDisableTiming));
     }
     *out = ctx;
     return APDA_OK;
@@ -143,7 +142,6 @@ extern "C" int apda_ctx_destroy(apda_ctx *ctx) {
     for (int i = 0; i < 2; ++i) {
         cudaFree(ctx->ws_pipe[i]);
         if (ctx->pipe[i]) cudaStreamDestroy(ctx->pipe[i]);
-        if (ctx->pipe_done[i]) cudaEventDestroy(ctx->pipe_done[i]);
     }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;

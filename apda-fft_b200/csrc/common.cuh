@@ -28,7 +28,6 @@ struct apda_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;  // stream the _dev entry points enqueue on
     cudaStream_t pipe[2] = {nullptr, nullptr};
-    cudaEvent_t pipe_done[2] = {nullptr, nullptr};
     std::map<int64_t, TwiddleTables> twiddles;
     void *ws = nullptr;  // grow-only workspace for the _dev entry points (spectrum for analyze, mags for large N)
     size_t ws_bytes = 0;

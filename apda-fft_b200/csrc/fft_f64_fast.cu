@@ -219,9 +219,14 @@ __device__ __forceinline__ void middle_or_last_pass(double2 *s, const double2 *_
         const int w = t + T * g;                 // work item: lo = low S0 bits, hi = the rest
         const int lo = w & ((1 << S0) - 1), hi = w >> S0;
         const int base = (hi << (S0 + Q)) + lo;
+        // pad16(base + (r << S0)) = pad16(base) + r * (2^S0 + 2^(S0-4)) because S0 >= 4: one padded base per work item and
+        // compile-time offsets, instead of a shift and two adds per access
+        static_assert(S0 >= 4, "the padded offsets are linear in r only from the second pass on");
+        constexpr int RSTEP = (1 << S0) + (1 << (S0 - 4));
+        double2 *sp = s + pad16(base);
         double2 v[1 << Q];
 #pragma unroll
-        for (int r = 0; r < (1 << Q); ++r) v[r] = s[pad16(base + (r << S0))];
+        for (int r = 0; r < (1 << Q); ++r) v[r] = sp[r * RSTEP];
         stages<Q>(v, tw, S0, lo);
         if (LAST) {
 #pragma unroll
@@ -232,7 +237,7 @@ __device__ __forceinline__ void middle_or_last_pass(double2 *s, const double2 *_
             }
         } else {
 #pragma unroll
-            for (int r = 0; r < (1 << Q); ++r) s[pad16(base + (r << S0))] = v[r];
+            for (int r = 0; r < (1 << Q); ++r) sp[r * RSTEP] = v[r];
         }
     }
 }
@@ -260,20 +265,21 @@ fft_f64_fast_kernel(const double *__restrict__ samples, int n_samples, int64_t l
             const int i = t + T * u;
             ld_v[u] = i < n_samples ? __ldcs(x + i) : CUDART_INF;
         }
+        double *rp = raw + (t + (t >> 3));  // (t + T*u) + ((t + T*u) >> 3) = t + (t >> 3) + u * (T + T/8): T is a multiple of 8
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const int i = t + T * u;
-            raw[i + (i >> 3)] = ld_v[u];
-        }
+        for (int u = 0; u < 16; ++u) rp[u * (T + T / 8)] = ld_v[u];
     }
     __syncthreads();
     // work item hi = t of pass 0 owns outputs idx = 16*t + r, i.e. inputs bitrev(idx) = bitrev4(r) * N/16 + bitrev(t)
     const int tb = (int)(__brev((unsigned)t) >> (32 - (LOGN - 4)));
     double val[16];
+    {
+        const double *gp = raw + (tb + (tb >> 3));  // src + (src >> 3) with src = brev4(r) * N/16 + tb: linear in brev4(r)
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
-        const int src = ((int)(__brev((unsigned)r) >> 28) << (LOGN - 4)) + tb;
-        val[r] = raw[src + (src >> 3)];
+        for (int r = 0; r < 16; ++r) {
+            constexpr int RS = (1 << (LOGN - 4)) + (1 << (LOGN - 7));
+            val[r] = gp[(int)(__brev((unsigned)r) >> 28) * RS];
+        }
     }
     __syncthreads();  // raw is dead from here on (s aliases it)
     double med = 0.0;
@@ -283,7 +289,7 @@ fft_f64_fast_kernel(const double *__restrict__ samples, int n_samples, int64_t l
     for (int r = 0; r < 16; ++r) v[r] = make_double2(val[r] < CUDART_INF ? sub_rn(val[r], med) : 0.0, 0.0);
     stages<4>(v, tw, 0, 0);
 #pragma unroll
-    for (int r = 0; r < 16; ++r) s[pad16(16 * t + r)] = v[r];
+    for (int r = 0; r < 16; ++r) s[17 * t + r] = v[r];  // pad16(16 t + r) = 16 t + r + t
     __syncthreads();
 
     double2 *out = spec + win * (int64_t)N;
