@@ -492,3 +492,25 @@ def test_peer_wait_times_out_and_resets():
     finally:
         ctx.call("apda_peer_table_destroy", _p(base.value))
         ctx.close()
+
+
+def test_large_window_median_unaligned_rows(an):
+    """K2's bracket-select median reads the window with 128-bit loads: rows that start on every possible misalignment
+    (batch of windows with an odd number of samples, fp64 rows 8-byte and fp32 rows 4-byte aligned only) must give the
+    bit-exact spectrum (fp64) / the exactly median-centred transform (fp32), for short and long windows alike."""
+    rng = np.random.default_rng(123)
+    for n_samples, n in ((50_001, 1 << 16), (16_387, 1 << 15), (70_003, 1 << 17)):
+        x = np.round(rng.standard_normal((5, n_samples)) * 0.3 + 0.77 + 0.2 * np.sin(np.arange(n_samples) * 0.01), 6)
+        x[1] = np.round(x[1] * 0 + 0.5, 6)              # a constant window
+        x[2, ::2] = 0.25                                 # half the samples equal
+        got = an.fft(x, n_fft=n)
+        want = c_oracle.start_fft_batch(x, n_fft=n)
+        assert np.array_equal(got.view(np.float64), want.view(np.float64)), (n_samples, "fp64")
+        x32 = x.astype(np.float32)
+        got32 = an.fft(x32, n_fft=n)
+        for w in range(x.shape[0]):
+            centred = x32[w] - np.float32(np.median(x32[w]))
+            ref = np.fft.fft(np.concatenate([centred.astype(np.float64), np.zeros(n - n_samples)]))
+            ref[0] = 0
+            scale = np.abs(ref).max() + 1e-30
+            assert np.abs(got32[w] - ref).max() <= 2e-5 * scale + 1e-3, (n_samples, w)
