@@ -768,6 +768,7 @@ def run_configs(an, dev, stream, sampler, peak):
 
     out = {"peak_gbs": peak, "note": "inputs resident in HBM; L2 (126 MB) is far smaller than every working set except "
                                      "cfg4 2^20 (fp32: 12 MB, fp64: 25 MB), which is marked l2_resident"}
+    out["cfg1_3axis_n1024_f64_dropin"] = cfg1_latency()
     out["cfg2_10k_n4096_f64_flexible"], _ = batch(10_000, 4096, "f64", True)
     out["cfg3_100k_n8192_f32_rigid"], r32 = batch(100_000, 8192, "f32", False)
     out["cfg3_100k_n8192_f64_rigid"], r64 = batch(100_000, 8192, "f64", False)
@@ -806,6 +807,40 @@ def run_configs(an, dev, stream, sampler, peak):
                 "peak_idx": [int(v) for v in r["pk"]["idx"][: int(r["count"])]], "clocks": clk}
             del x, spec
             torch.cuda.empty_cache()
+    return out
+
+
+def cfg1_latency():
+    """BASELINE configs[0]: one 3-axis sensor (three independent single-axis windows, N = 1024, fp64) through the drop-in
+    modules exactly as the gateway calls them (start_fft then get_top_peaks_prominence on host lists), and the unmodified
+    reference on one host core beside it when oracle/_ref is present.  Latency, not throughput."""
+    drop = os.path.join(ROOT, "apda-fft_b200")
+    if drop not in sys.path:
+        sys.path.insert(0, drop)
+    import apda_fft_b200.synth as synth
+    from metrics.fft_iterativa import start_fft
+    from utils.get_peak_prominence import get_top_peaks_prominence
+    axes = [synth.fleet_window(w, 1024).tolist() for w in range(3)]
+    for ax in axes:
+        get_top_peaks_prominence(start_fft(ax, 125.0), 125.0)
+    reps = 50
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        peaks = [get_top_peaks_prominence(start_fft(ax, 125.0), 125.0) for ax in axes]
+    ms = (time.perf_counter() - t0) / reps * 1e3
+    out = {"workload": "3 axes x N=1024 fp64: start_fft + get_top_peaks_prominence through the drop-in modules (host lists "
+                       "in, list of dicts out; H2D, kernels, D2H and the Python conversions inside the clock)",
+           "ms_per_3axis_sensor": ms, "idx": [[p["idx"] for p in pk] for pk in peaks]}
+    try:
+        from oracle import ref_copy
+        if ref_copy.available():
+            ref = ref_copy.RefModules()
+            t0 = time.perf_counter()
+            want = [ref.get_top_peaks_prominence(ref.start_fft(ax, 125.0), 125.0) for ax in axes]
+            out["reference_ms_per_3axis_sensor_1_core"] = (time.perf_counter() - t0) * 1e3
+            out["equal_to_reference"] = bool(want == peaks)
+    except Exception as exc:  # noqa: BLE001 - the reference copy is optional
+        out["reference_note"] = f"{type(exc).__name__}: {exc}"
     return out
 
 
