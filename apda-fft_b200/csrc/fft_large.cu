@@ -140,18 +140,35 @@ large_head_kernel(const T *__restrict__ samples, int64_t n_samples, int64_t ld, 
     const int rows = 1 << q;
 
     const int logC = 31 - __clz(C);  // C is a power of two
-    for (int e = tid; e < (C << q); e += NT) {
-        const int c = e & (C - 1), jh = e >> logC;
-        const int64_t j = ((int64_t)jh << (n - q)) + lo0 + c;
-        V2 val;
-        if (COMPLEX_IN) {
-            val = reinterpret_cast<const V2 *>(samples)[win * N + j];
-        } else {
-            val.x = j < n_samples ? sub_rn(samples[win * ld + j], med) : T(0);
-            val.y = T(0);
+    // eight loads of a thread are issued before the first of them is used: the gather's rows are 2^(n-q) samples apart, so
+    // every load is its own DRAM burst and the pass lives on memory-level parallelism
+    constexpr int UNR = 8;
+    const int total = C << q;
+    for (int e0 = tid; e0 < total; e0 += NT * UNR) {
+        V2 val[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int e = e0 + u * NT;
+            const int c = e & (C - 1), jh = e >> logC;
+            const int64_t j = ((int64_t)jh << (n - q)) + lo0 + c;
+            val[u].x = T(0);
+            val[u].y = T(0);
+            if (e < total) {
+                if (COMPLEX_IN) val[u] = reinterpret_cast<const V2 *>(samples)[win * N + j];
+                else if (j < n_samples) val[u].x = samples[win * ld + j];
+            }
         }
-        const int il = (int)(__brev((unsigned)jh) >> (32 - q));
-        work[c * LDW + il] = val;
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int e = e0 + u * NT;
+            if (e < total) {
+                const int c = e & (C - 1), jh = e >> logC;
+                const int64_t j = ((int64_t)jh << (n - q)) + lo0 + c;
+                if (!COMPLEX_IN && j < n_samples) val[u].x = sub_rn(val[u].x, med);
+                const int il = (int)(__brev((unsigned)jh) >> (32 - q));
+                work[c * LDW + il] = val[u];
+            }
+        }
     }
     __syncthreads();
 
