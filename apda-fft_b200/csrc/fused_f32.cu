@@ -28,8 +28,11 @@ struct FusedLayout {
     static_assert(2 * T * (int)sizeof(float) + SLOT_CAP * (int)sizeof(Slot) <= FFT_BYTES, "tail scratch must fit the FFT buffer");
 };
 
+#ifndef APDA_FUSED_MINB
+#define APDA_FUSED_MINB 8  // resident CTAs per SM the N = 4096 instance is compiled for
+#endif
 template <int N, int CENTER, bool FULL, bool FLEX>
-__global__ void __launch_bounds__(N / 32, (N == 4096 ? 8 : N < 4096 ? 1024 / (N / 32) / 2 : 2))
+__global__ void __launch_bounds__(N / 32, (N == 4096 ? APDA_FUSED_MINB : N < 4096 ? 1024 / (N / 32) / 2 : 2))
 fused_f32_kernel(const float *__restrict__ samples, int n_samples, int64_t ld, int64_t batch,
                  const float2 *__restrict__ tw1, const float2 *__restrict__ twu, double df_all,
                  const double *__restrict__ d_fs, int k, unsigned char *__restrict__ recs) {

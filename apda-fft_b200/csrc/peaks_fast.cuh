@@ -23,7 +23,10 @@
 
 namespace {
 
-constexpr int kWPC = 2;  // windows (warps) per CTA
+#ifndef APDA_K3_WPC
+#define APDA_K3_WPC 2
+#endif
+constexpr int kWPC = APDA_K3_WPC;  // windows (warps) per CTA
 
 template <typename T>
 struct SlotT {
