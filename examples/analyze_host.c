@@ -7,6 +7,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "apda_b200.h"
 
@@ -37,8 +38,25 @@ int main(void) {
             printf("  idx %d (%.4f Hz) mag %.4f", rec[w].pk[a].idx, rec[w].pk[a].idx * (fs / N), rec[w].pk[a].mag);
         printf("\n");
     }
+    /* the same batch sharded over two contexts by one host process (several GPUs: one context per device; here two
+     * contexts of device 0): every shard's records land in its rows of the caller's table - no collective, no Python */
+    apda_ctx *second = NULL;
+    apda_peak_rec *rec2 = (apda_peak_rec *)calloc(B, sizeof(apda_peak_rec));
+    if (!rec2 || apda_ctx_create(0, &second) != APDA_OK) {
+        fprintf(stderr, "second context: %s\n", apda_last_error());
+        return 1;
+    }
+    apda_ctx *both[2] = {ctx, second};
+    rc = apda_multi_analyze_f32_host(both, 2, x, N, N, B, N, APDA_CENTER_MEDIAN, 1, fs, NULL, 4, 5, rec2);
+    if (rc != APDA_OK) {
+        fprintf(stderr, "apda_multi_analyze_f32_host: %s\n", apda_last_error());
+        return 1;
+    }
+    printf("multi: 2 contexts, table %s\n", memcmp(rec, rec2, sizeof(apda_peak_rec) * B) == 0 ? "identical" : "DIFFERENT");
+    apda_ctx_destroy(second);
     apda_ctx_destroy(ctx);
     free(x);
     free(rec);
+    free(rec2);
     return 0;
 }

@@ -718,6 +718,7 @@ def test_c_host_example_runs(tmp_path):
     assert len(rows) == 8
     for w, row in enumerate(rows):
         assert f"window {w}: 3 peaks" in row and "idx 252" in row and "idx 498" in row and f"idx {round(101.6 + w)}" in row, row
+    assert "multi: 2 contexts, table identical" in out      # apda_multi_analyze_f32_host from plain C
 
 
 @pytest.mark.parametrize("n_samples", [1 << 16, (1 << 16) - 1, 50_001])
