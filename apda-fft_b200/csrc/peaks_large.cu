@@ -1,11 +1,16 @@
 // K3 (large form) for power-of-two spectra with n >= 2^16 bins: the picker of one long window spread over the chip.
 //
-//   A  mags_kernel      one CTA per block of 1024 bins: magnitudes -> HBM, block max / min, double-double partial sums
-//   B  stats_kernel     one CTA: mean, sample sigma, threshold (same correctly rounded results as peaks.cu)
+//   A  mags_kernel      one warp per block of 1024 bins: magnitudes -> HBM, block max / min, double-double partial sums
+//   B  stats_kernel     one CTA: mean, sample sigma, threshold (same correctly rounded results as peaks.cu), and the
+//                       second summary level (max / min of every 32 blocks)
 //   C  hot_kernel       one CTA per block whose max exceeds the threshold: strict local maxima (flexible) or every
 //                       bin above the threshold (rigid) -> candidate list
-//   D  pick_*_kernel    one CTA of 32 warps: the reference's decision logic on the candidate list; prominence walks skip
-//                       whole 1024-bin blocks through the block max / min summaries (32 blocks per ballot)
+//   D  eval_kernel      (flexible) one warp per candidate, grid-wide: prominence, width, damping gate -> found list.
+//                       A prominence walk moves through three levels (bins, 1024-bin blocks, 32-block groups), 128
+//                       entries per step with four independent loads per lane, so a walk over a 2^23-bin half
+//                       spectrum is a handful of dependent memory round trips instead of hundreds
+//   E  pick_*_kernel    one CTA of 32 warps: the reference's ordering / exclusion logic on the found (flexible) or
+//                       candidate (rigid) list
 //
 // Decision semantics are those of peaks.cu (utils/get_peak_prominence.py:149-226, utils/get_peak_resolution.py:80-128).
 #include <algorithm>
@@ -19,88 +24,129 @@ constexpr int SB = 1024;  // bins per summary block
 
 struct LargeState {
     double mean, sd, thr;
-    int ncand, nfound, overflow, pad;
+    int ncand, nfound, overflow, tie;
 };
 
-template <typename T>
-__global__ void __launch_bounds__(256)
+// WPB warps per 1024-bin block: 1 for long spectra (block max / min need no shared memory, eight loads in flight per
+// lane), 8 for short ones (one block per CTA, so that a 2^16-point spectrum still spreads over 32 CTAs).  A CTA's eight
+// warps fold their double-double sums into one partial.
+constexpr int MAGS_WARPS = 8;
+template <typename T, int WPB>
+__global__ void __launch_bounds__(32 * MAGS_WARPS)
 mags_kernel(const typename vec2<T>::type *__restrict__ spec, T *__restrict__ mags, T *__restrict__ bmax,
-            T *__restrict__ bmin, dd *__restrict__ part) {
-    __shared__ dd red[16];
-    __shared__ T rmx[8], rmn[8];
-    const int tid = threadIdx.x;
-    const int64_t b0 = (int64_t)blockIdx.x * SB;
-    dd sx = {0.0, 0.0}, sxx = {0.0, 0.0};
-    T mx = T(0), mn = T(0);
+            T *__restrict__ bmin, dd *__restrict__ part, int nblk) {
+    constexpr int SEG = SB / WPB, PER_LANE = SEG / 32, UNR = PER_LANE < 8 ? PER_LANE : 8, BPC = MAGS_WARPS / WPB;
+    __shared__ dd red[2 * MAGS_WARPS];
+    __shared__ T rmx[MAGS_WARPS], rmn[MAGS_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    dd sx[2] = {{0.0, 0.0}, {0.0, 0.0}}, sxx[2] = {{0.0, 0.0}, {0.0, 0.0}};  // two independent chains per lane
+    for (int blk = blockIdx.x * BPC + warp / WPB; blk < nblk; blk += gridDim.x * BPC) {
+        const int64_t b0 = (int64_t)blk * SB + (warp % WPB) * SEG;
+        T mx = T(0), mn = T(0);
+#pragma unroll 1
+        for (int r = 0; r < PER_LANE / UNR; ++r) {
+            typename vec2<T>::type v[UNR];
 #pragma unroll
-    for (int u = 0; u < SB / 256; ++u) {
-        const int64_t i = b0 + tid + 256 * u;
-        const typename vec2<T>::type v = spec[i];
-        const T m = magnitude(v.x, v.y);
-        mags[i] = m;
-        mx = (u == 0 || m > mx) ? m : mx;
-        mn = (u == 0 || m < mn) ? m : mn;
-        const double d = (double)m;
-        if (sizeof(T) == 8) {
-            sx = dd_add_d(sx, d);
-            sxx = dd_add(sxx, two_prod(d, d));
-        } else {
-            sx.hi += d;
-            sxx.hi = __fma_rn(d, d, sxx.hi);
+            for (int u = 0; u < UNR; ++u) v[u] = spec[b0 + 32 * UNR * r + 32 * u + lane];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const T m = magnitude(v[u].x, v[u].y);
+                mags[b0 + 32 * UNR * r + 32 * u + lane] = m;
+                const bool first = r == 0 && u == 0;
+                mx = (first || m > mx) ? m : mx;
+                mn = (first || m < mn) ? m : mn;
+                const double d = (double)m;
+                if (sizeof(T) == 8) {
+                    sx[u & 1] = dd_add_d(sx[u & 1], d);
+                    sxx[u & 1] = dd_add(sxx[u & 1], two_prod(d, d));
+                } else {
+                    sx[u & 1].hi += d;
+                    sxx[u & 1].hi = __fma_rn(d, d, sxx[u & 1].hi);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const T a = __shfl_xor_sync(0xffffffffu, mx, o), b = __shfl_xor_sync(0xffffffffu, mn, o);
+            mx = a > mx ? a : mx;
+            mn = b < mn ? b : mn;
+        }
+        if (WPB == 1) {
+            if (lane == 0) {
+                bmax[blk] = mx;
+                bmin[blk] = mn;
+            }
+        } else {  // BPC == 1: every warp of the CTA is in this iteration
+            if (lane == 0) {
+                rmx[warp] = mx;
+                rmn[warp] = mn;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                for (int w = 1; w < MAGS_WARPS; ++w) {
+                    mx = rmx[w] > mx ? rmx[w] : mx;
+                    mn = rmn[w] < mn ? rmn[w] : mn;
+                }
+                bmax[blk] = mx;
+                bmin[blk] = mn;
+            }
+            __syncthreads();
         }
     }
-    sx = warp_sum_dd(sx);
-    sxx = warp_sum_dd(sxx);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const T a = __shfl_xor_sync(0xffffffffu, mx, o), b = __shfl_xor_sync(0xffffffffu, mn, o);
-        mx = a > mx ? a : mx;
-        mn = b < mn ? b : mn;
-    }
-    if ((tid & 31) == 0) {
-        red[tid >> 5] = sx;
-        red[8 + (tid >> 5)] = sxx;
-        rmx[tid >> 5] = mx;
-        rmn[tid >> 5] = mn;
+    const dd wx = warp_sum_dd(dd_add(sx[0], sx[1])), wxx = warp_sum_dd(dd_add(sxx[0], sxx[1]));
+    if (lane == 0) {
+        red[warp] = wx;
+        red[MAGS_WARPS + warp] = wxx;
     }
     __syncthreads();
     if (tid == 0) {
-        dd a = red[0], b = red[8];
-        for (int w = 1; w < 8; ++w) {
+        dd a = red[0], b = red[MAGS_WARPS];
+        for (int w = 1; w < MAGS_WARPS; ++w) {
             a = dd_add(a, red[w]);
-            b = dd_add(b, red[8 + w]);
-            mx = rmx[w] > mx ? rmx[w] : mx;
-            mn = rmn[w] < mn ? rmn[w] : mn;
+            b = dd_add(b, red[MAGS_WARPS + w]);
         }
         part[2 * blockIdx.x] = a;
         part[2 * blockIdx.x + 1] = b;
-        bmax[blockIdx.x] = mx;
-        bmin[blockIdx.x] = mn;
     }
 }
 
-__global__ void __launch_bounds__(256) stats_kernel(const dd *__restrict__ part, int nblk, int half, LargeState *st) {
-    __shared__ dd red[16];
-    const int tid = threadIdx.x;
+// npart <= 1024 partial sums and nblk block summaries -> mean / sigma / threshold and the 32-block group summaries
+template <typename T>
+__global__ void __launch_bounds__(1024)
+stats_kernel(const dd *__restrict__ part, int npart, const T *__restrict__ bmax, const T *__restrict__ bmin,
+             T *__restrict__ smax, T *__restrict__ smin, int nblk, int half, LargeState *st) {
+    __shared__ dd red[64];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < nblk; i += 1024) {  // nblk is a multiple of 32: a warp's lanes hold one group of 32 blocks
+        T mx = bmax[i], mn = bmin[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const T x = __shfl_xor_sync(0xffffffffu, mx, o), y = __shfl_xor_sync(0xffffffffu, mn, o);
+            mx = x > mx ? x : mx;
+            mn = y < mn ? y : mn;
+        }
+        if (lane == 0) {
+            smax[i >> 5] = mx;
+            smin[i >> 5] = mn;
+        }
+    }
     dd a = {0.0, 0.0}, b = {0.0, 0.0};
-    for (int i = tid; i < nblk; i += 256) {
+    for (int i = tid; i < npart; i += 1024) {
         a = dd_add(a, part[2 * i]);
         b = dd_add(b, part[2 * i + 1]);
     }
     a = warp_sum_dd(a);
     b = warp_sum_dd(b);
-    if ((tid & 31) == 0) {
-        red[tid >> 5] = a;
-        red[8 + (tid >> 5)] = b;
+    if (lane == 0) {
+        red[warp] = a;
+        red[32 + warp] = b;
     }
     __syncthreads();
+    if (warp == 0) {
+        a = warp_sum_dd(red[lane]);
+        b = warp_sum_dd(red[32 + lane]);
+    }
     if (tid == 0) {
-        a = red[0];
-        b = red[8];
-        for (int w = 1; w < 8; ++w) {
-            a = dd_add(a, red[w]);
-            b = dd_add(b, red[8 + w]);
-        }
         const double n = (double)half;
         const dd mean = dd_div_d(a, n);
         const dd ss = dd_add(b, dd_neg(dd_div_d(dd_mul(a, a), n)));
@@ -111,6 +157,7 @@ __global__ void __launch_bounds__(256) stats_kernel(const dd *__restrict__ part,
         st->ncand = 0;
         st->nfound = 0;
         st->overflow = 0;
+        st->tie = 0;
     }
 }
 
@@ -119,87 +166,79 @@ __global__ void __launch_bounds__(256)
 hot_kernel(const T *__restrict__ mags, const T *__restrict__ bmax, int half, LargeState *st, int *__restrict__ cand, int cap) {
     const double thr = st->thr;
     if (!((double)bmax[blockIdx.x] > thr)) return;
-    const int b0 = blockIdx.x * SB;
+    const int b0 = blockIdx.x * SB, lane = threadIdx.x & 31;
     for (int u = 0; u < SB / 256; ++u) {
         const int j = b0 + threadIdx.x + 256 * u;
         const T m = mags[j];
-        if (!((double)m > thr)) continue;
-        bool take = true;
-        if (FLEX) take = j >= 1 && j <= half - 2 && m > mags[j - 1] && m > mags[j + 1];
+        bool take = (double)m > thr;
         if (take) {
-            const int pos = atomicAdd(&st->ncand, 1);
-            if (pos < cap) cand[pos] = j;
-            else st->overflow = 1;
+            if (sizeof(T) == 4 && j >= 1 && j <= half - 2 && fp32_tie_top(mags, half, j, m, thr)) st->tie = 1;
+            if (FLEX) take = j >= 1 && j <= half - 2 && m > mags[j - 1] && m > mags[j + 1];
+        }
+        const unsigned takers = __ballot_sync(0xffffffffu, take);  // one counter update per warp
+        if (takers) {
+            int pos = 0;
+            if (lane == __ffs(takers) - 1) pos = atomicAdd(&st->ncand, __popc(takers));
+            pos = __shfl_sync(0xffffffffu, pos, __ffs(takers) - 1) + __popc(takers & ((1u << lane) - 1u));
+            if (take) {
+                if (pos < cap) cand[pos] = j;
+                else st->overflow = 1;
+            }
         }
     }
 }
 
-// one direction of the prominence walk over bins [lo_b, hi_b] of the magnitude array (32 bins per step)
-template <typename T, int DIR>
-__device__ __forceinline__ bool scan_bins(const T *mags, int lo_b, int hi_b, T p, T &floor_lane, int lane) {
-    if (DIR < 0) {
-        for (int base = hi_b; base >= lo_b; base -= 32) {
-            const int i = base - lane;
-            const bool valid = i >= lo_b;
-            const T v = valid ? mags[i] : p;
-            const unsigned higher = __ballot_sync(0xffffffffu, valid && v > p);
-            const int stop = higher ? (__ffs(higher) - 1) : 32;
-            if (lane < stop && v < floor_lane) floor_lane = v;
-            if (higher) return true;
+// One direction of a prominence walk over the entries [lo, hi] of one summary level: an entry with mx[i] > p stops the
+// walk, mn[i] of the entries in front of it lowers the floor (level 0: mx == mn == magnitudes).  128 entries per step,
+// four independent loads per lane.  Returns the stopping entry, or -1 when the range ends first (warp-uniform).
+template <typename T, int DIR, bool SAME>
+__device__ __forceinline__ int walk_level(const T *__restrict__ mx, const T *__restrict__ mn, int lo, int hi, T p, T &floor_lane,
+                                          int lane) {
+    constexpr int U = 4;
+    for (int base = DIR < 0 ? hi : lo; DIR < 0 ? base >= lo : base <= hi; base += DIR * 32 * U) {
+        T vx[U], vn[U];
+        bool valid[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = base + DIR * (lane + 32 * u);
+            valid[u] = DIR < 0 ? i >= lo : i <= hi;
+            vx[u] = valid[u] ? mx[i] : p;
+            vn[u] = SAME ? vx[u] : (valid[u] ? mn[i] : p);
         }
-    } else {
-        for (int base = lo_b; base <= hi_b; base += 32) {
-            const int i = base + lane;
-            const bool valid = i <= hi_b;
-            const T v = valid ? mags[i] : p;
-            const unsigned higher = __ballot_sync(0xffffffffu, valid && v > p);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned higher = __ballot_sync(0xffffffffu, valid[u] && vx[u] > p);
             const int stop = higher ? (__ffs(higher) - 1) : 32;
-            if (lane < stop && v < floor_lane) floor_lane = v;
-            if (higher) return true;
+            if (lane < stop && vn[u] < floor_lane) floor_lane = vn[u];
+            if (higher) return base + DIR * (stop + 32 * u);
         }
     }
-    return false;
+    return -1;
 }
 
-// utils/get_peak_prominence.py:32-54 with block summaries: whole 1024-bin blocks are skipped 32 at a time
+// utils/get_peak_prominence.py:32-54 over three levels: bins of the peak's own block, blocks of its own group, groups;
+// then back down into the group and the block where the walk stops
 template <typename T>
-__device__ T summary_prominence(const T *mags, const T *bmax, const T *bmin, int half, int j, int lane) {
+__device__ T summary_prominence(const T *mags, const T *bmax, const T *bmin, const T *smax, const T *smin, int half, int j,
+                                int lane) {
     const T p = mags[j];
-    const int nblk = half / SB, bj = j / SB;
+    const int nblk = half / SB, bj = j / SB, sj = bj >> 5, nsup = nblk >> 5;
     T fl = p, fr = p;
-    if (!scan_bins<T, -1>(mags, bj * SB, j - 1, p, fl, lane)) {
-        for (int base = bj - 1; base >= 0; base -= 32) {
-            const int b = base - lane;
-            const bool valid = b >= 0;
-            const unsigned higher = __ballot_sync(0xffffffffu, valid && bmax[b] > p);
-            const int stop = higher ? (__ffs(higher) - 1) : 32;
-            if (valid && lane < stop) {
-                const T m = bmin[b];
-                if (m < fl) fl = m;
-            }
-            if (higher) {
-                const int bs = base - stop;
-                scan_bins<T, -1>(mags, bs * SB, bs * SB + SB - 1, p, fl, lane);
-                break;
-            }
+    if (walk_level<T, -1, true>(mags, mags, bj * SB, j - 1, p, fl, lane) < 0) {
+        int b = walk_level<T, -1, false>(bmax, bmin, sj * 32, bj - 1, p, fl, lane);
+        if (b < 0) {
+            const int s = walk_level<T, -1, false>(smax, smin, 0, sj - 1, p, fl, lane);
+            if (s >= 0) b = walk_level<T, -1, false>(bmax, bmin, s * 32, s * 32 + 31, p, fl, lane);
         }
+        if (b >= 0) walk_level<T, -1, true>(mags, mags, b * SB, b * SB + SB - 1, p, fl, lane);
     }
-    if (!scan_bins<T, +1>(mags, j + 1, bj * SB + SB - 1, p, fr, lane)) {
-        for (int base = bj + 1; base < nblk; base += 32) {
-            const int b = base + lane;
-            const bool valid = b < nblk;
-            const unsigned higher = __ballot_sync(0xffffffffu, valid && bmax[b] > p);
-            const int stop = higher ? (__ffs(higher) - 1) : 32;
-            if (valid && lane < stop) {
-                const T m = bmin[b];
-                if (m < fr) fr = m;
-            }
-            if (higher) {
-                const int bs = base + stop;
-                scan_bins<T, +1>(mags, bs * SB, bs * SB + SB - 1, p, fr, lane);
-                break;
-            }
+    if (walk_level<T, +1, true>(mags, mags, j + 1, bj * SB + SB - 1, p, fr, lane) < 0) {
+        int b = walk_level<T, +1, false>(bmax, bmin, bj + 1, sj * 32 + 31, p, fr, lane);
+        if (b < 0) {
+            const int s = walk_level<T, +1, false>(smax, smin, sj + 1, nsup - 1, p, fr, lane);
+            if (s >= 0) b = walk_level<T, +1, false>(bmax, bmin, s * 32, s * 32 + 31, p, fr, lane);
         }
+        if (b >= 0) walk_level<T, +1, true>(mags, mags, b * SB, b * SB + SB - 1, p, fr, lane);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -210,22 +249,22 @@ __device__ T summary_prominence(const T *mags, const T *bmax, const T *bmin, int
     return sub_rn(p, fl > fr ? fl : fr);
 }
 
+// flexible picker, per-candidate half: prominence gate, half-power width, damping gate (utils/get_peak_prominence.py:171-204)
+constexpr int EVAL_THREADS = 256;
 template <typename T>
-__global__ void __launch_bounds__(1024)
-pick_flexible_kernel(const T *__restrict__ mags, const T *__restrict__ bmax, const T *__restrict__ bmin, int64_t n,
-                     int half, double fs_all, const double *__restrict__ fs_ptr, int k, int rec_cap, LargeState *st, const int *__restrict__ cand,
-                     Found *__restrict__ found, int cap, int *__restrict__ acc_slot, unsigned char *__restrict__ rec) {
-    __shared__ int nfound_s;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+__global__ void __launch_bounds__(EVAL_THREADS)
+eval_kernel(const T *__restrict__ mags, const T *__restrict__ bmax, const T *__restrict__ bmin, const T *__restrict__ smax,
+            const T *__restrict__ smin, int64_t n, int half, double fs_all, const double *__restrict__ fs_ptr, LargeState *st,
+            const int *__restrict__ cand, Found *__restrict__ found, int cap) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * EVAL_THREADS + threadIdx.x) >> 5, nwarp = (gridDim.x * EVAL_THREADS) >> 5;
     const int ncand = min(st->ncand, cap);
     const double fs = fs_ptr ? *fs_ptr : fs_all;
     const double df = div_rn(fs, (double)n);
     const double half_sd = mul_rn(0.5, st->sd);
-    if (tid == 0) nfound_s = 0;
-    __syncthreads();
-    for (int c = warp; c < ncand; c += 32) {
+    for (int c = warp; c < ncand; c += nwarp) {
         const int j = cand[c];
-        const T prom = summary_prominence<T>(mags, bmax, bmin, half, j, lane);
+        const T prom = summary_prominence<T>(mags, bmax, bmin, smax, smin, half, j, lane);
         if (!((double)prom > half_sd)) continue;
         const int bins = half_power_bins<T>(mags, half, prom, j);
         const double width_hz = mul_rn((double)bins, df);
@@ -234,7 +273,7 @@ pick_flexible_kernel(const T *__restrict__ mags, const T *__restrict__ bmax, con
         const double q = div_rn(fn, width_hz);
         const double damping = div_rn(1.0, mul_rn(2.0, q));
         if (0.001 <= damping && damping <= 0.07 && lane == 0) {
-            const int pos = atomicAdd(&nfound_s, 1);
+            const int pos = atomicAdd(&st->nfound, 1);
             Found f;
             f.rmag = round_dec4((double)mags[j]);
             f.prom = (double)prom;
@@ -243,7 +282,15 @@ pick_flexible_kernel(const T *__restrict__ mags, const T *__restrict__ bmax, con
             found[pos] = f;
         }
     }
-    __syncthreads();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024)
+pick_flexible_kernel(const T *__restrict__ mags, int64_t n, double fs_all, const double *__restrict__ fs_ptr, int k, int rec_cap,
+                     LargeState *st, const Found *__restrict__ found, int *__restrict__ acc_slot, unsigned char *__restrict__ rec) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double fs = fs_ptr ? *fs_ptr : fs_all;
+    const double df = div_rn(fs, (double)n);
     // order by (rounded magnitude desc, idx asc) one element at a time; block-wide arg-max per step
     __shared__ double bk[32];
     __shared__ int bi[32], be[32];
@@ -256,7 +303,7 @@ pick_flexible_kernel(const T *__restrict__ mags, const T *__restrict__ bmax, con
         prev_idx_s = -1;
     }
     __syncthreads();
-    const int nfound = nfound_s;
+    const int nfound = st->nfound;
     while (true) {
         const double prev_mag = prev_mag_s;
         const int prev_idx = prev_idx_s;
@@ -320,7 +367,7 @@ pick_flexible_kernel(const T *__restrict__ mags, const T *__restrict__ bmax, con
     }
     if (tid == 0) {
         const int na = na_s;
-        write_rec_header(rec, na, st->overflow ? 1 : 0);
+        write_rec_header(rec, na, (st->overflow ? APDA_STATUS_TRUNCATED : 0) | (st->tie ? APDA_STATUS_FP32_TIE : 0));
         for (int a = 0; a < rec_cap; ++a) {
             if (a < na) {
                 const Found f = found[acc_slot[a]];
@@ -415,13 +462,13 @@ pick_rigid_kernel(T *__restrict__ mags, int64_t n, int half, double fs_all, cons
     }
     if (tid == 0) {
         const int na = ctl[3];
-        write_rec_header(rec, na, st->overflow ? 1 : 0);
+        write_rec_header(rec, na, (st->overflow ? APDA_STATUS_TRUNCATED : 0) | (st->tie ? APDA_STATUS_FP32_TIE : 0));
         for (int a = na; a < rec_cap; ++a) write_rec_peak(rec, a, -1, 0, 0.0, 0.0);
     }
 }
 
 struct LargeLayout {
-    size_t mags, bmax, bmin, part, state, cand, found, acc, bytes;
+    size_t mags, bmax, bmin, smax, smin, part, state, cand, found, acc, bytes;
     int cap, nblk;
 };
 template <typename T>
@@ -438,7 +485,9 @@ LargeLayout large_layout(int64_t half) {
     l.mags = take((size_t)half * sizeof(T));
     l.bmax = take((size_t)l.nblk * sizeof(T));
     l.bmin = take((size_t)l.nblk * sizeof(T));
-    l.part = take((size_t)l.nblk * 2 * sizeof(dd));
+    l.smax = take((size_t)(l.nblk / 32) * sizeof(T));
+    l.smin = take((size_t)(l.nblk / 32) * sizeof(T));
+    l.part = take((size_t)1024 * 2 * sizeof(dd));
     l.state = take(sizeof(LargeState));
     l.cand = take((size_t)l.cap * sizeof(int));
     l.found = take((size_t)l.cap * sizeof(Found));
@@ -468,21 +517,30 @@ int launch_peaks_large(apda_ctx *ctx, cudaStream_t st, const T *d_spec, int64_t 
     char *base = reinterpret_cast<char *>(ws);
     T *mags = reinterpret_cast<T *>(base + l.mags);
     T *bmax = reinterpret_cast<T *>(base + l.bmax), *bmin = reinterpret_cast<T *>(base + l.bmin);
+    T *smax = reinterpret_cast<T *>(base + l.smax), *smin = reinterpret_cast<T *>(base + l.smin);
     dd *part = reinterpret_cast<dd *>(base + l.part);
     LargeState *state = reinterpret_cast<LargeState *>(base + l.state);
     int *cand = reinterpret_cast<int *>(base + l.cand);
     Found *found = reinterpret_cast<Found *>(base + l.found);
     int *acc = reinterpret_cast<int *>(base + l.acc);
+    // one warp per candidate; tone spectra have a handful, noise-like ones ~2 % of the bins
+    const int eval_ctas = (int)std::min<int64_t>((int64_t)ctx->sm_count * 8, std::max<int64_t>(1, l.cap / (EVAL_THREADS / 32)));
+    const int mags_ctas = l.nblk <= 1024 ? l.nblk : std::min(l.nblk / MAGS_WARPS, 1024);  // <= 1024 partial sums
     for (int64_t w = 0; w < batch; ++w) {
         const V2 *spec = reinterpret_cast<const V2 *>(d_spec) + w * n;
         unsigned char *rec = reinterpret_cast<unsigned char *>(d_rec) + w * APDA_REC_BYTES(rec_cap);
         const double *fs_ptr = d_fs ? d_fs + w : nullptr;
-        mags_kernel<T><<<l.nblk, 256, 0, st>>>(spec, mags, bmax, bmin, part);
-        stats_kernel<<<1, 256, 0, st>>>(part, l.nblk, (int)half, state);
+        if (l.nblk <= 1024)
+            mags_kernel<T, MAGS_WARPS><<<mags_ctas, 32 * MAGS_WARPS, 0, st>>>(spec, mags, bmax, bmin, part, l.nblk);
+        else
+            mags_kernel<T, 1><<<mags_ctas, 32 * MAGS_WARPS, 0, st>>>(spec, mags, bmax, bmin, part, l.nblk);
+        stats_kernel<T><<<1, 1024, 0, st>>>(part, mags_ctas, bmax, bmin, smax, smin, l.nblk, (int)half, state);
         if (flexible) {
             hot_kernel<T, true><<<l.nblk, 256, 0, st>>>(mags, bmax, (int)half, state, cand, l.cap);
-            pick_flexible_kernel<T><<<1, 1024, 0, st>>>(mags, bmax, bmin, n, (int)half, fs, fs_ptr, k, rec_cap, state, cand, found,
-                                                        l.cap, acc, rec);
+            eval_kernel<T><<<eval_ctas, EVAL_THREADS, 0, st>>>(mags, bmax, bmin, smax, smin, n, (int)half, fs, fs_ptr, state, cand,
+                                                              found, l.cap);
+            pick_flexible_kernel<T><<<1, 1024, 0, st>>>(mags, n, fs, fs_ptr, k, rec_cap, state, found, acc, rec);
+            ctx->launches += 1;
         } else {
             hot_kernel<T, false><<<l.nblk, 256, 0, st>>>(mags, bmax, (int)half, state, cand, l.cap);
             pick_rigid_kernel<T><<<1, 1024, 0, st>>>(mags, n, (int)half, fs, fs_ptr, k, rec_cap, state, cand, l.cap, acc, rec);

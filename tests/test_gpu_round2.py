@@ -514,3 +514,66 @@ def test_large_window_median_unaligned_rows(an):
             ref[0] = 0
             scale = np.abs(ref).max() + 1e-30
             assert np.abs(got32[w] - ref).max() <= 2e-5 * scale + 1e-3, (n_samples, w)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# K3 large form: three-level prominence walks (bins / 1024-bin blocks / 32-block groups), grid-wide evaluation
+# ---------------------------------------------------------------------------------------------------------------
+def _hump_spectrum(log2n, seed):
+    """Picker-only spectrum: a noise floor with wide triangular humps placed so that walks stop in the peak's own
+    block, in another block of its own group, in another group, and at either end of the spectrum."""
+    n = 1 << log2n
+    half = n // 2
+    rng = np.random.default_rng(seed)
+    m = 0.5 + rng.uniform(0.0, 1.0, half)
+    i = np.arange(half, dtype=np.float64)
+
+    def hump(centre, height, radius):
+        np.maximum(m, height * (1.0 - np.abs(i - centre) / radius), out=m)
+
+    hump(700, 60.0, 300)                         # near the left end: the left walk runs off the spectrum
+    hump(40_000, 80.0, 2_000)                    # same group as the next one (blocks 39 and 41)
+    hump(42_500, 70.0, 1_500)
+    hump(half // 2 + 1_025, 95.0, half // 64)    # the highest: both walks cross every group
+    hump(half // 2 + 3 * (half // 8), 85.0, half // 96)
+    hump(half - 900, 65.0, 500)                  # right end
+    m[0] = 0.0
+    z = np.zeros((1, n), dtype=np.complex128)
+    z[0, :half] = m
+    return z
+
+
+@pytest.mark.parametrize("log2n", [20, 22])
+def test_peaks_large_three_level_walks(log2n, an):
+    n = 1 << log2n
+    z = _hump_spectrum(log2n, log2n)
+    for dt in (np.complex128, np.complex64):
+        for flexible in (True, False):
+            fast = an.peaks(z.astype(dt), 250.0, flexible=flexible)
+            an.ctx.set_generic_only(True)
+            try:
+                slow = an.peaks(z.astype(dt), 250.0, flexible=flexible)
+            finally:
+                an.ctx.set_generic_only(False)
+            assert fast.tobytes() == slow.tobytes(), (log2n, flexible, dt)
+            assert int(fast[0]["count"]) >= 3 and int(fast[0]["status"]) == 0
+    if log2n == 20:      # the reference-equivalent pure-Python picker is slow at these lengths: once is enough
+        assert _dicts(an.peaks(z, 250.0, flexible=True)[0], 250.0, n, True) == c_oracle.peaks_prominence(z[0], 250.0)
+        assert _dicts(an.peaks(z, 250.0, flexible=False)[0], 250.0, n, False) == c_oracle.peaks_resolution(z[0], 250.0)
+
+
+def test_peaks_large_reports_fp32_tie(an):
+    """The large form flags an fp32 plateau of two equal top bins like the windowed kernels do."""
+    from apda_fft_b200 import _cabi
+    n = 1 << 17
+    z = _hump_spectrum(17, 5).astype(np.complex64)
+    z[0, 30_000] = z[0, 30_001] = 200.0
+    for flexible in (True, False):
+        fast = an.peaks(z, 250.0, flexible=flexible)
+        an.ctx.set_generic_only(True)
+        try:
+            slow = an.peaks(z, 250.0, flexible=flexible)
+        finally:
+            an.ctx.set_generic_only(False)
+        assert int(fast[0]["status"]) & _cabi.STATUS_FP32_TIE and int(slow[0]["status"]) & _cabi.STATUS_FP32_TIE
+        assert fast.tobytes() == slow.tobytes()
