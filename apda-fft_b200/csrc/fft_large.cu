@@ -24,6 +24,10 @@
 
 #include "common.cuh"
 
+#ifndef APDA_K2_HEAD_UNR
+#define APDA_K2_HEAD_UNR 8  // gather loads in flight per thread in the head pass
+#endif
+
 namespace {
 
 constexpr int kThreads = 512;  // default CTA size; the pass kernels are templated on it (NT)
@@ -142,7 +146,7 @@ large_head_kernel(const T *__restrict__ samples, int64_t n_samples, int64_t ld, 
     const int logC = 31 - __clz(C);  // C is a power of two
     // eight loads of a thread are issued before the first of them is used: the gather's rows are 2^(n-q) samples apart, so
     // every load is its own DRAM burst and the pass lives on memory-level parallelism
-    constexpr int UNR = 8;
+    constexpr int UNR = APDA_K2_HEAD_UNR;
     const int total = C << q;
     for (int e0 = tid; e0 < total; e0 += NT * UNR) {
         V2 val[UNR];

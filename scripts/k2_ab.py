@@ -79,11 +79,13 @@ def main():
     ap.add_argument("--child", action="store_true")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "k2_ab.json"))
     ap.add_argument("--only", default="")
+    ap.add_argument("--libs", nargs="*", default=[], help="library builds to compare (APDA_LIB) instead of the env variants")
     args = ap.parse_args()
     if args.child:
         return child()
     results = {}
-    for name, env in VARIANTS.items():
+    variants = {os.path.basename(p): {"APDA_LIB": os.path.abspath(p)} for p in args.libs} if args.libs else VARIANTS
+    for name, env in variants.items():
         if args.only and args.only not in name:
             continue
         res = subprocess.run([sys.executable, os.path.abspath(__file__), "--child"], env=dict(os.environ, **env),

@@ -557,6 +557,17 @@ def test_peaks_large_three_level_walks(log2n, an):
                 an.ctx.set_generic_only(False)
             assert fast.tobytes() == slow.tobytes(), (log2n, flexible, dt)
             assert int(fast[0]["count"]) >= 3 and int(fast[0]["status"]) == 0
+    # any k, several windows per call (the scratch of the large form is reused window after window)
+    z2 = np.concatenate([z, _hump_spectrum(log2n, 77)])
+    for flexible in (True, False):
+        fast = an.peaks(z2, 250.0, flexible=flexible, k=12)
+        an.ctx.set_generic_only(True)
+        try:
+            slow = an.peaks(z2, 250.0, flexible=flexible, k=12)
+        finally:
+            an.ctx.set_generic_only(False)
+        assert fast.tobytes() == slow.tobytes() and int(fast[1]["count"]) >= 4, (log2n, flexible)
+        assert fast[0].tobytes() == an.peaks(z, 250.0, flexible=flexible, k=12)[0].tobytes()
     if log2n == 20:      # the reference-equivalent pure-Python picker is slow at these lengths: once is enough
         assert _dicts(an.peaks(z, 250.0, flexible=True)[0], 250.0, n, True) == c_oracle.peaks_prominence(z[0], 250.0)
         assert _dicts(an.peaks(z, 250.0, flexible=False)[0], 250.0, n, False) == c_oracle.peaks_resolution(z[0], 250.0)
