@@ -50,6 +50,14 @@ int apda_reserve(void **buf, size_t *have, size_t need) {
     return APDA_OK;
 }
 
+int apda_pdl_mask() {
+    static const int mask = [] {
+        const char *e = getenv("APDA_PDL");
+        return e && e[0] ? atoi(e) : 15;
+    }();
+    return mask;
+}
+
 int apda_func_smem(const void *kernel, int device, size_t bytes) {
     static std::mutex mu;
     static std::map<std::pair<int, const void *>, size_t> done;

@@ -63,6 +63,33 @@ int apda_cuda_fail(cudaError_t e, const char *what);
         if (_s != APDA_OK) return _s;  \
     } while (0)
 
+// ---- programmatic dependent launch (chains of short dependent kernels: K2's median + passes, K3-large) ---------------
+// A kernel launched through apda_launch_pdl may become resident while the kernel in front of it in the stream drains
+// (that kernel lets it go with pdl_trigger(), or implicitly when it ends); it must call pdl_wait() before its first
+// global-memory access: the wait returns when the kernel in front has completed and its writes are visible.  Both
+// instructions are no-ops in a kernel launched the ordinary way.  APDA_PDL=<mask> selects the kernel groups that get the attribute (0: none; A/B runs).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+enum { APDA_PDL_MEDIAN = 1, APDA_PDL_HEAD = 2, APDA_PDL_TAIL = 4, APDA_PDL_K3 = 8 };
+int apda_pdl_mask();  // APDA_PDL environment variable (default: every group)
+template <typename... KArgs, typename... Args>
+inline cudaError_t apda_launch_pdl(int group, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                   Args &&...args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = (apda_pdl_mask() & group) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
+}
+
 int apda_get_twiddles(apda_ctx *ctx, int64_t N, TwiddleTables *out);
 int apda_reserve(void **buf, size_t *have, size_t need);
 // cudaFuncAttributeMaxDynamicSharedMemorySize, set once per (device, kernel): the attribute call is a driver round trip that

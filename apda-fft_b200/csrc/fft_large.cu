@@ -134,6 +134,8 @@ large_head_kernel(const T *__restrict__ samples, int64_t n_samples, int64_t ld, 
                   const T *__restrict__ med_ptr) {
     using V2 = typename vec2<T>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_trigger();
+    pdl_wait();
     V2 *work = reinterpret_cast<V2 *>(smem_raw);
     const int LDW = (1 << q) + 1;
     const int tid = threadIdx.x;
@@ -193,6 +195,8 @@ large_tail_kernel(typename vec2<T>::type *__restrict__ spec, int n, int s0, int 
                   const typename vec2<T>::type *__restrict__ tw, int zero_dc) {
     using V2 = typename vec2<T>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_trigger();
+    pdl_wait();
     V2 *tile = reinterpret_cast<V2 *>(smem_raw);
     const int LD = C + 1;
     const int tid = threadIdx.x;
@@ -249,10 +253,12 @@ large_tail_tma_kernel(const __grid_constant__ CUtensorMap tmap, int n, int s0, i
     const int c0 = (int)(2 * lo0), c2 = (int)((int64_t)blockIdx.y * n_hi + hi);
     const uint32_t bar_a = smem_u32(&bar);
 
+    pdl_trigger();
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    pdl_wait();  // the pass in front wrote this tile
     __syncthreads();
     if (tid == 0) {
         const uint32_t bytes = (uint32_t)((size_t)rows * C * sizeof(V2));
@@ -513,6 +519,7 @@ __global__ void __launch_bounds__(1024) br_sample_kernel(const T *__restrict__ x
     __shared__ unsigned wt[32];
     __shared__ T red_min[32], red_max[32];
     __shared__ int s_a, s_b;
+    pdl_trigger();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int S = (int)(n < kBrSample ? n : kBrSample);
     const int64_t g = n / S;  // stratum size (>= 1)
@@ -634,7 +641,9 @@ template <typename T>
 __global__ void __launch_bounds__(kBrThreads) br_count_kernel(const T *__restrict__ x, int64_t n, BracketState<T> *st) {
     constexpr int E = 4 * 16 / (int)sizeof(T);
     __shared__ unsigned h[kBrBuckets];
+    pdl_trigger();
     for (int i = threadIdx.x; i < kBrBuckets; i += kBrThreads) h[i] = 0;
+    pdl_wait();  // the bracket comes from br_sample_kernel
     __syncthreads();
     const T lo = st->lo, hi = st->hi, scale = st->scale;
     unsigned below = 0;
@@ -675,6 +684,8 @@ __global__ void __launch_bounds__(kBrThreads) br_compact_kernel(const T *__restr
     __shared__ long long s_rank;
     __shared__ unsigned long long blk[3][kBrThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_trigger();
+    pdl_wait();
     // ---- pick: which region holds rank (n-1)/2, and the rank inside it (every CTA derives the same answer) ----------
     {
         unsigned long long mine = 0;
@@ -797,6 +808,8 @@ __global__ void __launch_bounds__(1024) br_finish_kernel(const T *__restrict__ b
     __shared__ unsigned wt[32];
     __shared__ unsigned long long s_prefix, s_mask, s_le, s_above, s_lo;
     __shared__ long long s_rank;
+    pdl_trigger();
+    pdl_wait();
     const long long m = (long long)st->m;
     const long long rank0 = st->rank;
     if (threadIdx.x == 0) {
@@ -913,9 +926,9 @@ int large_median(apda_ctx *ctx, cudaStream_t st, const T *d_x, int64_t n, void *
     constexpr int64_t per_cta = (int64_t)kBrThreads * 4 * (16 / (int)sizeof(T));  // samples per CTA and trip
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + per_cta - 1) / per_cta, (int64_t)ctx->sm_count * 8));
     br_sample_kernel<T><<<1, 1024, 0, st>>>(d_x, n, state);
-    br_count_kernel<T><<<grid, kBrThreads, 0, st>>>(d_x, n, state);
-    br_compact_kernel<T><<<grid, kBrThreads, 0, st>>>(d_x, n, state, d_bucket);
-    br_finish_kernel<T><<<1, 1024, 0, st>>>(d_bucket, state, n, d_med);
+    APDA_CUDA(apda_launch_pdl(APDA_PDL_MEDIAN, br_count_kernel<T>, dim3(grid), dim3(kBrThreads), 0, st, d_x, n, state));
+    APDA_CUDA(apda_launch_pdl(APDA_PDL_MEDIAN, br_compact_kernel<T>, dim3(grid), dim3(kBrThreads), 0, st, d_x, n, state, d_bucket));
+    APDA_CUDA(apda_launch_pdl(APDA_PDL_MEDIAN, br_finish_kernel<T>, dim3(1), dim3(1024), 0, st, (const T *)d_bucket, state, n, d_med));
     ctx->launches += 4;
     APDA_CUDA(cudaGetLastError());
     return APDA_OK;
@@ -989,11 +1002,19 @@ static K2Tune k2_tune() {
     return t;
 }
 
+// A pass whose grid fits the chip in one wave is launched the ordinary way: its dependent's CTAs would become resident
+// at once and (measured, 2^20: 23 -> 39 us for the two passes) slow the pass down; with several waves the dependent
+// only enters while the last wave drains (2^22: 71 -> 65 us, 2^24: 240 -> 235 us).
+static int pass_pdl_group(const apda_ctx *ctx, dim3 grid, int group) {
+    return (int64_t)grid.x * grid.y > 3 * (int64_t)ctx->sm_count ? group : 0;
+}
+
 template <typename T, int NT, int MINB>
 static int launch_tail_tma(apda_ctx *ctx, cudaStream_t st, dim3 grid, size_t smem, const CUtensorMap &tm, int n, int s0, int q, int C,
                            const typename vec2<T>::type *twp, int zero_dc) {
     APDA_FUNC_SMEM(ctx, (large_tail_tma_kernel<T, NT, MINB>), smem);
-    large_tail_tma_kernel<T, NT, MINB><<<grid, NT, smem, st>>>(tm, n, s0, q, C, twp, zero_dc);
+    APDA_CUDA(apda_launch_pdl(pass_pdl_group(ctx, grid, APDA_PDL_TAIL), large_tail_tma_kernel<T, NT, MINB>, grid, dim3(NT), smem, st, tm, n,
+                              s0, q, C, twp, zero_dc));
     return APDA_OK;
 }
 
@@ -1001,7 +1022,8 @@ template <typename T, bool CPLX, int NT>
 static int launch_head(apda_ctx *ctx, cudaStream_t st, dim3 grid, size_t smem, const T *d_samples, int64_t n_samples, int64_t ld, int n, int q,
                        int C, const typename vec2<T>::type *twp, typename vec2<T>::type *spec, const T *d_med) {
     APDA_FUNC_SMEM(ctx, (large_head_kernel<T, CPLX, NT>), smem);
-    large_head_kernel<T, CPLX, NT><<<grid, NT, smem, st>>>(d_samples, n_samples, ld, n, q, C, twp, spec, d_med);
+    APDA_CUDA(apda_launch_pdl(pass_pdl_group(ctx, grid, APDA_PDL_HEAD), large_head_kernel<T, CPLX, NT>, grid, dim3(NT), smem, st, d_samples,
+                              n_samples, ld, n, q, C, twp, spec, d_med));
     return APDA_OK;
 }
 
@@ -1091,7 +1113,8 @@ int launch_fft_large(apda_ctx *ctx, cudaStream_t st, const T *d_samples, int64_t
                 return APDA_ERR_UNSUPPORTED;
             }
             APDA_FUNC_SMEM(ctx, large_tail_kernel<T>, smem);
-            large_tail_kernel<T><<<grid, kThreads, smem, st>>>(reinterpret_cast<V2 *>(d_spec), n, s0, q, C, twp, zero_dc);
+            APDA_CUDA(apda_launch_pdl(pass_pdl_group(ctx, grid, APDA_PDL_TAIL), large_tail_kernel<T>, grid, dim3(kThreads), smem, st,
+                                      reinterpret_cast<V2 *>(d_spec), n, s0, q, C, twp, zero_dc));
         }
         ctx->launches++;
         APDA_CUDA(cudaGetLastError());

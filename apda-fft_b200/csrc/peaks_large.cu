@@ -38,6 +38,8 @@ mags_kernel(const typename vec2<T>::type *__restrict__ spec, T *__restrict__ mag
     constexpr int SEG = SB / WPB, PER_LANE = SEG / 32, UNR = PER_LANE < 8 ? PER_LANE : 8, BPC = MAGS_WARPS / WPB;
     __shared__ dd red[2 * MAGS_WARPS];
     __shared__ T rmx[MAGS_WARPS], rmn[MAGS_WARPS];
+    pdl_trigger();
+    pdl_wait();  // the spectrum usually comes from the kernel in front (K2's last pass)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     dd sx[2] = {{0.0, 0.0}, {0.0, 0.0}}, sxx[2] = {{0.0, 0.0}, {0.0, 0.0}};  // two independent chains per lane
     for (int blk = blockIdx.x * BPC + warp / WPB; blk < nblk; blk += gridDim.x * BPC) {
@@ -116,6 +118,8 @@ __global__ void __launch_bounds__(1024)
 stats_kernel(const dd *__restrict__ part, int npart, const T *__restrict__ bmax, const T *__restrict__ bmin,
              T *__restrict__ smax, T *__restrict__ smin, int nblk, int half, LargeState *st) {
     __shared__ dd red[64];
+    pdl_trigger();
+    pdl_wait();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < nblk; i += 1024) {  // nblk is a multiple of 32: a warp's lanes hold one group of 32 blocks
         T mx = bmax[i], mn = bmin[i];
@@ -164,6 +168,8 @@ stats_kernel(const dd *__restrict__ part, int npart, const T *__restrict__ bmax,
 template <typename T, bool FLEX>
 __global__ void __launch_bounds__(256)
 hot_kernel(const T *__restrict__ mags, const T *__restrict__ bmax, int half, LargeState *st, int *__restrict__ cand, int cap) {
+    pdl_trigger();
+    pdl_wait();
     const double thr = st->thr;
     if (!((double)bmax[blockIdx.x] > thr)) return;
     const int b0 = blockIdx.x * SB, lane = threadIdx.x & 31;
@@ -256,6 +262,8 @@ __global__ void __launch_bounds__(EVAL_THREADS)
 eval_kernel(const T *__restrict__ mags, const T *__restrict__ bmax, const T *__restrict__ bmin, const T *__restrict__ smax,
             const T *__restrict__ smin, int64_t n, int half, double fs_all, const double *__restrict__ fs_ptr, LargeState *st,
             const int *__restrict__ cand, Found *__restrict__ found, int cap) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * EVAL_THREADS + threadIdx.x) >> 5, nwarp = (gridDim.x * EVAL_THREADS) >> 5;
     const int ncand = min(st->ncand, cap);
@@ -288,6 +296,8 @@ template <typename T>
 __global__ void __launch_bounds__(1024)
 pick_flexible_kernel(const T *__restrict__ mags, int64_t n, double fs_all, const double *__restrict__ fs_ptr, int k, int rec_cap,
                      LargeState *st, const Found *__restrict__ found, int *__restrict__ acc_slot, unsigned char *__restrict__ rec) {
+    pdl_trigger();
+    pdl_wait();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double fs = fs_ptr ? *fs_ptr : fs_all;
     const double df = div_rn(fs, (double)n);
@@ -386,6 +396,8 @@ pick_rigid_kernel(T *__restrict__ mags, int64_t n, int half, double fs_all, cons
     __shared__ double best_m[32];
     __shared__ int best_j[32];
     __shared__ int ctl[4];
+    pdl_trigger();
+    pdl_wait();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nhot = min(st->ncand, cap);
     const double thr = st->thr;
@@ -530,20 +542,25 @@ int launch_peaks_large(apda_ctx *ctx, cudaStream_t st, const T *d_spec, int64_t 
         const V2 *spec = reinterpret_cast<const V2 *>(d_spec) + w * n;
         unsigned char *rec = reinterpret_cast<unsigned char *>(d_rec) + w * APDA_REC_BYTES(rec_cap);
         const double *fs_ptr = d_fs ? d_fs + w : nullptr;
-        if (l.nblk <= 1024)
-            mags_kernel<T, MAGS_WARPS><<<mags_ctas, 32 * MAGS_WARPS, 0, st>>>(spec, mags, bmax, bmin, part, l.nblk);
-        else
-            mags_kernel<T, 1><<<mags_ctas, 32 * MAGS_WARPS, 0, st>>>(spec, mags, bmax, bmin, part, l.nblk);
-        stats_kernel<T><<<1, 1024, 0, st>>>(part, mags_ctas, bmax, bmin, smax, smin, l.nblk, (int)half, state);
+        const dim3 mg(mags_ctas), mb(32 * MAGS_WARPS), hg(l.nblk);
+        if (l.nblk <= 1024) APDA_CUDA(apda_launch_pdl(APDA_PDL_K3, mags_kernel<T, MAGS_WARPS>, mg, mb, 0, st, spec, mags, bmax, bmin, part, l.nblk));
+        else APDA_CUDA(apda_launch_pdl(APDA_PDL_K3, mags_kernel<T, 1>, mg, mb, 0, st, spec, mags, bmax, bmin, part, l.nblk));
+        APDA_CUDA(apda_launch_pdl(APDA_PDL_K3, stats_kernel<T>, dim3(1), dim3(1024), 0, st, (const dd *)part, mags_ctas, (const T *)bmax,
+                                  (const T *)bmin, smax, smin, l.nblk, (int)half, state));
         if (flexible) {
-            hot_kernel<T, true><<<l.nblk, 256, 0, st>>>(mags, bmax, (int)half, state, cand, l.cap);
-            eval_kernel<T><<<eval_ctas, EVAL_THREADS, 0, st>>>(mags, bmax, bmin, smax, smin, n, (int)half, fs, fs_ptr, state, cand,
-                                                              found, l.cap);
-            pick_flexible_kernel<T><<<1, 1024, 0, st>>>(mags, n, fs, fs_ptr, k, rec_cap, state, found, acc, rec);
+            APDA_CUDA(apda_launch_pdl(APDA_PDL_K3, hot_kernel<T, true>, hg, dim3(256), 0, st, (const T *)mags, (const T *)bmax, (int)half, state, cand,
+                                      l.cap));
+            APDA_CUDA(apda_launch_pdl(APDA_PDL_K3, eval_kernel<T>, dim3(eval_ctas), dim3(EVAL_THREADS), 0, st, (const T *)mags, (const T *)bmax,
+                                      (const T *)bmin, (const T *)smax, (const T *)smin, n, (int)half, fs, fs_ptr, state,
+                                      (const int *)cand, found, l.cap));
+            APDA_CUDA(apda_launch_pdl(APDA_PDL_K3, pick_flexible_kernel<T>, dim3(1), dim3(1024), 0, st, (const T *)mags, n, fs, fs_ptr, k, rec_cap,
+                                      state, (const Found *)found, acc, rec));
             ctx->launches += 1;
         } else {
-            hot_kernel<T, false><<<l.nblk, 256, 0, st>>>(mags, bmax, (int)half, state, cand, l.cap);
-            pick_rigid_kernel<T><<<1, 1024, 0, st>>>(mags, n, (int)half, fs, fs_ptr, k, rec_cap, state, cand, l.cap, acc, rec);
+            APDA_CUDA(apda_launch_pdl(APDA_PDL_K3, hot_kernel<T, false>, hg, dim3(256), 0, st, (const T *)mags, (const T *)bmax, (int)half, state, cand,
+                                      l.cap));
+            APDA_CUDA(apda_launch_pdl(APDA_PDL_K3, pick_rigid_kernel<T>, dim3(1), dim3(1024), 0, st, mags, n, (int)half, fs, fs_ptr, k, rec_cap, state,
+                                      (const int *)cand, l.cap, acc, rec));
         }
         ctx->launches += 4;
     }

@@ -20,6 +20,11 @@ sys.path.insert(0, ROOT)
 
 VARIANTS = {
     "default": {},
+    "no PDL": {"APDA_PDL": "0"},
+    "PDL median only": {"APDA_PDL": "1"},
+    "PDL median+head": {"APDA_PDL": "3"},
+    "PDL median+tail": {"APDA_PDL": "5"},
+    "PDL head+tail": {"APDA_PDL": "6"},
     "f64 512x1 (round 1)": {"APDA_K2_NT64": "512", "APDA_K2_MINB64": "1"},
     "f32 256x2": {"APDA_K2_MINB32": "2"},
     "f32 512x2": {"APDA_K2_NT32": "512", "APDA_K2_MINB32": "2"},
@@ -86,7 +91,7 @@ def main():
     results = {}
     variants = {os.path.basename(p): {"APDA_LIB": os.path.abspath(p)} for p in args.libs} if args.libs else VARIANTS
     for name, env in variants.items():
-        if args.only and args.only not in name:
+        if args.only and not any(o in name for o in args.only.split(",")):
             continue
         res = subprocess.run([sys.executable, os.path.abspath(__file__), "--child"], env=dict(os.environ, **env),
                              capture_output=True, text=True, timeout=900)
