@@ -467,7 +467,9 @@ __global__ void select_prepare_upper_kernel(SelectState *st) {
 // Exact for any input: the bracket only steers where the resolution goes.
 constexpr int kBrBuckets = 4096;
 constexpr int kBrSample = 1024;
-constexpr int kBrThreads = 256;
+// threads per CTA of the two streaming kernels: 256 for short windows (more CTAs), 1024 for long ones (the per-CTA
+// histogram clear / flush and the per-CTA pick are paid 148 x 2 times instead of 148 x 8 times)
+constexpr int kBrThreadsSmall = 256, kBrThreadsLarge = 1024;
 
 template <typename T>
 struct BracketState {  // device resident, one per stream
@@ -592,10 +594,10 @@ __global__ void __launch_bounds__(1024) br_sample_kernel(const T *__restrict__ x
     }
 }
 
-// One pass over x[0, n) with 128-bit loads, four in flight per thread: body(e, valid) sees E = 4 * 16/sizeof(T) elements
+// One pass over x[0, n) with 128-bit loads, four in flight per thread (and the next four requested ahead): body(e, valid) sees E = 4 * 16/sizeof(T) elements
 // per call (bit u of `valid`: e[u] is a sample).  Warp-uniform trip count (the bodies use warp collectives); the
 // few samples before the first / after the last aligned 16-byte vector go through the same body, one per lane.
-template <typename T, typename Body>
+template <typename T, int NT, typename Body>
 __device__ __forceinline__ void br_stream(const T *__restrict__ x, int64_t n, Body body) {
     constexpr int VEC = 16 / (int)sizeof(T), UNR = 4, E = VEC * UNR;
     const uintptr_t addr = reinterpret_cast<uintptr_t>(x);
@@ -603,22 +605,30 @@ __device__ __forceinline__ void br_stream(const T *__restrict__ x, int64_t n, Bo
     if (a0 > n) a0 = n;
     const int64_t nvec = (n - a0) / VEC;
     const int4 *xv = reinterpret_cast<const int4 *>(x + a0);
-    const int64_t per_it = (int64_t)gridDim.x * kBrThreads * UNR;
+    const int64_t per_it = (int64_t)gridDim.x * NT * UNR;
+    // software pipeline: the next trip's four vectors are requested before the current ones are processed
+    int4 nxt[UNR];
+    auto fetch = [&](int64_t it0) {
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int64_t iv = it0 + ((int64_t)blockIdx.x * UNR + u) * NT + threadIdx.x;
+            nxt[u] = make_int4(0, 0, 0, 0);
+            if (iv < nvec) nxt[u] = __ldg(xv + iv);
+        }
+    };
+    if (nvec > 0) fetch(0);
     for (int64_t it0 = 0; it0 < nvec; it0 += per_it) {
         T e[E];
         unsigned valid = 0;
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-            const int64_t iv = it0 + ((int64_t)blockIdx.x * UNR + u) * kBrThreads + threadIdx.x;
-            int4 raw = make_int4(0, 0, 0, 0);
-            if (iv < nvec) {
-                raw = __ldg(xv + iv);
-                valid |= ((1u << VEC) - 1u) << (u * VEC);
-            }
-            const T *p = reinterpret_cast<const T *>(&raw);
+            const int64_t iv = it0 + ((int64_t)blockIdx.x * UNR + u) * NT + threadIdx.x;
+            if (iv < nvec) valid |= ((1u << VEC) - 1u) << (u * VEC);
+            const T *p = reinterpret_cast<const T *>(&nxt[u]);
 #pragma unroll
             for (int q = 0; q < VEC; ++q) e[u * VEC + q] = p[q];
         }
+        if (it0 + per_it < nvec) fetch(it0 + per_it);
         body(e, valid);
     }
     if (blockIdx.x == 0 && threadIdx.x < 32) {  // leftovers: < VEC in front, < VEC behind
@@ -637,52 +647,74 @@ __device__ __forceinline__ void br_stream(const T *__restrict__ x, int64_t n, Bo
     }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kBrThreads) br_count_kernel(const T *__restrict__ x, int64_t n, BracketState<T> *st) {
+template <typename T, int NT>
+__global__ void __launch_bounds__(NT) br_count_kernel(const T *__restrict__ x, int64_t n, BracketState<T> *st) {
     constexpr int E = 4 * 16 / (int)sizeof(T);
     __shared__ unsigned h[kBrBuckets];
     pdl_trigger();
-    for (int i = threadIdx.x; i < kBrBuckets; i += kBrThreads) h[i] = 0;
+    for (int i = threadIdx.x; i < kBrBuckets; i += NT) h[i] = 0;
     pdl_wait();  // the bracket comes from br_sample_kernel
     __syncthreads();
     const T lo = st->lo, hi = st->hi, scale = st->scale;
     unsigned below = 0;
-    br_stream<T>(x, n, [&](const T (&e)[E], unsigned valid) {
-        int cur = -1;  // run of equal buckets among this thread's consecutive samples: one atomic per run
-        unsigned run = 0;
+    // Per 128-bit vector: two comparisons per sample decide below / inside / above (three quarters of a window are
+    // outside the bracket and take nothing else); the buckets of a vector that is inside are computed together, and a
+    // vector that falls into ONE bucket (smooth signals) costs one atomic.
+    br_stream<T, NT>(x, n, [&](const T (&e)[E], unsigned valid) {
+        constexpr int VEC = 16 / (int)sizeof(T);
 #pragma unroll
-        for (int u = 0; u < E; ++u) {
-            const bool ok = (valid >> u) & 1u;
-            below += ok && e[u] < lo;
-            if (ok && !(e[u] < lo) && !(e[u] >= hi)) {
-                const int b = br_bucket<T>(e[u], lo, scale);
-                if (b == cur) {
-                    ++run;
-                } else {
-                    if (run) atomicAdd(&h[cur], run);
-                    cur = b;
-                    run = 1;
-                }
+        for (int v = 0; v < E / VEC; ++v) {
+            const unsigned vmask = (valid >> (v * VEC)) & ((1u << VEC) - 1u);
+            if (!vmask) continue;
+            const bool full = vmask == (1u << VEC) - 1u;  // else: a leftover sample in slot 0
+            bool in[VEC];
+            bool any = false;
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) {
+                const T xq = e[v * VEC + q];
+                const bool ok = q == 0 || full;
+                const bool lt = ok && xq < lo;
+                in[q] = ok && !(xq < lo) && !(xq >= hi);
+                below += lt;
+                any |= in[q];
+            }
+            if (!any) continue;
+            int bk[VEC];
+            bool same = true;
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) {
+                bk[q] = in[q] ? br_bucket<T>(e[v * VEC + q], lo, scale) : -1 - q;
+                same &= bk[q] == bk[0];
+            }
+            if (same) {
+                atomicAdd(&h[bk[0]], (unsigned)VEC);
+            } else {
+#pragma unroll
+                for (int q = 0; q < VEC; ++q)
+                    if (in[q]) atomicAdd(&h[bk[q]], 1u);
             }
         }
-        if (run) atomicAdd(&h[cur], run);
     });
     below = __reduce_add_sync(0xffffffffu, below);
     if ((threadIdx.x & 31) == 0 && below) atomicAdd(&st->below, (unsigned long long)below);
     __syncthreads();
-    for (int b = threadIdx.x; b < kBrBuckets; b += kBrThreads)
-        if (h[b]) atomicAdd(&st->hist[b], h[b]);
+    unsigned mine[kBrBuckets / NT];  // all shared-memory reads first: the reductions then go out back to back
+#pragma unroll
+    for (int u = 0; u < kBrBuckets / NT; ++u) mine[u] = h[threadIdx.x + u * NT];
+#pragma unroll
+    for (int u = 0; u < kBrBuckets / NT; ++u)
+        if (mine[u]) atomicAdd(&st->hist[threadIdx.x + u * NT], mine[u]);
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kBrThreads) br_compact_kernel(const T *__restrict__ x, int64_t n, BracketState<T> *st,
+template <typename T, int NT>
+__global__ void __launch_bounds__(NT) br_compact_kernel(const T *__restrict__ x, int64_t n, BracketState<T> *st,
                                                                T *__restrict__ bucket) {
     constexpr int E = 4 * 16 / (int)sizeof(T);
-    constexpr int PER = kBrBuckets / kBrThreads;
-    __shared__ unsigned long long wsum[kBrThreads / 32];
+    constexpr int PER = kBrBuckets / NT;
+    __shared__ unsigned long long wsum[NT / 32];
     __shared__ int s_mode;
     __shared__ long long s_rank;
-    __shared__ unsigned long long blk[3][kBrThreads / 32];
+    __shared__ unsigned long long blk[3][NT / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     pdl_trigger();
     pdl_wait();
@@ -704,7 +736,7 @@ __global__ void __launch_bounds__(kBrThreads) br_compact_kernel(const T *__restr
         if (lane == 31) wsum[warp] = incl;
         __syncthreads();
         unsigned long long ahead = 0, inside = 0;
-        for (int w = 0; w < kBrThreads / 32; ++w) {
+        for (int w = 0; w < NT / 32; ++w) {
             if (w < warp) ahead += wsum[w];
             inside += wsum[w];
         }
@@ -740,14 +772,47 @@ __global__ void __launch_bounds__(kBrThreads) br_compact_kernel(const T *__restr
     const T lo = st->lo, hi = st->hi, scale = st->scale;
     T amin = CUDART_INF;                       // smallest value after the region
     unsigned long long kmin = ~0ull, kmax = 0ull;  // key range of the copied values
-    br_stream<T>(x, n, [&](const T (&e)[E], unsigned valid) {
+    br_stream<T, NT>(x, n, [&](const T (&e)[E], unsigned valid) {
+        constexpr int VEC = 16 / (int)sizeof(T);
         unsigned take = 0;
 #pragma unroll
-        for (int u = 0; u < E; ++u) {
-            if (!((valid >> u) & 1u)) continue;
-            const int r = e[u] < lo ? -1 : (e[u] >= hi ? kBrBuckets : br_bucket<T>(e[u], lo, scale));
-            if (r == mode) take |= 1u << u;
-            else if (r > mode && e[u] < amin) amin = e[u];
+        for (int v = 0; v < E / VEC; ++v) {
+            const unsigned vmask = (valid >> (v * VEC)) & ((1u << VEC) - 1u);
+            if (!vmask) continue;
+            const bool full = vmask == (1u << VEC) - 1u;
+            if (mode >= 0 && mode < kBrBuckets) {  // the usual case: one bucket of the bracket
+                bool in[VEC];
+                bool any = false;
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) {
+                    const T xq = e[v * VEC + q];
+                    const bool ok = q == 0 || full;
+                    in[q] = ok && !(xq < lo) && !(xq >= hi);
+                    if (ok && xq >= hi && xq < amin) amin = xq;
+                    any |= in[q];
+                }
+                if (!any) continue;
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) {
+                    if (!in[q]) continue;
+                    const T xq = e[v * VEC + q];
+                    const int r = br_bucket<T>(xq, lo, scale);
+                    if (r == mode) take |= 1u << (v * VEC + q);
+                    else if (r > mode && xq < amin) amin = xq;
+                }
+            } else if (mode < 0) {  // the sample missed: the middle lies below the bracket
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) {
+                    const T xq = e[v * VEC + q];
+                    const bool ok = q == 0 || full;
+                    if (ok && xq < lo) take |= 1u << (v * VEC + q);
+                    else if (ok && xq < amin) amin = xq;
+                }
+            } else {  // ... or at / above its upper end
+#pragma unroll
+                for (int q = 0; q < VEC; ++q)
+                    if ((q == 0 || full) && e[v * VEC + q] >= hi) take |= 1u << (v * VEC + q);
+            }
         }
         if (!__any_sync(0xffffffffu, take != 0)) return;
         unsigned incl = (unsigned)__popc(take);  // offsets inside the warp's append
@@ -786,7 +851,7 @@ __global__ void __launch_bounds__(kBrThreads) br_compact_kernel(const T *__restr
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < kBrThreads / 32; ++w) {
+        for (int w = 1; w < NT / 32; ++w) {
             above = blk[0][w] < above ? blk[0][w] : above;
             kmin = blk[1][w] < kmin ? blk[1][w] : kmin;
             kmax = blk[2][w] > kmax ? blk[2][w] : kmax;
@@ -923,11 +988,18 @@ __global__ void __launch_bounds__(1024) br_finish_kernel(const T *__restrict__ b
 template <typename T>
 int large_median(apda_ctx *ctx, cudaStream_t st, const T *d_x, int64_t n, void *state_raw, T *d_med, T *d_bucket) {
     BracketState<T> *state = reinterpret_cast<BracketState<T> *>(state_raw);
-    constexpr int64_t per_cta = (int64_t)kBrThreads * 4 * (16 / (int)sizeof(T));  // samples per CTA and trip
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + per_cta - 1) / per_cta, (int64_t)ctx->sm_count * 8));
+    const bool big = n * (int64_t)sizeof(T) >= (int64_t)16 << 20;
+    const int nt = big ? kBrThreadsLarge : kBrThreadsSmall;
+    const int64_t per_cta = (int64_t)nt * 4 * (16 / (int)sizeof(T));  // samples per CTA and trip
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + per_cta - 1) / per_cta, (int64_t)ctx->sm_count * (2048 / nt)));
     br_sample_kernel<T><<<1, 1024, 0, st>>>(d_x, n, state);
-    APDA_CUDA(apda_launch_pdl(APDA_PDL_MEDIAN, br_count_kernel<T>, dim3(grid), dim3(kBrThreads), 0, st, d_x, n, state));
-    APDA_CUDA(apda_launch_pdl(APDA_PDL_MEDIAN, br_compact_kernel<T>, dim3(grid), dim3(kBrThreads), 0, st, d_x, n, state, d_bucket));
+    if (big) {
+        APDA_CUDA(apda_launch_pdl(APDA_PDL_MEDIAN, br_count_kernel<T, kBrThreadsLarge>, dim3(grid), dim3(nt), 0, st, d_x, n, state));
+        APDA_CUDA(apda_launch_pdl(APDA_PDL_MEDIAN, br_compact_kernel<T, kBrThreadsLarge>, dim3(grid), dim3(nt), 0, st, d_x, n, state, d_bucket));
+    } else {
+        APDA_CUDA(apda_launch_pdl(APDA_PDL_MEDIAN, br_count_kernel<T, kBrThreadsSmall>, dim3(grid), dim3(nt), 0, st, d_x, n, state));
+        APDA_CUDA(apda_launch_pdl(APDA_PDL_MEDIAN, br_compact_kernel<T, kBrThreadsSmall>, dim3(grid), dim3(nt), 0, st, d_x, n, state, d_bucket));
+    }
     APDA_CUDA(apda_launch_pdl(APDA_PDL_MEDIAN, br_finish_kernel<T>, dim3(1), dim3(1024), 0, st, (const T *)d_bucket, state, n, d_med));
     ctx->launches += 4;
     APDA_CUDA(cudaGetLastError());
