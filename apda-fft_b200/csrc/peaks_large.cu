@@ -409,13 +409,23 @@ pick_rigid_kernel(T *__restrict__ mags, int64_t n, int half, double fs_all, cons
     while (true) {
         double bm = -1.0;
         int bj = -1;
-        for (int e = tid; e < nhot; e += 1024) {
-            const int j = cand[e];
-            const T m = mags[j];
-            if (j >= 1 && j <= half - 2 && (double)m > thr && m > mags[j - 1] && m > mags[j + 1] &&
-                ((double)m > bm || ((double)m == bm && j < bj))) {
-                bm = (double)m;
-                bj = j;
+        // four candidates in flight per thread; the neighbours are only read for a bin that would beat the thread's best
+        for (int e0 = tid; e0 < nhot; e0 += 4 * 1024) {
+            int js[4];
+            T ms[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) js[u] = e0 + 1024 * u < nhot ? cand[e0 + 1024 * u] : -1;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ms[u] = js[u] >= 0 ? mags[js[u]] : T(0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = js[u];
+                const T m = ms[u];
+                if (j >= 1 && j <= half - 2 && (double)m > thr && ((double)m > bm || ((double)m == bm && j < bj)) &&
+                    m > mags[j - 1] && m > mags[j + 1]) {
+                    bm = (double)m;
+                    bj = j;
+                }
             }
         }
 #pragma unroll
