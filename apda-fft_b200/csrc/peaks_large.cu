@@ -52,15 +52,21 @@ mags_kernel(const typename vec2<T>::type *__restrict__ spec, T *__restrict__ mag
             for (int u = 0; u < UNR; ++u) v[u] = spec[b0 + 32 * UNR * r + 32 * u + lane];
 #pragma unroll
             for (int u = 0; u < UNR; ++u) {
-                const T m = magnitude(v[u].x, v[u].y);
+                const T m = magnitude_fast(v[u].x, v[u].y);
                 mags[b0 + 32 * UNR * r + 32 * u + lane] = m;
                 const bool first = r == 0 && u == 0;
                 mx = (first || m > mx) ? m : mx;
                 mn = (first || m < mn) ? m : mn;
                 const double d = (double)m;
                 if (sizeof(T) == 8) {
-                    sx[u & 1] = dd_add_d(sx[u & 1], d);
-                    sxx[u & 1] = dd_add(sxx[u & 1], two_prod(d, d));
+                    // non-negative summands: TwoSum on the high words, plain adds on the error words (exact to ~2^-94)
+                    const dd s = two_sum(sx[u & 1].hi, d);
+                    sx[u & 1].hi = s.hi;
+                    sx[u & 1].lo = add_rn(sx[u & 1].lo, s.lo);
+                    const dd pr = two_prod(d, d);
+                    const dd s2 = two_sum(sxx[u & 1].hi, pr.hi);
+                    sxx[u & 1].hi = s2.hi;
+                    sxx[u & 1].lo = add_rn(add_rn(sxx[u & 1].lo, pr.lo), s2.lo);
                 } else {
                     sx[u & 1].hi += d;
                     sxx[u & 1].hi = __fma_rn(d, d, sxx[u & 1].hi);
@@ -95,7 +101,8 @@ mags_kernel(const typename vec2<T>::type *__restrict__ spec, T *__restrict__ mag
             __syncthreads();
         }
     }
-    const dd wx = warp_sum_dd(dd_add(sx[0], sx[1])), wxx = warp_sum_dd(dd_add(sxx[0], sxx[1]));
+    const dd wx = warp_sum_dd(dd_add(two_sum(sx[0].hi, sx[0].lo), two_sum(sx[1].hi, sx[1].lo)));
+    const dd wxx = warp_sum_dd(dd_add(two_sum(sxx[0].hi, sxx[0].lo), two_sum(sxx[1].hi, sxx[1].lo)));
     if (lane == 0) {
         red[warp] = wx;
         red[MAGS_WARPS + warp] = wxx;
