@@ -41,7 +41,11 @@ struct K3 {
     static constexpr int C = HALF / 32;                // bins per lane chunk
     static constexpr int PAD = 16 / (int)sizeof(T);    // 16-byte pad per chunk: the lanes' 128-bit LDS are conflict free
     static constexpr int MAGW = HALF + PAD * 32;       // magnitude elements incl. the pads
-    static constexpr int SLOTS = 96;                   // candidates / hot bins kept on chip; more -> repair list (general kernel)
+    // candidates (flexible) kept on chip; more -> repair list (general kernel).  160 for the longest windows (a pure-noise
+    // spectrum of 4096 bins has ~95 +- 10 hot local maxima) costs no residency: 6 CTAs of 2 windows per SM either way.
+    // The rigid picker keeps bare 16-bit bin indices in the same bytes: 4 (fp32) or 8 (fp64) times as many hot bins.
+    static constexpr int SLOTS = HALF >= 4096 ? 160 : 96;
+    static constexpr int HOT_CAP = SLOTS * (int)sizeof(SlotT<T>) / 2;
     static constexpr int REC_OFF = MAGW * (int)sizeof(T) + SLOTS * (int)sizeof(SlotT<T>);
     static constexpr int BYTES = (REC_OFF + 128 + 15) & ~15;
     __device__ static __forceinline__ int addr(int b) { return b + PAD * (b / C); }
@@ -392,10 +396,80 @@ __device__ __forceinline__ int k3_gate(const T *mags, int j, T prom, double half
     return 0;
 }
 
+// Flexible picker for windows with many candidates (noise-like spectra: dozens of hot local maxima of which only the k
+// largest can be reported).  A candidate's gates do not depend on the other candidates, and the reference walks the
+// gated candidates in the order "descending round(mag, 4), ascending idx" until k are accepted: so the candidates are
+// extracted in that order FIRST (warp arg-max, as in order_and_exclude) and prominence, width and damping are computed
+// only for the ones reached.  Same records as evaluating every candidate (the general kernel does; tests compare).
+template <typename T, int HALF, int PER, typename P = K3<T, HALF>>
+__device__ __forceinline__ int order_eval_exclude_lazy(const SlotT<T> *slots, int nslot, const T *mags, unsigned char *rec_s,
+                                                       T cmax, T cmin, double sd, double df, int k, int lane) {
+    double key[PER];
+    int sidx[PER];
+#pragma unroll
+    for (int r = 0; r < PER; ++r) {
+        const int e = lane + 32 * r;
+        const bool ok = e < nslot;
+        sidx[r] = ok ? (int)slots[e].idx : -1;
+        key[r] = ok ? round_dec4_units((double)mags[P::addr(sidx[r])]) : -1.0;
+    }
+    const double half_sd = mul_rn(0.5, sd);
+    int na = 0;
+    while (na < k) {
+        double bk = key[0];
+        int bi = sidx[0], br = 0;
+#pragma unroll
+        for (int r = 1; r < PER; ++r) {
+            if (sidx[r] >= 0 && (bi < 0 || key[r] > bk || (key[r] == bk && sidx[r] < bi))) {
+                bk = key[r];
+                bi = sidx[r];
+                br = r;
+            }
+        }
+        const int mine = bi;
+        warp_argmax(bk, bi);
+        if (bi < 0) break;
+        if (mine == bi) {  // bin indices are unique: one lane owns the extracted candidate
+#pragma unroll
+            for (int r = 0; r < PER; ++r)
+                if (r == br) sidx[r] = -1;
+        }
+        const int c_idx = bi;
+        const T cprom = coop_prominence<T, HALF>(mags, c_idx, cmax, cmin, lane);
+        const int width = k3_gate<T, HALF, P>(mags, c_idx, cprom, half_sd, df);  // same value in every lane
+        if (width == 0) continue;
+        const T cmag = mags[P::addr(c_idx)];
+        bool hump = false;
+        for (int a = 0; a < na && !hump; ++a) {
+            const int ja = reinterpret_cast<const int *>(rec_s + 8 + 24 * a)[0];
+            const double fc = mul_rn((double)c_idx, df), fa = mul_rn((double)ja, df);
+            if (fabs(fc - fa) - 1.0e-4 > 0.05 * (fa + 5.0e-5) * (1.0 + 1e-9)) continue;
+            const double cf = round_dec4_d(fc), af = round_dec4_d(fa);
+            if (div_rn(fabs(sub_rn(cf, af)), af) < 0.05 && div_rn((double)cprom, div_rn(bk, 1e4)) < 0.10) hump = true;
+        }
+        if (!hump) {
+            if (lane == 0) {
+                unsigned char *pk = rec_s + 8 + 24 * na;
+                reinterpret_cast<int *>(pk)[0] = c_idx;
+                reinterpret_cast<int *>(pk)[1] = width;
+                reinterpret_cast<double *>(pk + 8)[0] = (double)cmag;
+                reinterpret_cast<double *>(pk + 8)[1] = (double)cprom;
+            }
+            ++na;
+            __syncwarp();
+        }
+    }
+    return na;
+}
+
 // Rigid picker on the hot list (utils/get_peak_resolution.py:94-126), one warp; returns the number of accepted peaks and
 // writes them into the record under construction.  Zeroes magnitudes in shared memory as the reference does.
-template <typename T, int HALF, typename P>
-__device__ __forceinline__ int k3_rigid(T *mags, const SlotT<T> *slots, int nslot, T thr_f, double df, int k, int lane,
+__device__ __forceinline__ int hot_bin(const uint16_t *list, int e) { return list[e]; }
+template <typename T>
+__device__ __forceinline__ int hot_bin(const SlotT<T> *list, int e) { return list[e].idx; }
+// `hot`: bare 16-bit bin indices (pipeline kernels) or slot structs (fused kernel)
+template <typename T, int HALF, typename P, typename List>
+__device__ __forceinline__ int k3_rigid(T *mags, const List *hot, int nslot, T thr_f, double df, int k, int lane,
                                         unsigned char *rec_s) {
     const double distance = sub_rn(mul_rn(2.0, df), mul_rn(1.0, df));
     int acc_idx[5];
@@ -407,10 +481,10 @@ __device__ __forceinline__ int k3_rigid(T *mags, const SlotT<T> *slots, int nslo
         T bm = (T)-1;
         int bj = -1;
         for (int e = lane; e < nslot; e += 32) {
-            const int j = slots[e].idx;
+            const int j = hot_bin(hot, e);
             const T m = mags[P::addr(j)];
-            if (j >= 1 && j <= HALF - 2 && m > thr_f && m > mags[P::addr(j - 1)] && m > mags[P::addr(j + 1)] &&
-                (m > bm || (m == bm && j < bj))) {
+            if (j >= 1 && j <= HALF - 2 && m > thr_f && (m > bm || (m == bm && j < bj)) && m > mags[P::addr(j - 1)] &&
+                m > mags[P::addr(j + 1)]) {
                 bm = m;
                 bj = j;
             }
@@ -508,7 +582,11 @@ __device__ __forceinline__ void k3_tail(T *mags, SlotT<T> *slots, const int slot
                         take = j >= 1 && j <= HALF - 2 && e[u] > mags[P::addr(j - 1)] && e[u] > mags[P::addr(j + 1)];
                     if (take) {
                         const int pos = atomicAdd(&(*nslot_ptr), 1);
-                        if (pos < slot_cap) slots[pos].idx = (uint16_t)j;
+                        if (FLEX) {
+                            if (pos < slot_cap) slots[pos].idx = (uint16_t)j;
+                        } else {
+                            if (pos < P::HOT_CAP) reinterpret_cast<uint16_t *>(slots)[pos] = (uint16_t)j;
+                        }
                     }
                     // Two adjacent bins that are EQUAL in fp32 and higher than both outer neighbours: neither is a strict
                     // local maximum, so no peak is reported there, while the fp64 reference (whose magnitudes differ in
@@ -522,7 +600,7 @@ __device__ __forceinline__ void k3_tail(T *mags, SlotT<T> *slots, const int slot
     }
     __syncwarp();
     const int nslot_raw = (*nslot_ptr);
-    if (nslot_raw > slot_cap) {  // more candidates than the on-chip list holds: hand the window to the general kernel
+    if (nslot_raw > (FLEX ? slot_cap : P::HOT_CAP)) {  // more than the on-chip list holds: hand the window to the general kernel
         if (lane == 0) repair[1 + atomicAdd(&repair[0], 1)] = (int)win;
         return;
     }
@@ -530,7 +608,12 @@ __device__ __forceinline__ void k3_tail(T *mags, SlotT<T> *slots, const int slot
     const int status = (sizeof(T) == 4 && __any_sync(0xffffffffu, tie_lane)) ? APDA_STATUS_FP32_TIE : 0;
 
     int na = 0;
-    if (FLEX) {
+    if (FLEX && nslot > 32) {
+        // noise-like window (dozens of hot local maxima): the candidates are visited in the reference's output order and
+        // evaluated only until k of them are accepted
+        na = P::SLOTS > 96 ? order_eval_exclude_lazy<T, HALF, 5>(slots, nslot, mags, rec_s, cmax, cmin, sd, df, k, lane)
+                           : order_eval_exclude_lazy<T, HALF, 3>(slots, nslot, mags, rec_s, cmax, cmin, sd, df, k, lane);
+    } else if (FLEX) {
         // ---- A: cooperative prominence per candidate -----------------------------------------------------------------
         for (int c = 0; c < nslot; ++c) {
             const int j = slots[c].idx;
@@ -544,11 +627,9 @@ __device__ __forceinline__ void k3_tail(T *mags, SlotT<T> *slots, const int slot
             slots[c].width = (uint16_t)k3_gate<T, HALF, P>(mags, slots[c].idx, slots[c].prom, half_sd, df);
         __syncwarp();
         // ---- C: order "descending round(mag,4), ascending idx" (stable sort of the reference), greedy hump exclusion ------
-        na = nslot <= 32   ? order_and_exclude<T, HALF, 1>(slots, nslot, mags, rec_s, df, k, lane)
-             : nslot <= 96 ? order_and_exclude<T, HALF, 3>(slots, nslot, mags, rec_s, df, k, lane)
-                           : order_and_exclude_any<T, HALF>(slots, nslot, mags, rec_s, df, k, lane);
+        na = order_and_exclude<T, HALF, 1>(slots, nslot, mags, rec_s, df, k, lane);
     } else {
-        na = k3_rigid<T, HALF, P>(mags, slots, nslot, thr_f, df, k, lane, rec_s);
+        na = k3_rigid<T, HALF, P>(mags, reinterpret_cast<const uint16_t *>(slots), nslot, thr_f, df, k, lane, rec_s);
     }
     if (lane == 0) {
         reinterpret_cast<int *>(rec_s)[0] = na;

@@ -86,8 +86,9 @@ def test_gateway_work_flow_fft_unmodified_call_site(flexible, tmp_path, golden):
 # device-side window lists are per stream
 # ---------------------------------------------------------------------------------------------------------------
 def test_multichunk_pinned_noise_spectra_repair_list_per_stream(an):
-    """More than three chunks of N = 8192 noise spectra in PINNED memory (so the two pipeline streams really overlap):
-    every window has ~150 bins above mean + 2 sigma, more than the fast picker's 96 on-chip slots, so every window goes
+    """More than three chunks of N = 8192 spectra in PINNED memory (so the two pipeline streams really overlap): noise
+    plus 680 isolated spikes per window, i.e. 680 hot local maxima - more than the fast picker keeps on chip (160
+    candidates for the flexible picker, 640 16-bit hot bins for the rigid one), so every window goes
     through the device-side repair list and the general kernel.  With one list per context, the next chunk's
     memset / appends on the other stream raced with this chunk's; now every record must equal, byte for byte, what the
     general kernel alone produces (apda_ctx_set_generic_only), and the oracle on a sample."""
@@ -99,6 +100,10 @@ def test_multichunk_pinned_noise_spectra_repair_list_per_stream(an):
     zn = z.numpy()
     zn[:] = rng.standard_normal((b, n, 2), dtype=np.float32)
     zn[:, 0, :] = 0
+    for w in range(b):      # isolated spikes (even bins, distinct heights) well above mean + 2 sigma of the window
+        at = 2 * rng.permutation(n // 4 - 2)[:680] + 2
+        zn[w, at, 0] = 10.0 + 0.5 * rng.random(680, dtype=np.float32)
+        zn[w, at, 1] = 0.0
     for flexible in (True, False):
         name = "apda_peaks_prominence_f32_host" if flexible else "apda_peaks_resolution_f32_host"
         k = 4 if flexible else 5
@@ -588,3 +593,43 @@ def test_peaks_large_reports_fp32_tie(an):
             an.ctx.set_generic_only(False)
         assert int(fast[0]["status"]) & _cabi.STATUS_FP32_TIE and int(slow[0]["status"]) & _cabi.STATUS_FP32_TIE
         assert fast.tobytes() == slow.tobytes()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# windowed pickers on noise-like spectra: lazy evaluation in output order (flexible), packed hot list (rigid)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1024, 2048, 4096, 8192])
+def test_noise_windows_fast_pickers_equal_general_kernel(n, an):
+    """Pure-noise spectra have dozens of hot local maxima (about 2.3 % of the bins).  The fast flexible picker then visits
+    the candidates in the reference's output order and evaluates prominence / width / damping only until k are accepted;
+    the rigid one keeps bare 16-bit hot bins.  Both must give what the general kernel gives by evaluating everything:
+    byte-equal records in fp64, equal index / width lists and magnitudes within fp32 rounding in fp32."""
+    rng = np.random.default_rng(n)
+    b = 96
+    z = (rng.standard_normal((b, n)) + 1j * rng.standard_normal((b, n)))
+    z[:, 0] = 0
+    z[::7] *= np.linspace(1.0, 3.0, n)[None, :]          # coloured noise: candidates pile up at one end
+    z[5::11, 300] = 40.0                                  # one dominant line on top of the noise
+    for dt in (np.complex128, np.complex64):
+        for flexible in (True, False):
+            for k in ((1, 4, 5) if flexible else (2, 5)):
+                fast = an.peaks(z.astype(dt), 125.0, flexible=flexible, k=k)
+                an.ctx.set_generic_only(True)
+                try:
+                    slow = an.peaks(z.astype(dt), 125.0, flexible=flexible, k=k)
+                finally:
+                    an.ctx.set_generic_only(False)
+                assert (fast["status"] == 0).all() and (slow["status"] == 0).all()
+                if dt is np.complex128:
+                    assert fast.tobytes() == slow.tobytes(), (n, flexible, k)
+                else:
+                    assert np.array_equal(fast["count"], slow["count"]), (n, flexible, k)
+                    assert np.array_equal(fast["pk"]["idx"], slow["pk"]["idx"]), (n, flexible, k)
+                    assert np.array_equal(fast["pk"]["width_bins"], slow["pk"]["width_bins"]), (n, flexible, k)
+                    assert np.allclose(fast["pk"]["mag"], slow["pk"]["mag"], rtol=3e-7, atol=0)
+                    assert np.allclose(fast["pk"]["prominence"], slow["pk"]["prominence"], rtol=1e-5, atol=1e-6)
+            assert int(fast["count"].max()) >= 2
+    # and against the reference-equivalent oracle on a few windows (fp64)
+    rec = an.peaks(z[:6], 125.0, flexible=True)
+    for w in range(6):
+        assert _dicts(rec[w], 125.0, n, True) == c_oracle.peaks_prominence(z[w], 125.0), w
