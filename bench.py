@@ -568,6 +568,17 @@ def run_ours(args):
             variants["half_spectrum_pipeline"] = half_variant()
             variants["fused_kernel_median"] = fused_variant(_cabi.CENTER_MEDIAN)
             variants["fused_kernel_mean"] = fused_variant(_cabi.CENTER_MEAN)
+        # the same pipeline on windows of pure noise (a fleet at rest): dozens of hot local maxima per window instead of
+        # three tones - the picker's worst case; the windows are regenerated afterwards
+        g = torch.Generator(device=dev).manual_seed(1234)
+        for lo in range(0, b, 65536):
+            fleet.d_x[lo:lo + 65536].normal_(generator=g)
+        ms, k1, clk, tab = fleet.timed(args.steps, 3)
+        nrec = tab[:total].cpu().numpy().view(record_dtype(5)).reshape(-1)
+        variants["noise_windows"] = dict(variant_line(ms, k1, clk, total), mean_peaks_per_window=float(nrec["count"].mean()),
+                                         status_nonzero=int((nrec["status"] != 0).sum()),
+                                         note="standard-normal samples instead of the three-tone windows; same kernels")
+        an.synth_device(lo_w, b, n, args.dtype, fleet.d_x.data_ptr())
         fleet.step()            # leave the headline configuration's records in d_rec for the e2e comparison
         fence()
     if not args.no_variants and world > 1:
