@@ -26,6 +26,9 @@ namespace {
 #ifndef APDA_K3_WPC
 #define APDA_K3_WPC 2
 #endif
+#ifndef APDA_K3_LAZY_MIN
+#define APDA_K3_LAZY_MIN 8  // flexible picker: more candidates than this -> evaluate in output order until k are accepted
+#endif
 constexpr int kWPC = APDA_K3_WPC;  // windows (warps) per CTA
 
 template <typename T>
@@ -608,7 +611,7 @@ __device__ __forceinline__ void k3_tail(T *mags, SlotT<T> *slots, const int slot
     const int status = (sizeof(T) == 4 && __any_sync(0xffffffffu, tie_lane)) ? APDA_STATUS_FP32_TIE : 0;
 
     int na = 0;
-    if (FLEX && nslot > 32) {
+    if (FLEX && nslot > APDA_K3_LAZY_MIN) {
         // noise-like window (dozens of hot local maxima): the candidates are visited in the reference's output order and
         // evaluated only until k of them are accepted
         na = P::SLOTS > 96 ? order_eval_exclude_lazy<T, HALF, 5>(slots, nslot, mags, rec_s, cmax, cmin, sd, df, k, lane)
