@@ -184,6 +184,33 @@ __device__ __forceinline__ float next_above(float v) {  // smallest float strict
 // the key space, which bounds the worst case).  When at most 32 values remain in the bracket one warp ranks them.
 // Exact for any input; the estimates only steer the pivots.  Padding slots (index >= n_valid) must hold +inf.
 // Returns statistics.median: the middle value (odd n) or the mean of the two middle values (even n).
+// smallest / largest of the warp's values whose bit is set in `inb` (bit 31 - q: value q); out of line on purpose: it
+// serves the rare windows of quantised samples (see select_median) and must not lengthen everybody's instruction stream
+__device__ __noinline__ float2 bracket_minmax(float2 a0, float2 a1, float2 a2, float2 a3, float2 a4, float2 a5, float2 a6,
+                                              float2 a7, float2 a8, float2 a9, float2 a10, float2 a11, float2 a12, float2 a13,
+                                              float2 a14, float2 a15, unsigned inb) {
+    const float2 a[16] = {a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11, a12, a13, a14, a15};
+    float vmin = CUDART_INF_F, vmax = -CUDART_INF_F;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        if (inb & (0x80000000u >> (2 * i))) {
+            vmin = fminf(vmin, a[i].x);
+            vmax = fmaxf(vmax, a[i].x);
+        }
+        if (inb & (0x80000000u >> (2 * i + 1))) {
+            vmin = fminf(vmin, a[i].y);
+            vmax = fmaxf(vmax, a[i].y);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    }
+    return make_float2(vmin, vmax);
+}
+
+constexpr int kTightenFrom = 4;  // counting rounds before the bracket is cut to the values inside it
 template <int T, bool FULL, typename Reload>
 __device__ float select_median(const float2 (&v2)[16], int n_valid, uint32_t *sh /* 64 words */, int t, int slot,
                                Reload reload /* reload(q): value q (0..31) of this thread, re-read from memory */) {
@@ -259,6 +286,33 @@ __device__ float select_median(const float2 (&v2)[16], int n_valid, uint32_t *sh
     for (int round = 0;; ++round) {
         if (round > 0) {
             if (c_hi - c_lo <= 32) break;
+            if (round >= kTightenFrom) {
+                // Still more than 32 values in the bracket after several rounds: quantised samples (an ADC's few hundred
+                // levels, a sensor at rest), where the middle value is repeated more often than the final ranking holds and
+                // the key-space bisection would need one round per bit.  Take the smallest and largest value INSIDE the
+                // bracket: if they are equal, that value is both middle order statistics; otherwise they are the new ends
+                // (no value lies between the old and the new ends, so counts and sign words stay valid) and every further
+                // pivot in (vmin, vmax] removes at least one level from one side.
+                const float2 mm = bracket_minmax(v2[0], v2[1], v2[2], v2[3], v2[4], v2[5], v2[6], v2[7], v2[8], v2[9], v2[10],
+                                                 v2[11], v2[12], v2[13], v2[14], v2[15], ~mask_lo & mask_hi);
+                if (lane == 0) {
+                    shf[warp] = mm.x;
+                    shf[8 + warp] = mm.y;
+                }
+                group_sync<T>(slot);
+                float vmin = shf[0], vmax = shf[8];
+#pragma unroll
+                for (int w = 1; w < NW; ++w) {
+                    vmin = fminf(vmin, shf[w]);
+                    vmax = fmaxf(vmax, shf[8 + w]);
+                }
+                if (vmin == vmax) {
+                    group_sync<T>(slot);
+                    return vmin;
+                }
+                lo = vmin;
+                hi = next_above(vmax);
+            }
             const float lo_next = lo > -CUDART_INF_F ? next_above(lo) : -3.4028234e38f;
             if (!(lo_next < hi)) break;  // a single distinct value is left in the bracket
             const float want = (float)r_lo + 0.5f;
@@ -329,8 +383,12 @@ __device__ float select_median(const float2 (&v2)[16], int n_valid, uint32_t *sh
             return (below + above) * 0.5f;
         }
     }
-    // <= 32 values in [lo, hi), or one distinct value: gather (the counter was zeroed in the prologue; the list area
-    // [0, 32) was last read before the first round's barrier) and rank
+    if (c_hi - c_lo > 32) {  // the loop ends like this only with ONE distinct value in the bracket: both middle order statistics
+        group_sync<T>(slot);
+        return lo;
+    }
+    // <= 32 values in [lo, hi): gather (the counter was zeroed in the prologue; the list area [0, 32) was last read
+    // before the first round's barrier) and rank
     for (unsigned inb = ~mask_lo & mask_hi; inb; ) {  // at most 32 bits in the whole window (or one repeated value)
         const int q = __clz(inb);
         inb &= ~(0x80000000u >> q);

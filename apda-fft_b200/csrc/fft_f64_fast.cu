@@ -39,6 +39,27 @@ struct Plan64 {
 
 __device__ __forceinline__ int pad16(int idx) { return idx + (idx >> 4); }
 
+// smallest / largest of the warp's values inside [lo, hi); out of line on purpose (see bracket_minmax in fft_f32_fast.cuh)
+__device__ __noinline__ double2 bracket_minmax_f64(double a0, double a1, double a2, double a3, double a4, double a5, double a6,
+                                                   double a7, double a8, double a9, double a10, double a11, double a12,
+                                                   double a13, double a14, double a15, double lo, double hi) {
+    const double a[16] = {a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11, a12, a13, a14, a15};
+    double vmin = CUDART_INF, vmax = -CUDART_INF;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        if (a[i] >= lo && a[i] < hi) {
+            vmin = fmin(vmin, a[i]);
+            vmax = fmax(vmax, a[i]);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+        vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    }
+    return make_double2(vmin, vmax);
+}
+
 // exact statistics.median of the window; every thread holds 16 of its values (invalid slots: +inf)
 template <int T>
 __device__ double select_median_f64(const double (&val)[16], int n_valid, double *shd /* 72 doubles */, int tid) {
@@ -98,6 +119,30 @@ __device__ double select_median_f64(const double (&val)[16], int n_valid, double
     for (int round = 0;; ++round) {
         if (round > 0) {
             if (c_hi - c_lo <= 32) break;
+            if (round >= 4) {
+                // quantised samples (see select_median in fft_f32_fast.cuh): cut the bracket to the smallest / largest value
+                // inside it; equal -> that value is the median, else every further pivot removes at least one level
+                const double2 mm = bracket_minmax_f64(val[0], val[1], val[2], val[3], val[4], val[5], val[6], val[7], val[8],
+                                                      val[9], val[10], val[11], val[12], val[13], val[14], val[15], lo, hi);
+                if (lane == 0) {
+                    shd[2 + warp] = mm.x;
+                    shd[2 + 16 + warp] = mm.y;
+                }
+                __syncthreads();
+                double vmin = shd[2], vmax = shd[2 + 16];
+#pragma unroll
+                for (int w = 1; w < NW; ++w) {
+                    vmin = fmin(vmin, shd[2 + w]);
+                    vmax = fmax(vmax, shd[2 + 16 + w]);
+                }
+                if (vmin == vmax) {
+                    __syncthreads();
+                    return vmin;
+                }
+                lo = vmin;
+                hi = key_value(ordered_key(vmax) + 1ull, 0.0);
+                if (!(hi > vmax)) hi = key_value(ordered_key(vmax) + 2ull, 0.0);
+            }
             double lo_next = -1.7976931348623157e308;
             if (lo > -CUDART_INF) {
                 lo_next = key_value(ordered_key(lo) + 1ull, 0.0);
@@ -159,6 +204,10 @@ __device__ double select_median_f64(const double (&val)[16], int n_valid, double
             __syncthreads();
             return div_rn(add_rn(below, above), 2.0);
         }
+    }
+    if (c_hi - c_lo > 32) {  // the loop ends like this only with ONE distinct value in the bracket: both middle order statistics
+        __syncthreads();
+        return lo;
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {  // the counter was zeroed in the prologue; the list area was last read before round 0's barrier

@@ -578,6 +578,18 @@ def run_ours(args):
         variants["noise_windows"] = dict(variant_line(ms, k1, clk, total), mean_peaks_per_window=float(nrec["count"].mean()),
                                          status_nonzero=int((nrec["status"] != 0).sum()),
                                          note="standard-normal samples instead of the three-tone windows; same kernels")
+        # ... and on windows as a 16-bit sensor delivers them: the three tones at 20 mg over 13 LSB of noise and a 0.98 g
+        # offset, rounded to the ADC's 1/16384 g - a few hundred distinct values per window, the median value repeated
+        an.synth_device(lo_w, b, n, args.dtype, fleet.d_x.data_ptr())
+        for lo in range(0, b, 65536):
+            blk = fleet.d_x[lo:lo + 65536]
+            blk.mul_(0.02 * 16384.0).add_(torch.randn(blk.shape, generator=g, device=dev, dtype=blk.dtype), alpha=13.0)
+            blk.round_().div_(16384.0).add_(0.98)
+        ms, k1, clk, tab = fleet.timed(args.steps, 3)
+        qrec = tab[:total].cpu().numpy().view(record_dtype(5)).reshape(-1)
+        variants["quantised_windows"] = dict(variant_line(ms, k1, clk, total), mean_peaks_per_window=float(qrec["count"].mean()),
+                                             status_nonzero=int((qrec["status"] != 0).sum()),
+                                             note="tones + noise rounded to 1/16384 (16-bit sensor words); same kernels")
         an.synth_device(lo_w, b, n, args.dtype, fleet.d_x.data_ptr())
         fleet.step()            # leave the headline configuration's records in d_rec for the e2e comparison
         fence()

@@ -633,3 +633,43 @@ def test_noise_windows_fast_pickers_equal_general_kernel(n, an):
     rec = an.peaks(z[:6], 125.0, flexible=True)
     for w in range(6):
         assert _dicts(rec[w], 125.0, n, True) == c_oracle.peaks_prominence(z[w], 125.0), w
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# exact median of quantised windows (an ADC's levels: the middle value is repeated hundreds of times)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_fft", [1024, 2048, 4096, 8192])
+def test_quantised_windows_exact_median(n_fft, an):
+    """Sensor words are 16-bit: a window holds a few dozen to a few hundred distinct values and the median value is
+    repeated far more often than the selection's final ranking holds.  The in-register counting selection then cuts its
+    bracket to the values inside it (plateau -> done).  fp64 spectra must stay bit-identical to the oracle, fp32 within
+    the median test's bound; odd, even and padded lengths; plateaus that end exactly at the middle."""
+    rng = np.random.default_rng(n_fft + 5)
+    for n_samples in (n_fft, n_fft - 1, n_fft // 2 + 3, n_fft // 2 + 4):
+        rows = []
+        for lv in (50.0, 13.0, 5.0, 1.0, 0.3):                      # sigma in LSB; 1 LSB = 1/16384, offset 0.98 (gravity)
+            rows.append(np.round(rng.standard_normal(n_samples) * lv) / 16384.0 + 0.98)
+        rows.append((rng.random(n_samples) < 0.5) * 0.25)             # two levels
+        rows.append(np.full(n_samples, 0.5))                          # constant
+        r = np.full(n_samples, 1.25)                                  # 60 % plateau, outliers on both sides
+        m = n_samples // 5
+        r[:m] = 1.25 - rng.random(m)
+        r[m:2 * m] = 1.25 + rng.random(m)
+        rows.append(rng.permutation(r))
+        h = np.empty(n_samples)                                       # lower half one value, upper half another
+        h[: (n_samples + 1) // 2] = -0.375
+        h[(n_samples + 1) // 2:] = 0.625
+        rows.append(rng.permutation(h))
+        t = np.concatenate([np.full(n_samples // 2 - 1, 2.0), [2.5, 3.0], np.full(n_samples - n_samples // 2 - 1, 4.0)])
+        rows.append(rng.permutation(t))                               # single values at the middle between two plateaus
+        x = np.stack(rows)
+        want = c_oracle.start_fft_batch(x, n_fft=n_fft)
+        got = an.fft(x, n_fft=n_fft)
+        assert np.array_equal(got.view(np.float64), want.view(np.float64)), (n_fft, n_samples)
+        x32 = x.astype(np.float32)
+        want32 = c_oracle.start_fft_batch(x32.astype(np.float64), n_fft=n_fft)
+        got32 = an.fft(x32, n_fft=n_fft)
+        for q in range(x.shape[0]):
+            scale = max(np.abs(want32[q]).max(), 1e-3)
+            err = np.abs(got32[q].astype(np.complex128) - want32[q]).max()
+            assert err <= 3e-6 * scale + n_samples * float(np.abs(x32[q]).max()) * 1.2e-7, (n_fft, n_samples, q, err, scale)
