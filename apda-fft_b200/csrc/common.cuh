@@ -143,7 +143,7 @@ int launch_fft_f64_fast(apda_ctx *ctx, cudaStream_t st, const double *d_samples,
 bool peaks_f32_fast_supports(int64_t n, int k, int rec_cap);
 bool peaks_large_supports(int64_t n);
 template <typename T>
-size_t peaks_large_workspace_bytes(int64_t n);
+size_t peaks_large_workspace_bytes(int64_t n, int64_t batch);
 template <typename T>
 int launch_peaks_large(apda_ctx *ctx, cudaStream_t st, const T *d_spec, int64_t n, int64_t batch, double fs,
                        const double *d_fs, int k, int rec_cap, int flexible, void *d_rec, void *ws);

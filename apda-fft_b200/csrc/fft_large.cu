@@ -516,7 +516,9 @@ __device__ __forceinline__ unsigned block_scan_incl_1024(unsigned v, unsigned *w
 }
 
 template <typename T>
-__global__ void __launch_bounds__(1024) br_sample_kernel(const T *__restrict__ x, int64_t n, BracketState<T> *st) {
+__global__ void __launch_bounds__(1024) br_sample_kernel(const T *__restrict__ x, int64_t n, BracketState<T> *st, int64_t ld) {
+    x += (int64_t)blockIdx.y * ld;  // blockIdx.y: window of the batch (its own state, bucket copy and result)
+    st += blockIdx.y;
     __shared__ unsigned bins[1024];
     __shared__ unsigned wt[32];
     __shared__ T red_min[32], red_max[32];
@@ -648,7 +650,9 @@ __device__ __forceinline__ void br_stream(const T *__restrict__ x, int64_t n, Bo
 }
 
 template <typename T, int NT>
-__global__ void __launch_bounds__(NT) br_count_kernel(const T *__restrict__ x, int64_t n, BracketState<T> *st) {
+__global__ void __launch_bounds__(NT) br_count_kernel(const T *__restrict__ x, int64_t n, BracketState<T> *st, int64_t ld) {
+    x += (int64_t)blockIdx.y * ld;
+    st += blockIdx.y;
     constexpr int E = 4 * 16 / (int)sizeof(T);
     __shared__ unsigned h[kBrBuckets];
     pdl_trigger();
@@ -708,7 +712,10 @@ __global__ void __launch_bounds__(NT) br_count_kernel(const T *__restrict__ x, i
 
 template <typename T, int NT>
 __global__ void __launch_bounds__(NT) br_compact_kernel(const T *__restrict__ x, int64_t n, BracketState<T> *st,
-                                                               T *__restrict__ bucket) {
+                                                               T *__restrict__ bucket, int64_t ld) {
+    x += (int64_t)blockIdx.y * ld;
+    st += blockIdx.y;
+    bucket += (int64_t)blockIdx.y * n;
     constexpr int E = 4 * 16 / (int)sizeof(T);
     constexpr int PER = kBrBuckets / NT;
     __shared__ unsigned long long wsum[NT / 32];
@@ -866,6 +873,9 @@ __global__ void __launch_bounds__(NT) br_compact_kernel(const T *__restrict__ x,
 template <typename T>
 __global__ void __launch_bounds__(1024) br_finish_kernel(const T *__restrict__ bucket, BracketState<T> *st, int64_t n,
                                                           T *med_out) {
+    bucket += (int64_t)blockIdx.y * n;
+    st += blockIdx.y;
+    med_out += blockIdx.y;
     using K = typename KeyT<T>::type;
     constexpr int kDirect = 256;  // copies up to this size are ranked directly (m^2 comparisons)
     __shared__ K keys[kDirect];
@@ -985,22 +995,32 @@ __global__ void __launch_bounds__(1024) br_finish_kernel(const T *__restrict__ b
     }
 }
 
+// windows of one call that share a launch set (blockIdx.y): a batch of 2^14 ... 2^17-point windows is launch bound otherwise
 template <typename T>
-int large_median(apda_ctx *ctx, cudaStream_t st, const T *d_x, int64_t n, void *state_raw, T *d_med, T *d_bucket) {
+static int64_t median_windows(int64_t n, int64_t batch) {
+    const int64_t fit = std::max<int64_t>(1, ((int64_t)256 << 20) / std::max<int64_t>(1, n * (int64_t)sizeof(T)));
+    return std::max<int64_t>(1, std::min<int64_t>(batch, std::min<int64_t>(fit, 256)));
+}
+
+// medians of `wins` windows (rows of d_x, `ld` apart): states[wins], d_bucket[wins * n], d_med[wins]
+template <typename T>
+int large_median(apda_ctx *ctx, cudaStream_t st, const T *d_x, int64_t n, int64_t ld, int64_t wins, void *state_raw, T *d_med,
+                 T *d_bucket) {
     BracketState<T> *state = reinterpret_cast<BracketState<T> *>(state_raw);
     const bool big = n * (int64_t)sizeof(T) >= (int64_t)16 << 20;
     const int nt = big ? kBrThreadsLarge : kBrThreadsSmall;
     const int64_t per_cta = (int64_t)nt * 4 * (16 / (int)sizeof(T));  // samples per CTA and trip
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + per_cta - 1) / per_cta, (int64_t)ctx->sm_count * (2048 / nt)));
-    br_sample_kernel<T><<<1, 1024, 0, st>>>(d_x, n, state);
+    const dim3 one(1, (unsigned)wins), many((unsigned)grid, (unsigned)wins);
+    br_sample_kernel<T><<<one, 1024, 0, st>>>(d_x, n, state, ld);
     if (big) {
-        APDA_CUDA(apda_launch_pdl(APDA_PDL_MEDIAN, br_count_kernel<T, kBrThreadsLarge>, dim3(grid), dim3(nt), 0, st, d_x, n, state));
-        APDA_CUDA(apda_launch_pdl(APDA_PDL_MEDIAN, br_compact_kernel<T, kBrThreadsLarge>, dim3(grid), dim3(nt), 0, st, d_x, n, state, d_bucket));
+        APDA_CUDA(apda_launch_pdl(APDA_PDL_MEDIAN, br_count_kernel<T, kBrThreadsLarge>, many, dim3(nt), 0, st, d_x, n, state, ld));
+        APDA_CUDA(apda_launch_pdl(APDA_PDL_MEDIAN, br_compact_kernel<T, kBrThreadsLarge>, many, dim3(nt), 0, st, d_x, n, state, d_bucket, ld));
     } else {
-        APDA_CUDA(apda_launch_pdl(APDA_PDL_MEDIAN, br_count_kernel<T, kBrThreadsSmall>, dim3(grid), dim3(nt), 0, st, d_x, n, state));
-        APDA_CUDA(apda_launch_pdl(APDA_PDL_MEDIAN, br_compact_kernel<T, kBrThreadsSmall>, dim3(grid), dim3(nt), 0, st, d_x, n, state, d_bucket));
+        APDA_CUDA(apda_launch_pdl(APDA_PDL_MEDIAN, br_count_kernel<T, kBrThreadsSmall>, many, dim3(nt), 0, st, d_x, n, state, ld));
+        APDA_CUDA(apda_launch_pdl(APDA_PDL_MEDIAN, br_compact_kernel<T, kBrThreadsSmall>, many, dim3(nt), 0, st, d_x, n, state, d_bucket, ld));
     }
-    APDA_CUDA(apda_launch_pdl(APDA_PDL_MEDIAN, br_finish_kernel<T>, dim3(1), dim3(1024), 0, st, (const T *)d_bucket, state, n, d_med));
+    APDA_CUDA(apda_launch_pdl(APDA_PDL_MEDIAN, br_finish_kernel<T>, one, dim3(1024), 0, st, (const T *)d_bucket, state, n, d_med));
     ctx->launches += 4;
     APDA_CUDA(cudaGetLastError());
     return APDA_OK;
@@ -1122,19 +1142,25 @@ int launch_fft_large(apda_ctx *ctx, cudaStream_t st, const T *d_samples, int64_t
     if (!complex_input && flags != APDA_CENTER_NONE) {
         // per-stream scratch: the two host-pipeline streams may run long transforms concurrently
         const size_t med_bytes = ((size_t)batch * sizeof(T) + 255) & ~(size_t)255;
-        constexpr size_t kStateBytes = (sizeof(BracketState<T>) + sizeof(SelectState) + 255) & ~(size_t)255;
-        const size_t need = kStateBytes + med_bytes + (size_t)n_samples * sizeof(T);  // state, medians, bucket copy (worst case: all samples)
+        const int64_t wins = ctx->generic_only ? 1 : median_windows<T>(n_samples, batch);
+        const size_t state_bytes = (std::max(sizeof(BracketState<T>) * (size_t)wins, sizeof(SelectState)) + 255) & ~(size_t)255;
+        // states, medians, bucket copies (worst case: all samples of every window of a launch set)
+        const size_t need = state_bytes + med_bytes + (size_t)wins * (size_t)n_samples * sizeof(T);
         auto &slot = ctx->stream_scratch[st];
         if (need > slot.second) {
             APDA_CUDA(cudaStreamSynchronize(st));
             APDA_TRY(apda_reserve(&slot.first, &slot.second, need));
         }
         SelectState *state = reinterpret_cast<SelectState *>(slot.first);
-        d_med = reinterpret_cast<T *>(reinterpret_cast<char *>(slot.first) + kStateBytes);
-        T *d_bucket = reinterpret_cast<T *>(reinterpret_cast<char *>(slot.first) + kStateBytes + med_bytes);
-        for (int64_t w = 0; w < batch; ++w) {
-            if (ctx->generic_only) APDA_TRY(large_median_passes<T>(ctx, st, d_samples + w * ld, n_samples, state, d_med + w));
-            else APDA_TRY(large_median<T>(ctx, st, d_samples + w * ld, n_samples, slot.first, d_med + w, d_bucket));
+        d_med = reinterpret_cast<T *>(reinterpret_cast<char *>(slot.first) + state_bytes);
+        T *d_bucket = reinterpret_cast<T *>(reinterpret_cast<char *>(slot.first) + state_bytes + med_bytes);
+        if (ctx->generic_only) {
+            for (int64_t w = 0; w < batch; ++w)
+                APDA_TRY(large_median_passes<T>(ctx, st, d_samples + w * ld, n_samples, state, d_med + w));
+        } else {
+            for (int64_t w0 = 0; w0 < batch; w0 += wins)
+                APDA_TRY(large_median<T>(ctx, st, d_samples + w0 * ld, n_samples, ld, std::min<int64_t>(wins, batch - w0), slot.first,
+                                         d_med + w0, d_bucket));
         }
     }
 

@@ -325,7 +325,7 @@ __global__ void mag_helpers_kernel(const double *__restrict__ mags, int n, int i
 
 template <typename T>
 size_t peaks_mag_workspace_bytes(apda_ctx *ctx, int64_t n, int64_t batch) {
-    if (peaks_large_supports(n) && !ctx->generic_only) return peaks_large_workspace_bytes<T>(n);
+    if (peaks_large_supports(n) && !ctx->generic_only) return peaks_large_workspace_bytes<T>(n, batch);
     Layout lay = make_layout<T>((int)(n / 2));
     if (lay.bytes + 4096 <= (size_t)ctx->smem_optin) return 0;
     return lay.bytes * (size_t)batch;

@@ -14,6 +14,7 @@
 //
 // Decision semantics are those of peaks.cu (utils/get_peak_prominence.py:149-226, utils/get_peak_resolution.py:80-128).
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 #include "peaks_common.cuh"
@@ -21,6 +22,12 @@
 namespace {
 
 constexpr int SB = 1024;  // bins per summary block
+
+// scratch pointer of window blockIdx.y of a launch set: every window has its own slab, `stride` bytes apart
+template <typename P>
+__device__ __forceinline__ P *win_slab(P *p, size_t stride) {
+    return reinterpret_cast<P *>(reinterpret_cast<char *>(const_cast<typename std::remove_const<P>::type *>(p)) + blockIdx.y * stride);
+}
 
 struct LargeState {
     double mean, sd, thr;
@@ -34,12 +41,17 @@ constexpr int MAGS_WARPS = 8;
 template <typename T, int WPB>
 __global__ void __launch_bounds__(32 * MAGS_WARPS)
 mags_kernel(const typename vec2<T>::type *__restrict__ spec, T *__restrict__ mags, T *__restrict__ bmax,
-            T *__restrict__ bmin, dd *__restrict__ part, int nblk) {
+            T *__restrict__ bmin, dd *__restrict__ part, int nblk, int64_t n, size_t stride) {
     constexpr int SEG = SB / WPB, PER_LANE = SEG / 32, UNR = PER_LANE < 8 ? PER_LANE : 8, BPC = MAGS_WARPS / WPB;
     __shared__ dd red[2 * MAGS_WARPS];
     __shared__ T rmx[MAGS_WARPS], rmn[MAGS_WARPS];
     pdl_trigger();
     pdl_wait();  // the spectrum usually comes from the kernel in front (K2's last pass)
+    spec += (int64_t)blockIdx.y * n;
+    mags = win_slab(mags, stride);
+    bmax = win_slab(bmax, stride);
+    bmin = win_slab(bmin, stride);
+    part = win_slab(part, stride);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     dd sx[2] = {{0.0, 0.0}, {0.0, 0.0}}, sxx[2] = {{0.0, 0.0}, {0.0, 0.0}};  // two independent chains per lane
     for (int blk = blockIdx.x * BPC + warp / WPB; blk < nblk; blk += gridDim.x * BPC) {
@@ -123,10 +135,16 @@ mags_kernel(const typename vec2<T>::type *__restrict__ spec, T *__restrict__ mag
 template <typename T>
 __global__ void __launch_bounds__(1024)
 stats_kernel(const dd *__restrict__ part, int npart, const T *__restrict__ bmax, const T *__restrict__ bmin,
-             T *__restrict__ smax, T *__restrict__ smin, int nblk, int half, LargeState *st) {
+             T *__restrict__ smax, T *__restrict__ smin, int nblk, int half, LargeState *st, size_t stride) {
     __shared__ dd red[64];
     pdl_trigger();
     pdl_wait();
+    part = win_slab(part, stride);
+    bmax = win_slab(bmax, stride);
+    bmin = win_slab(bmin, stride);
+    smax = win_slab(smax, stride);
+    smin = win_slab(smin, stride);
+    st = win_slab(st, stride);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < nblk; i += 1024) {  // nblk is a multiple of 32: a warp's lanes hold one group of 32 blocks
         T mx = bmax[i], mn = bmin[i];
@@ -174,9 +192,14 @@ stats_kernel(const dd *__restrict__ part, int npart, const T *__restrict__ bmax,
 
 template <typename T, bool FLEX>
 __global__ void __launch_bounds__(256)
-hot_kernel(const T *__restrict__ mags, const T *__restrict__ bmax, int half, LargeState *st, int *__restrict__ cand, int cap) {
+hot_kernel(const T *__restrict__ mags, const T *__restrict__ bmax, int half, LargeState *st, int *__restrict__ cand, int cap,
+           size_t stride) {
     pdl_trigger();
     pdl_wait();
+    mags = win_slab(mags, stride);
+    bmax = win_slab(bmax, stride);
+    st = win_slab(st, stride);
+    cand = win_slab(cand, stride);
     const double thr = st->thr;
     if (!((double)bmax[blockIdx.x] > thr)) return;
     const int b0 = blockIdx.x * SB, lane = threadIdx.x & 31;
@@ -268,9 +291,18 @@ template <typename T>
 __global__ void __launch_bounds__(EVAL_THREADS)
 eval_kernel(const T *__restrict__ mags, const T *__restrict__ bmax, const T *__restrict__ bmin, const T *__restrict__ smax,
             const T *__restrict__ smin, int64_t n, int half, double fs_all, const double *__restrict__ fs_ptr, LargeState *st,
-            const int *__restrict__ cand, Found *__restrict__ found, int cap) {
+            const int *__restrict__ cand, Found *__restrict__ found, int cap, size_t stride) {
     pdl_trigger();
     pdl_wait();
+    mags = win_slab(mags, stride);
+    bmax = win_slab(bmax, stride);
+    bmin = win_slab(bmin, stride);
+    smax = win_slab(smax, stride);
+    smin = win_slab(smin, stride);
+    st = win_slab(st, stride);
+    cand = win_slab(cand, stride);
+    found = win_slab(found, stride);
+    if (fs_ptr) fs_ptr += blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * EVAL_THREADS + threadIdx.x) >> 5, nwarp = (gridDim.x * EVAL_THREADS) >> 5;
     const int ncand = min(st->ncand, cap);
@@ -302,9 +334,16 @@ eval_kernel(const T *__restrict__ mags, const T *__restrict__ bmax, const T *__r
 template <typename T>
 __global__ void __launch_bounds__(1024)
 pick_flexible_kernel(const T *__restrict__ mags, int64_t n, double fs_all, const double *__restrict__ fs_ptr, int k, int rec_cap,
-                     LargeState *st, const Found *__restrict__ found, int *__restrict__ acc_slot, unsigned char *__restrict__ rec) {
+                     LargeState *st, const Found *__restrict__ found, int *__restrict__ acc_slot, unsigned char *__restrict__ rec,
+                     size_t stride) {
     pdl_trigger();
     pdl_wait();
+    mags = win_slab(mags, stride);
+    st = win_slab(st, stride);
+    found = win_slab(found, stride);
+    acc_slot = win_slab(acc_slot, stride);
+    rec += (size_t)blockIdx.y * APDA_REC_BYTES(rec_cap);
+    if (fs_ptr) fs_ptr += blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double fs = fs_ptr ? *fs_ptr : fs_all;
     const double df = div_rn(fs, (double)n);
@@ -399,12 +438,18 @@ pick_flexible_kernel(const T *__restrict__ mags, int64_t n, double fs_all, const
 template <typename T>
 __global__ void __launch_bounds__(1024)
 pick_rigid_kernel(T *__restrict__ mags, int64_t n, int half, double fs_all, const double *__restrict__ fs_ptr, int k, int rec_cap, LargeState *st,
-                  const int *__restrict__ cand, int cap, int *__restrict__ acc_idx, unsigned char *__restrict__ rec) {
+                  const int *__restrict__ cand, int cap, int *__restrict__ acc_idx, unsigned char *__restrict__ rec, size_t stride) {
     __shared__ double best_m[32];
     __shared__ int best_j[32];
     __shared__ int ctl[4];
     pdl_trigger();
     pdl_wait();
+    mags = win_slab(mags, stride);
+    st = win_slab(st, stride);
+    cand = win_slab(cand, stride);
+    acc_idx = win_slab(acc_idx, stride);
+    rec += (size_t)blockIdx.y * APDA_REC_BYTES(rec_cap);
+    if (fs_ptr) fs_ptr += blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nhot = min(st->ncand, cap);
     const double thr = st->thr;
@@ -529,20 +574,31 @@ LargeLayout large_layout(int64_t half) {
 
 bool peaks_large_supports(int64_t n) { return is_pow2_i64(n) && n >= (int64_t(1) << 16) && n <= (int64_t(1) << 31); }
 
+// windows of one call that share a launch set (blockIdx.y), each with its own scratch slab: a batch of 2^16 ... 2^18-point
+// spectra is launch bound otherwise (five dependent launches per window)
 template <typename T>
-size_t peaks_large_workspace_bytes(int64_t n) {
-    return large_layout<T>(n / 2).bytes;
+static int64_t large_windows(int64_t n, int64_t batch) {
+    const int64_t slab = (int64_t)large_layout<T>(n / 2).bytes;
+    const int64_t fit = std::max<int64_t>(1, ((int64_t)192 << 20) / slab);
+    return std::max<int64_t>(1, std::min<int64_t>(batch, std::min<int64_t>(fit, 64)));
 }
-template size_t peaks_large_workspace_bytes<double>(int64_t);
-template size_t peaks_large_workspace_bytes<float>(int64_t);
 
-// windows are processed one after the other (long windows are few); ws holds one window's scratch
+template <typename T>
+size_t peaks_large_workspace_bytes(int64_t n, int64_t batch) {
+    return large_layout<T>(n / 2).bytes * (size_t)large_windows<T>(n, batch);
+}
+template size_t peaks_large_workspace_bytes<double>(int64_t, int64_t);
+template size_t peaks_large_workspace_bytes<float>(int64_t, int64_t);
+
+// ws: peaks_large_workspace_bytes(n, batch') bytes for some batch' >= batch
 template <typename T>
 int launch_peaks_large(apda_ctx *ctx, cudaStream_t st, const T *d_spec, int64_t n, int64_t batch, double fs,
                        const double *d_fs, int k, int rec_cap, int flexible, void *d_rec, void *ws) {
     using V2 = typename vec2<T>::type;
     const int64_t half = n / 2;
     const LargeLayout l = large_layout<T>(half);
+    const size_t stride = l.bytes;
+    const int64_t wins = large_windows<T>(n, batch);
     char *base = reinterpret_cast<char *>(ws);
     T *mags = reinterpret_cast<T *>(base + l.mags);
     T *bmax = reinterpret_cast<T *>(base + l.bmax), *bmin = reinterpret_cast<T *>(base + l.bmin);
@@ -552,32 +608,37 @@ int launch_peaks_large(apda_ctx *ctx, cudaStream_t st, const T *d_spec, int64_t 
     int *cand = reinterpret_cast<int *>(base + l.cand);
     Found *found = reinterpret_cast<Found *>(base + l.found);
     int *acc = reinterpret_cast<int *>(base + l.acc);
-    // one warp per candidate; tone spectra have a handful, noise-like ones ~2 % of the bins
-    const int eval_ctas = (int)std::min<int64_t>((int64_t)ctx->sm_count * 8, std::max<int64_t>(1, l.cap / (EVAL_THREADS / 32)));
+    // one warp per candidate; tone spectra have a handful, noise-like ones ~2 % of the bins.  The chip's resident CTAs are
+    // shared among the windows of a launch set (tens of thousands of CTAs that find no candidate would cost more than the walks)
+    const int64_t eval_max = std::max<int64_t>(1, l.cap / (EVAL_THREADS / 32));
+    const int eval_ctas = (int)std::min<int64_t>(eval_max, std::max<int64_t>(4, (int64_t)ctx->sm_count * 8 / wins));
     const int mags_ctas = l.nblk <= 1024 ? l.nblk : std::min(l.nblk / MAGS_WARPS, 1024);  // <= 1024 partial sums
-    for (int64_t w = 0; w < batch; ++w) {
-        const V2 *spec = reinterpret_cast<const V2 *>(d_spec) + w * n;
-        unsigned char *rec = reinterpret_cast<unsigned char *>(d_rec) + w * APDA_REC_BYTES(rec_cap);
-        const double *fs_ptr = d_fs ? d_fs + w : nullptr;
-        const dim3 mg(mags_ctas), mb(32 * MAGS_WARPS), hg(l.nblk);
-        if (l.nblk <= 1024) APDA_CUDA(apda_launch_pdl(APDA_PDL_K3, mags_kernel<T, MAGS_WARPS>, mg, mb, 0, st, spec, mags, bmax, bmin, part, l.nblk));
-        else APDA_CUDA(apda_launch_pdl(APDA_PDL_K3, mags_kernel<T, 1>, mg, mb, 0, st, spec, mags, bmax, bmin, part, l.nblk));
-        APDA_CUDA(apda_launch_pdl(APDA_PDL_K3, stats_kernel<T>, dim3(1), dim3(1024), 0, st, (const dd *)part, mags_ctas, (const T *)bmax,
-                                  (const T *)bmin, smax, smin, l.nblk, (int)half, state));
+    for (int64_t w0 = 0; w0 < batch; w0 += wins) {
+        const unsigned wy = (unsigned)std::min<int64_t>(wins, batch - w0);
+        const V2 *spec = reinterpret_cast<const V2 *>(d_spec) + w0 * n;
+        unsigned char *rec = reinterpret_cast<unsigned char *>(d_rec) + w0 * APDA_REC_BYTES(rec_cap);
+        const double *fs_ptr = d_fs ? d_fs + w0 : nullptr;
+        const dim3 mg(mags_ctas, wy), mb(32 * MAGS_WARPS), hg(l.nblk, wy), one(1, wy), eg(eval_ctas, wy);
+        if (l.nblk <= 1024)
+            APDA_CUDA(apda_launch_pdl(APDA_PDL_K3, mags_kernel<T, MAGS_WARPS>, mg, mb, 0, st, spec, mags, bmax, bmin, part, l.nblk, n, stride));
+        else
+            APDA_CUDA(apda_launch_pdl(APDA_PDL_K3, mags_kernel<T, 1>, mg, mb, 0, st, spec, mags, bmax, bmin, part, l.nblk, n, stride));
+        APDA_CUDA(apda_launch_pdl(APDA_PDL_K3, stats_kernel<T>, one, dim3(1024), 0, st, (const dd *)part, mags_ctas, (const T *)bmax,
+                                  (const T *)bmin, smax, smin, l.nblk, (int)half, state, stride));
         if (flexible) {
             APDA_CUDA(apda_launch_pdl(APDA_PDL_K3, hot_kernel<T, true>, hg, dim3(256), 0, st, (const T *)mags, (const T *)bmax, (int)half, state, cand,
-                                      l.cap));
-            APDA_CUDA(apda_launch_pdl(APDA_PDL_K3, eval_kernel<T>, dim3(eval_ctas), dim3(EVAL_THREADS), 0, st, (const T *)mags, (const T *)bmax,
+                                      l.cap, stride));
+            APDA_CUDA(apda_launch_pdl(APDA_PDL_K3, eval_kernel<T>, eg, dim3(EVAL_THREADS), 0, st, (const T *)mags, (const T *)bmax,
                                       (const T *)bmin, (const T *)smax, (const T *)smin, n, (int)half, fs, fs_ptr, state,
-                                      (const int *)cand, found, l.cap));
-            APDA_CUDA(apda_launch_pdl(APDA_PDL_K3, pick_flexible_kernel<T>, dim3(1), dim3(1024), 0, st, (const T *)mags, n, fs, fs_ptr, k, rec_cap,
-                                      state, (const Found *)found, acc, rec));
+                                      (const int *)cand, found, l.cap, stride));
+            APDA_CUDA(apda_launch_pdl(APDA_PDL_K3, pick_flexible_kernel<T>, one, dim3(1024), 0, st, (const T *)mags, n, fs, fs_ptr, k, rec_cap,
+                                      state, (const Found *)found, acc, rec, stride));
             ctx->launches += 1;
         } else {
             APDA_CUDA(apda_launch_pdl(APDA_PDL_K3, hot_kernel<T, false>, hg, dim3(256), 0, st, (const T *)mags, (const T *)bmax, (int)half, state, cand,
-                                      l.cap));
-            APDA_CUDA(apda_launch_pdl(APDA_PDL_K3, pick_rigid_kernel<T>, dim3(1), dim3(1024), 0, st, mags, n, (int)half, fs, fs_ptr, k, rec_cap, state,
-                                      (const int *)cand, l.cap, acc, rec));
+                                      l.cap, stride));
+            APDA_CUDA(apda_launch_pdl(APDA_PDL_K3, pick_rigid_kernel<T>, one, dim3(1024), 0, st, mags, n, (int)half, fs, fs_ptr, k, rec_cap, state,
+                                      (const int *)cand, l.cap, acc, rec, stride));
         }
         ctx->launches += 4;
     }

@@ -673,3 +673,33 @@ def test_quantised_windows_exact_median(n_fft, an):
             scale = max(np.abs(want32[q]).max(), 1e-3)
             err = np.abs(got32[q].astype(np.complex128) - want32[q]).max()
             assert err <= 3e-6 * scale + n_samples * float(np.abs(x32[q]).max()) * 1.2e-7, (n_fft, n_samples, q, err, scale)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# batches of long windows: the median kernels of K2 and the large-form picker run many windows per launch set
+# ---------------------------------------------------------------------------------------------------------------
+def test_batches_of_long_windows_share_launch_sets(an):
+    """N = 2^14 (fp64) and 2^15 ... 2^16 windows in batches larger than one launch set (256 windows for the median, 64 for
+    the picker): every window's spectrum is bit-identical to the oracle's (fp64) and every record equals the one the same
+    window gets when it is sent alone; different lengths, medians and peak positions per window."""
+    rng = np.random.default_rng(99)
+    for n, b, ns in ((1 << 14, 300, 16000), (1 << 15, 70, 1 << 15), (1 << 16, 70, 60001)):
+        i = np.arange(ns, dtype=np.float64)
+        x = np.empty((b, ns))
+        for w in range(b):
+            x[w] = np.round(0.5 * np.sin(2 * np.pi * (101.6 + 3 * w) * i / n) + 0.2 * np.sin(2 * np.pi * 1498.0 * i / n + 0.1 * w)
+                            + 0.02 * rng.standard_normal(ns) + 0.01 * w, 6)
+        got = an.fft(x, n_fft=n)
+        want = c_oracle.start_fft_batch(x, n_fft=n)
+        assert np.array_equal(got.view(np.float64), want.view(np.float64)), n
+        got32 = an.fft(x.astype(np.float32), n_fft=n)
+        scale = np.abs(want).max(axis=1, keepdims=True)
+        assert (np.abs(got32.astype(np.complex128) - want) <= 2e-5 * scale).all(), n
+        for flexible in (True, False):
+            recs = an.analyze(x, 250.0, flexible=flexible, n_fft=n)
+            assert (recs["status"] == 0).all()
+            for w in (0, 1, 63, 64, 65, b - 1):
+                alone = an.analyze(x[w:w + 1], 250.0, flexible=flexible, n_fft=n)
+                assert recs[w].tobytes() == alone[0].tobytes(), (n, flexible, w)
+            top = recs["pk"]["idx"][:, 0]
+            assert np.array_equal(top, np.round(101.6 + 3 * np.arange(b)).astype(top.dtype)), (n, flexible)
