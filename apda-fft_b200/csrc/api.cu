@@ -297,7 +297,14 @@ static int fft_dispatch(apda_ctx *ctx, cudaStream_t st, const T *d_samples, int6
     if (sizeof(T) == 8 && !complex_in && !ctx->generic_only && fft_f64_fast_supports(N))
         return launch_fft_f64_fast(ctx, st, reinterpret_cast<const double *>(d_samples), n_samples, ld, batch, N, flags,
                                    reinterpret_cast<double *>(d_spec));
-    if (N <= fft_smem_max_n<T>(ctx)) return launch_fft_smem<T>(ctx, st, d_samples, n_samples, ld, batch, N, flags, d_spec, complex_in);
+    // largest N that goes to the one-CTA-per-window kernel: fp32 N = 16384 fits its shared memory, but two K2 passes are
+    // faster there (277 vs 483 ns per window); APDA_SMEM_MAXN overrides for A/B runs
+    static const int64_t smem_cap = [] {
+        const char *e = getenv("APDA_SMEM_MAXN");
+        return e && e[0] ? (int64_t)atoll(e) : (int64_t)8192;
+    }();
+    if (N <= std::min(fft_smem_max_n<T>(ctx), smem_cap))
+        return launch_fft_smem<T>(ctx, st, d_samples, n_samples, ld, batch, N, flags, d_spec, complex_in);
     return launch_fft_large<T>(ctx, st, d_samples, n_samples, ld, batch, N, flags, d_spec, complex_in);
 }
 
