@@ -141,6 +141,14 @@ __device__ __forceinline__ double round_dec4_units(double x) {
     return n;
 }
 
+// Exact half of the flexible picker's "hump" test (utils/get_peak_prominence.py:199-207) for ONE accepted peak; out of
+// line on purpose: the callers first run a product-only pre-filter that proves most pairs more than 5 % apart, and the
+// roundings / divisions below must not be hoisted in front of that filter (they were: ~140 warp instructions per window).
+static __device__ __noinline__ bool hump_exact(int c_idx, int ja, double df, double cprom, double key_units) {
+    const double cf = round_dec4_d(mul_rn((double)c_idx, df)), af = round_dec4_d(mul_rn((double)ja, df));
+    return div_rn(fabs(sub_rn(cf, af)), af) < 0.05 && div_rn(cprom, div_rn(key_units, 1e4)) < 0.10;
+}
+
 __device__ __forceinline__ float4 ldg_stream(const float4 *p) {
     float4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
@@ -265,15 +273,19 @@ __device__ __forceinline__ int order_and_exclude(const SlotT<T> *slots, int nslo
     // words: largest round(mag, 4), ties -> lowest idx), at most k + rejected times
     double key[PER];
     int sidx[PER];
+    int left = 0;
 #pragma unroll
     for (int r = 0; r < PER; ++r) {
         const int e = lane + 32 * r;
         const bool ok = e < nslot && slots[e].width != 0;
         sidx[r] = ok ? (int)slots[e].idx : -1;
         key[r] = ok ? round_dec4_units((double)mags[P::addr(sidx[r])]) : -1.0;
+        left += ok ? 1 : 0;
     }
+    left = __reduce_add_sync(0xffffffffu, left);  // gated candidates not yet extracted: no arg-max round for an empty list
     int na = 0;
-    while (na < k) {
+    while (na < k && left > 0) {
+        --left;
         double bk = key[0];
         int bi = sidx[0], br = 0;
 #pragma unroll
@@ -303,8 +315,7 @@ __device__ __forceinline__ int order_and_exclude(const SlotT<T> *slots, int nslo
             const double fc = mul_rn((double)c_idx, df), fa = mul_rn((double)ja, df);
             // |round4(fc) - round4(fa)| >= |fc - fa| - 1e-4 and round4(fa) <= fa + 5e-5: most pairs are provably > 5 % apart
             if (fabs(fc - fa) - 1.0e-4 > 0.05 * (fa + 5.0e-5) * (1.0 + 1e-9)) continue;
-            const double cf = round_dec4_d(fc), af = round_dec4_d(fa);
-            if (div_rn(fabs(sub_rn(cf, af)), af) < 0.05 && div_rn((double)cprom, div_rn(bk, 1e4)) < 0.10) hump = true;
+            if (hump_exact(c_idx, ja, df, (double)cprom, bk)) hump = true;
         }
         if (!hump) {
             if (lane == 0) {
@@ -447,8 +458,7 @@ __device__ __forceinline__ int order_eval_exclude_lazy(const SlotT<T> *slots, in
             const int ja = reinterpret_cast<const int *>(rec_s + 8 + 24 * a)[0];
             const double fc = mul_rn((double)c_idx, df), fa = mul_rn((double)ja, df);
             if (fabs(fc - fa) - 1.0e-4 > 0.05 * (fa + 5.0e-5) * (1.0 + 1e-9)) continue;
-            const double cf = round_dec4_d(fc), af = round_dec4_d(fa);
-            if (div_rn(fabs(sub_rn(cf, af)), af) < 0.05 && div_rn((double)cprom, div_rn(bk, 1e4)) < 0.10) hump = true;
+            if (hump_exact(c_idx, ja, df, (double)cprom, bk)) hump = true;
         }
         if (!hump) {
             if (lane == 0) {
@@ -546,6 +556,21 @@ __device__ __forceinline__ int k3_rigid(T *mags, const List *hot, int nslot, T t
     return na;
 }
 
+// fp32 tie test of the four bins jb..jb+3 (see APDA_STATUS_FP32_TIE): a hot bin equal to its right neighbour and higher
+// than both outer neighbours.  Out of line: reached only when the quad holds two equal adjacent magnitudes.
+template <typename T, int HALF>
+static __device__ __noinline__ bool plateau_top_in_quad(const T *mags, int jb, T thr_f) {
+    using P = K3<T, HALF>;
+    bool tie = false;
+    for (int j = jb; j < jb + 4; ++j) {
+        const T e = mags[P::addr(j)];
+        if (e > thr_f && j >= 1 && j + 1 <= HALF - 1 && e == mags[P::addr(j + 1)] && e > mags[P::addr(j - 1)] &&
+            (j + 2 > HALF - 1 || e > mags[P::addr(j + 2)]))
+            tie = true;
+    }
+    return tie;
+}
+
 // Everything after the magnitudes are in shared memory: hot-bin list, picker, record.  Shared by the pipeline kernels
 // (peaks_f32_fast.cu, peaks_f64_fast.cu).  Runs on ONE warp.
 // thr_f: largest T with  m > thr  <=>  m > thr_f  for every magnitude m (the threshold itself when T is double).
@@ -571,34 +596,39 @@ __device__ __forceinline__ void k3_tail(T *mags, SlotT<T> *slots, const int slot
             cmin = vmin(cmin, vmin(vmin(v.x, v.y), vmin(v.z, v.w)));
             if (m4 > thr_f) hotq |= 1u << q;
         }
-        while (hotq) {  // rare: a handful of bins per window
+        while (hotq) {  // rare: a handful of quads per window; every test of the quad on registers, one counter update
             const int q = __ffs(hotq) - 1;
             hotq &= hotq - 1;
+            const int jb = C * lane + 4 * q;  // first bin of the quad
             const Quad<T> v = lds_quad(ch + 4 * q);
-            const T e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (e[u] > thr_f) {
-                    const int j = C * lane + 4 * q + u;
-                    bool take = true;
-                    if (FLEX)  // strict local maximum, candidates j in [1, HALF-2]
-                        take = j >= 1 && j <= HALF - 2 && e[u] > mags[P::addr(j - 1)] && e[u] > mags[P::addr(j + 1)];
-                    if (take) {
-                        const int pos = atomicAdd(&(*nslot_ptr), 1);
-                        if (FLEX) {
-                            if (pos < slot_cap) slots[pos].idx = (uint16_t)j;
-                        } else {
-                            if (pos < P::HOT_CAP) reinterpret_cast<uint16_t *>(slots)[pos] = (uint16_t)j;
-                        }
+            const T left = mags[P::addr(jb > 0 ? jb - 1 : 0)];                   // jb == 0: v.x itself, v.x > left fails
+            const T right = mags[P::addr(jb + 4 < HALF ? jb + 4 : HALF - 1)];    // last quad: v.w itself
+            unsigned take;
+            if (FLEX)  // strict local maxima above the threshold, candidates j in [1, HALF-2]
+                take = (v.x > thr_f && jb >= 1 && v.x > left && v.x > v.y ? 1u : 0u) |
+                       (v.y > thr_f && v.y > v.x && v.y > v.z ? 2u : 0u) |
+                       (v.z > thr_f && v.z > v.y && v.z > v.w ? 4u : 0u) |
+                       (v.w > thr_f && jb + 3 <= HALF - 2 && v.w > v.z && v.w > right ? 8u : 0u);
+            else
+                take = (v.x > thr_f ? 1u : 0u) | (v.y > thr_f ? 2u : 0u) | (v.z > thr_f ? 4u : 0u) | (v.w > thr_f ? 8u : 0u);
+            if (take) {
+                int pos = atomicAdd(&(*nslot_ptr), __popc(take));
+                do {
+                    const int j = jb + __ffs(take) - 1;
+                    take &= take - 1;
+                    if (FLEX) {
+                        if (pos < slot_cap) slots[pos].idx = (uint16_t)j;
+                    } else {
+                        if (pos < P::HOT_CAP) reinterpret_cast<uint16_t *>(slots)[pos] = (uint16_t)j;
                     }
-                    // Two adjacent bins that are EQUAL in fp32 and higher than both outer neighbours: neither is a strict
-                    // local maximum, so no peak is reported there, while the fp64 reference (whose magnitudes differ in
-                    // the bits fp32 drops) reports one of them.  The window is flagged so the caller can re-run it in fp64.
-                    if (sizeof(T) == 4 && j >= 1 && j + 1 <= HALF - 1 && e[u] == mags[P::addr(j + 1)] &&
-                        e[u] > mags[P::addr(j - 1)] && (j + 2 > HALF - 1 || e[u] > mags[P::addr(j + 2)]))
-                        tie = true;
-                }
+                    ++pos;
+                } while (take);
             }
+            // Two adjacent bins that are EQUAL in fp32 and higher than both outer neighbours: neither is a strict
+            // local maximum, so no peak is reported there, while the fp64 reference (whose magnitudes differ in
+            // the bits fp32 drops) reports one of them.  The window is flagged so the caller can re-run it in fp64.
+            if (sizeof(T) == 4 && (v.x == v.y || v.y == v.z || v.z == v.w || v.w == right))
+                tie = tie || plateau_top_in_quad<T, HALF>(mags, jb, thr_f);
         }
     }
     __syncwarp();
