@@ -333,4 +333,15 @@ __device__ __forceinline__ double dd_sqrt_to_double(dd a) {  // correctly rounde
     dd r = dd_add(a, dd_neg(s2));
     return add_rn(s, div_rn(r.hi, mul_rn(2.0, s)));
 }
+// approximate reciprocal / square root (one MUFU each) for values that only STEER an exact algorithm (selection pivots)
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 #endif  // __CUDACC__

@@ -266,11 +266,12 @@ __device__ float select_median(const float2 (&v2)[16], int n_valid, uint32_t *sh
             s2 += shf[8 + w];
             if (!FULL) cntv += (int)sh[16 + w];
         }
-        const float inv = 1.f / (float)max(cntv, 1);
+        // steering values only (the counts decide): approximate reciprocal / root
+        const float inv = rcp_approx((float)max(cntv, 1));
         mean = s1 * inv;
-        sd = sqrtf(fmaxf(fmaf(-mean, mean, s2 * inv), 0.f));
+        sd = sqrt_approx(fmaxf(fmaf(-mean, mean, s2 * inv), 0.f));
     }
-    const float density = (float)n_valid / fmaxf(2.5f * sd, 1e-30f);  // values per unit near the centre
+    const float inv_density = fmaxf(2.5f * sd, 1e-30f) * rcp_approx((float)n_valid);  // 1 / (values per unit near the centre)
 
     float lo = -CUDART_INF_F, hi = CUDART_INF_F;  // bracket [lo, hi): c_lo = #(v < lo) <= r_lo, c_hi = #(v < hi) > r_hi
     int c_lo = 0, c_hi = n_valid;
@@ -317,14 +318,14 @@ __device__ float select_median(const float2 (&v2)[16], int n_valid, uint32_t *sh
             if (!(lo_next < hi)) break;  // a single distinct value is left in the bracket
             const float want = (float)r_lo + 0.5f;
             if (lo == -CUDART_INF_F) {
-                pivot = hi - 1.5f * fmaxf((float)c_hi - want, 1.f) / density * (float)(1 << min(round - 1, 20));
+                pivot = hi - 1.5f * fmaxf((float)c_hi - want, 1.f) * inv_density * (float)(1 << min(round - 1, 20));
             } else if (hi == CUDART_INF_F) {
-                pivot = lo + 1.5f * fmaxf(want - (float)c_lo, 1.f) / density * (float)(1 << min(round - 1, 20));
+                pivot = lo + 1.5f * fmaxf(want - (float)c_lo, 1.f) * inv_density * (float)(1 << min(round - 1, 20));
             } else if (round % 3 == 2) {  // key-space bisection: guarantees termination in <= 3*32 rounds
                 const uint32_t a = ordered_key(lo), b = ordered_key(hi);
                 pivot = key_value(a + ((b - a) >> 1), 0.f);
             } else {
-                pivot = lo + (hi - lo) * ((want - (float)c_lo) / (float)(c_hi - c_lo));
+                pivot = lo + (hi - lo) * __fdividef(want - (float)c_lo, (float)(c_hi - c_lo));
             }
             if (!(pivot > lo)) pivot = lo_next;       // also catches NaN
             if (!(pivot < hi)) pivot = lo_next;

@@ -108,11 +108,16 @@ __device__ double select_median_f64(const double (&val)[16], int n_valid, double
             s2 += shd[2 + 16 + w];
             cv += (int)cnt_part[w];
         }
-        const double nv = (double)max(cv, 1);
-        mean = s1 / nv;
-        sd = sqrt(fmax(s2 / nv - mean * mean, 0.0));
+        // steering values only (the counts decide): single-precision reciprocals / roots instead of fp64 divisions and
+        // a square root on the pipe the transform needs; data outside the float range takes the exact forms
+        const double inv_nv = (double)rcp_approx((float)max(cv, 1));
+        mean = s1 * inv_nv;
+        const double var = fmax(s2 * inv_nv - mean * mean, 0.0);
+        const float var_f = (float)var;
+        sd = (var_f > 1e-30f && var_f < 1e30f) ? (double)sqrt_approx(var_f) : sqrt(var);
     }
-    const double density = (double)n_valid / fmax(2.5 * sd, 1e-300);
+    // 1 / (values per unit near the centre)
+    const double inv_density = fmax(2.5 * sd, 1e-300) * (double)rcp_approx((float)n_valid);
     double lo = -CUDART_INF, hi = CUDART_INF;  // bracket [lo, hi): c_lo = #(v < lo) <= r_lo, c_hi = #(v < hi) > r_hi
     int c_lo = 0, c_hi = n_valid;
     double pivot = mean;
@@ -151,14 +156,14 @@ __device__ double select_median_f64(const double (&val)[16], int n_valid, double
             if (!(lo_next < hi)) break;
             const double want = (double)r_lo + 0.5;
             if (lo == -CUDART_INF) {
-                pivot = hi - 1.5 * fmax((double)c_hi - want, 1.0) / density * (double)(1 << min(round - 1, 30));
+                pivot = hi - 1.5 * fmax((double)c_hi - want, 1.0) * inv_density * (double)(1 << min(round - 1, 30));
             } else if (hi == CUDART_INF) {
-                pivot = lo + 1.5 * fmax(want - (double)c_lo, 1.0) / density * (double)(1 << min(round - 1, 30));
+                pivot = lo + 1.5 * fmax(want - (double)c_lo, 1.0) * inv_density * (double)(1 << min(round - 1, 30));
             } else if (round % 4 == 0) {  // key-space bisection bounds the worst case
                 const uint64_t a = ordered_key(lo), b = ordered_key(hi);
                 pivot = key_value(a + ((b - a) >> 1), 0.0);
             } else {
-                pivot = lo + (hi - lo) * ((want - (double)c_lo) / (double)(c_hi - c_lo));
+                pivot = lo + (hi - lo) * (double)__fdividef((float)r_lo + 0.5f - (float)c_lo, (float)(c_hi - c_lo));
             }
             if (!(pivot > lo)) pivot = lo_next;
             if (!(pivot < hi)) pivot = lo_next;

@@ -485,9 +485,7 @@ template <typename T, int HALF, typename P, typename List>
 __device__ __forceinline__ int k3_rigid(T *mags, const List *hot, int nslot, T thr_f, double df, int k, int lane,
                                         unsigned char *rec_s) {
     const double distance = sub_rn(mul_rn(2.0, df), mul_rn(1.0, df));
-    int acc_idx[5];
-#pragma unroll
-    for (int a = 0; a < 5; ++a) acc_idx[a] = -1;
+    const bool df_plain = df > 1e-300 && df < 1e300;
     int na = 0;
     __syncwarp();
     while (na < k) {
@@ -505,22 +503,23 @@ __device__ __forceinline__ int k3_rigid(T *mags, const List *hot, int nslot, T t
         warp_argmax(bm, bj);
         if (bj < 0) break;
         const int w2 = half_height_bins_warp<T, HALF, P>(mags, bj, lane);
-        bool separated = true;
-#pragma unroll
-        for (int a = 0; a < 5; ++a) {
-            if (a < na && separated) {
-                // an accepted peak's own bin was zeroed when it was found, so its half-height width is 0 (the
-                // reference's resolution() degenerates to 1.18*dist/w_candidate); walk only if that ever fails
-                const int w1 = mags[P::addr(acc_idx[a])] == (T)0 ? 0 : half_height_bins_f<T, HALF, P>(mags, acc_idx[a]);
-                bool ok = false;
-                if (w1 + w2 != 0) {
-                    const double num = mul_rn(1.18, (double)abs(bj - acc_idx[a])), den = 1.5 * (double)(w1 + w2);
-                    if (num >= den * (1.0 + 1e-12)) ok = true;                       // rs >= 1.5 by a clear margin
-                    else if (!(num < den * (1.0 - 1e-12))) ok = div_rn(num, (double)(w1 + w2)) >= 1.5;
-                }
-                if (!ok) separated = false;
+        // resolution against every accepted peak, one accepted peak per lane (their bins are in the record under
+        // construction; the barrier that ends every round orders lane 0's stores before these reads)
+        bool clash = false;
+        if (lane < na) {
+            const int ja = reinterpret_cast<const int *>(rec_s + 8 + 24 * lane)[0];
+            // an accepted peak's own bin was zeroed when it was found, so its half-height width is 0 (the
+            // reference's resolution() degenerates to 1.18*dist/w_candidate); walk only if that ever fails
+            const int w1 = mags[P::addr(ja)] == (T)0 ? 0 : half_height_bins_f<T, HALF, P>(mags, ja);
+            bool ok = false;
+            if (w1 + w2 != 0) {
+                const double num = mul_rn(1.18, (double)abs(bj - ja)), den = 1.5 * (double)(w1 + w2);
+                if (num >= den * (1.0 + 1e-12)) ok = true;                       // rs >= 1.5 by a clear margin
+                else if (!(num < den * (1.0 - 1e-12))) ok = div_rn(num, (double)(w1 + w2)) >= 1.5;
             }
+            clash = !ok;
         }
+        const bool separated = !__any_sync(0xffffffffu, clash);
         if (separated) {
             if (lane == 0) {
                 unsigned char *pk = rec_s + 8 + 24 * na;
@@ -528,26 +527,24 @@ __device__ __forceinline__ int k3_rigid(T *mags, const List *hot, int nslot, T t
                 reinterpret_cast<int *>(pk)[1] = w2;
                 reinterpret_cast<double *>(pk + 8)[0] = (double)bm;
             }
-#pragma unroll
-            for (int a = 0; a < 5; ++a)
-                if (a == na) acc_idx[a] = bj;
             ++na;
         }
-        // zeroing radius round((freq * 0.02) / (frequencies[2] - frequencies[1])): equals round-half-even(0.02 * idx)
-        // unless that product sits within 1e-6 of a tie; only then (or for a degenerate df) the exact expression runs
-        double reach_d;
+        // zeroing radius round((freq * 0.02) / (frequencies[2] - frequencies[1])): equals round-half-even(idx / 50),
+        // which is floor(idx / 50) + (idx mod 50 > 25) on integers, unless idx / 50 is an exact tie; only then (or for a
+        // degenerate df) the exact expression runs
+        int reach;
         {
-            const double x02 = 0.02 * (double)bj, fr = x02 - floor(x02);
-            if (df > 1e-300 && df < 1e300 && fabs(fr - 0.5) > 1e-6) {
-                reach_d = rint(x02);
+            const int q50 = bj / 50, r50 = bj - 50 * q50;
+            if (df_plain && r50 != 25) {
+                reach = q50 + (r50 > 25 ? 1 : 0);
             } else {
                 const double f = mul_rn((double)bj, df);
-                reach_d = rint(div_rn(mul_rn(f, 0.02), distance));
+                double reach_d = rint(div_rn(mul_rn(f, 0.02), distance));
+                if (!(reach_d >= 0.0)) reach_d = 0.0;
+                if (reach_d > (double)HALF) reach_d = (double)HALF;
+                reach = (int)reach_d;
             }
         }
-        if (!(reach_d >= 0.0)) reach_d = 0.0;
-        if (reach_d > (double)HALF) reach_d = (double)HALF;
-        const int reach = (int)reach_d;
         const int z0 = max(0, bj - reach), z1 = min(HALF, bj + reach + 1);
         __syncwarp();
         for (int b = z0 + lane; b < z1; b += 32) mags[P::addr(b)] = (T)0;
