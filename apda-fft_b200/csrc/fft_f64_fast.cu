@@ -13,6 +13,9 @@
 //   last pass results go straight from registers to HBM with coalesced 128-bit stores; bin 0 := 0.
 #include "common.cuh"
 
+#include <mutex>
+#include <set>
+
 namespace {
 
 __device__ __forceinline__ void bfly(double2 &u, double2 &v, const double2 w) {
@@ -246,6 +249,23 @@ __device__ double select_median_f64(const double (&val)[16], int n_valid, double
     return shd[40];  // nothing writes this word again before the window is done
 }
 
+// Twiddles of stages 1..4 (entries [0, 15) of the recurrence table: stage with half-span h at [h-1, 2h-1)).  They depend
+// on the stage only, not on N, and every thread of pass 0 needs the same 15: in the constant bank they are operands of
+// the multiplications themselves - no loads, no scoreboard waits, no registers (ncu: pass 0 spent half of its stall
+// samples on the L1 round trips of these 15 loads).
+__constant__ double2 c_tw_head[15];
+
+__device__ __forceinline__ void stages_head(double2 *v) {
+#pragma unroll
+    for (int t = 1; t <= 4; ++t) {
+        const int h = 1 << (t - 1);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            if ((r & h) == 0) bfly(v[r], v[r + h], c_tw_head[(h - 1) + (r & (h - 1))]);
+        }
+    }
+}
+
 // q radix-2 stages on 2^q register values of one work item (stride 2^s0, low index bits `lo`)
 template <int Q>
 __device__ __forceinline__ void stages(double2 *v, const double2 *__restrict__ tw, int s0, int lo) {
@@ -341,7 +361,7 @@ fft_f64_fast_kernel(const double *__restrict__ samples, int n_samples, int64_t l
     double2 v[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) v[r] = make_double2(val[r] < CUDART_INF ? sub_rn(val[r], med) : 0.0, 0.0);
-    stages<4>(v, tw, 0, 0);
+    stages_head(v);
 #pragma unroll
     for (int r = 0; r < 16; ++r) s[17 * t + r] = v[r];  // pad16(16 t + r) = 16 t + r + t
     __syncthreads();
@@ -379,6 +399,15 @@ int launch_fft_f64_fast(apda_ctx *ctx, cudaStream_t st, const double *d_samples,
                         int64_t batch, int64_t N, int flags, double *d_spec, const int *d_nv) {
     TwiddleTables tw;
     APDA_TRY(apda_get_twiddles(ctx, N, &tw));
+    {   // the head twiddles are the same for every N: one upload per device (the symbol is per device, not per context)
+        static std::mutex mu;
+        static std::set<int> uploaded;
+        std::lock_guard<std::mutex> lock(mu);
+        if (!uploaded.count(ctx->device)) {
+            APDA_CUDA(cudaMemcpyToSymbol(c_tw_head, tw.d64, sizeof(double2) * 15, 0, cudaMemcpyDeviceToDevice));
+            uploaded.insert(ctx->device);
+        }
+    }
     switch (N) {
         case 1024: return launch_n<10>(ctx, st, d_samples, n_samples, ld, batch, flags, tw.d64, d_spec, d_nv);
         case 2048: return launch_n<11>(ctx, st, d_samples, n_samples, ld, batch, flags, tw.d64, d_spec, d_nv);
