@@ -555,9 +555,8 @@ __device__ __forceinline__ int k3_rigid(T *mags, const List *hot, int nslot, T t
 
 // fp32 tie test of the four bins jb..jb+3 (see APDA_STATUS_FP32_TIE): a hot bin equal to its right neighbour and higher
 // than both outer neighbours.  Out of line: reached only when the quad holds two equal adjacent magnitudes.
-template <typename T, int HALF>
+template <typename T, int HALF, typename P = K3<T, HALF>>
 static __device__ __noinline__ bool plateau_top_in_quad(const T *mags, int jb, T thr_f) {
-    using P = K3<T, HALF>;
     bool tie = false;
     for (int j = jb; j < jb + 4; ++j) {
         const T e = mags[P::addr(j)];
@@ -786,26 +785,33 @@ __device__ __forceinline__ void k3_tail_mw(float *mags, float *cmaxs, float *cmi
         }
         cmaxs[t] = cmax;
         cmins[t] = cmin;
-        while (hotq) {
+        while (hotq) {  // every test of the quad on registers, one counter update per quad (see k3_tail)
             const int q = __ffs(hotq) - 1;
             hotq &= hotq - 1;
+            const int jb = 16 * t + 4 * q;
             const float4 v = *reinterpret_cast<const float4 *>(ch + 4 * q);
-            const float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (e[u] > thr_f) {
-                    const int j = 16 * t + 4 * q + u;
-                    bool take = true;
-                    if (FLEX) take = j >= 1 && j <= HALF - 2 && e[u] > mags[P::addr(j - 1)] && e[u] > mags[P::addr(j + 1)];
-                    if (take) {
-                        const int pos = atomicAdd(&ctl[0], 1);
-                        if (pos < slot_cap) slots[pos].idx = (uint16_t)j;
-                    }
-                    if (j >= 1 && j + 1 <= HALF - 1 && e[u] == mags[P::addr(j + 1)] && e[u] > mags[P::addr(j - 1)] &&
-                        (j + 2 > HALF - 1 || e[u] > mags[P::addr(j + 2)]))
-                        ctl[1] = 1;  // APDA_STATUS_FP32_TIE, see k3_tail
-                }
+            const float left = mags[P::addr(jb > 0 ? jb - 1 : 0)];
+            const float right = mags[P::addr(jb + 4 < HALF ? jb + 4 : HALF - 1)];
+            unsigned take;
+            if (FLEX)
+                take = (v.x > thr_f && jb >= 1 && v.x > left && v.x > v.y ? 1u : 0u) |
+                       (v.y > thr_f && v.y > v.x && v.y > v.z ? 2u : 0u) |
+                       (v.z > thr_f && v.z > v.y && v.z > v.w ? 4u : 0u) |
+                       (v.w > thr_f && jb + 3 <= HALF - 2 && v.w > v.z && v.w > right ? 8u : 0u);
+            else
+                take = (v.x > thr_f ? 1u : 0u) | (v.y > thr_f ? 2u : 0u) | (v.z > thr_f ? 4u : 0u) | (v.w > thr_f ? 8u : 0u);
+            if (take) {
+                int pos = atomicAdd(&ctl[0], __popc(take));
+                do {
+                    const int j = jb + __ffs(take) - 1;
+                    take &= take - 1;
+                    if (pos < slot_cap) slots[pos].idx = (uint16_t)j;
+                    ++pos;
+                } while (take);
             }
+            if ((v.x == v.y || v.y == v.z || v.z == v.w || v.w == right) &&
+                plateau_top_in_quad<float, HALF, P>(mags, jb, thr_f))
+                ctl[1] = 1;  // APDA_STATUS_FP32_TIE, see k3_tail
         }
     }
     window_sync<NT>();
