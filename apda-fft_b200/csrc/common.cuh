@@ -344,4 +344,18 @@ __device__ __forceinline__ float sqrt_approx(float x) {
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+// Ask L2 for the bytes [p, p + bytes) of a window a LATER CTA will stream (128-byte lines dealt out to the callers), so
+// that its loads find the data on chip instead of waiting a DRAM round trip; `ahead` = windows resident on the whole GPU.
+#ifndef APDA_L2_PREFETCH
+#define APDA_L2_PREFETCH 1
+#endif
+__device__ __forceinline__ unsigned sm_count_reg() {
+    unsigned n;
+    asm("mov.u32 %0, %%nsmid;" : "=r"(n));
+    return n;
+}
+__device__ __forceinline__ void l2_prefetch_span(const void *p, int bytes, int tid, int nthreads) {
+    const char *c = reinterpret_cast<const char *>(p);
+    for (int off = tid * 128; off < bytes; off += nthreads * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + off));
+}
 #endif  // __CUDACC__

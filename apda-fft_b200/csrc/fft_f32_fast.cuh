@@ -425,10 +425,10 @@ __device__ float select_median(const float2 (&v2)[16], int n_valid, uint32_t *sh
 // Passes 1-3 of one window: HBM samples -> centred -> M-point complex FFT Z[k] in natural order in `s`
 // (ends with the window barrier, so every thread may read any Z[k]).  Shared by the pipeline kernel
 // (fft_f32_fast.cu) and the fused window->record kernel (fused_f32.cu).
-template <int N, int CENTER, bool FULL>
+template <int N, int CENTER, bool FULL, int PF_AHEAD = 0>
 __device__ __forceinline__ void k1_forward(const float *__restrict__ samples, const int n_samples, const int64_t ld,
                                            const int64_t winc, const float2 *__restrict__ tw1, float2 *s, uint32_t *sel_w,
-                                           float *red_w, const int wslot, const int t) {
+                                           float *red_w, const int wslot, const int t, const int64_t pf_batch = 0) {
     constexpr int center = CENTER;
     using P = Plan<N>;
     constexpr int M = N / 2, R1 = P::R1, R2 = P::R2, R3 = P::R3, T = M / 16;
@@ -455,6 +455,10 @@ __device__ __forceinline__ void k1_forward(const float *__restrict__ samples, co
             }
             v[g * R1 + n1] = val;
         }
+    }
+    if (APDA_L2_PREFETCH && PF_AHEAD > 0) {  // samples of the window a later CTA of this slot will load
+        const int64_t wn = winc + (int64_t)sm_count_reg() * PF_AHEAD;
+        if (wn < pf_batch) l2_prefetch_span(samples + wn * ld, n_samples * (int)sizeof(float), t, T);
     }
     float shift = 0.f;
     if (center == APDA_CENTER_MEDIAN) {

@@ -255,6 +255,10 @@ __device__ double select_median_f64(const double (&val)[16], int n_valid, double
 // samples on the L1 round trips of these 15 loads).
 __constant__ double2 c_tw_head[15];
 
+#ifndef APDA_K1F64_PF
+#define APDA_K1F64_PF 1
+#endif
+
 __device__ __forceinline__ void stages_head(double2 *v) {
 #pragma unroll
     for (int t = 1; t <= 4; ++t) {
@@ -342,6 +346,10 @@ fft_f64_fast_kernel(const double *__restrict__ samples, int n_samples, int64_t l
         double *rp = raw + (t + (t >> 3));  // (t + T*u) + ((t + T*u) >> 3) = t + (t >> 3) + u * (T + T/8): T is a multiple of 8
 #pragma unroll
         for (int u = 0; u < 16; ++u) rp[u * (T + T / 8)] = ld_v[u];
+    }
+    if (APDA_L2_PREFETCH && APDA_K1F64_PF) {  // samples of the window the next CTA of this slot will load (see l2_prefetch_span)
+        const int64_t wn = win + (int64_t)sm_count_reg() * (LOGN <= 12 ? 768 / T : 1);
+        if (wn < (int64_t)gridDim.x) l2_prefetch_span(samples + wn * ld, n_samples * (int)sizeof(double), t, T);
     }
     __syncthreads();
     // work item hi = t of pass 0 owns outputs idx = 16*t + r, i.e. inputs bitrev(idx) = bitrev4(r) * N/16 + bitrev(t)

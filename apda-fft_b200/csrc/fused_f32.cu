@@ -52,7 +52,8 @@ fused_f32_kernel(const float *__restrict__ samples, int n_samples, int64_t ld, i
     if (win >= batch) return;
     if (t == 0) ctl[0] = ctl[1] = 0;  // slot count, tie flag (published by the barriers inside k1_forward)
 
-    k1_forward<N, CENTER, FULL>(samples, n_samples, ld, win, tw1, s, sel, red, 0, t);
+    k1_forward<N, CENTER, FULL, (N == 4096 ? APDA_FUSED_MINB : N < 4096 ? 1024 / (N / 32) / 2 : 2)>(
+        samples, n_samples, ld, win, tw1, s, sel, red, 0, t, batch);
 
     // split step, lower half only: X[k] = S/2 + Wt*D for k = 2p, 2p+1 -> magnitudes in the tail's shared-memory layout
     if (t < 16) reinterpret_cast<uint64_t *>(rec_s)[t] = (t % 3 == 1) ? 0x00000000ffffffffull : 0ull;

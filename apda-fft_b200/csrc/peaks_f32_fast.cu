@@ -6,7 +6,13 @@ namespace {
 #ifndef APDA_K3_BATCH
 #define APDA_K3_BATCH 8
 #endif
-constexpr int kK3Batch = APDA_K3_BATCH;  // 128-bit loads in flight per lane in phase 1
+constexpr int kK3Batch = APDA_K3_BATCH;
+#ifndef APDA_K3_PF_CTAS
+#define APDA_K3_PF_CTAS 6  // prefetch distance in CTAs per SM (11 are resident at N = 4096; sweep: 6 -> 2.49 ns, 11 -> 2.52, 20 -> 2.93)
+#endif
+#ifndef APDA_K3_PF_CTAS_LONG
+#define APDA_K3_PF_CTAS_LONG 6  // the same at N = 8192 (6 resident; sweep: 6 -> 5.85 ns, 11 -> 6.84, 20 -> 9.33, none 6.97)
+#endif  // 128-bit loads in flight per lane in phase 1
 
 template <int HALF, bool FLEX>
 __global__ void __launch_bounds__(32 * kWPC)
@@ -62,6 +68,13 @@ peaks_f32_fast_kernel(const float2 *__restrict__ spec, int64_t batch, double df_
     const float thr_f = __double2float_rd(thr);  // for floats m:  m > thr  <=>  m > thr_f
     const double df = d_fs ? div_rn(d_fs[win], (double)N) : df_all;  // fs / n (host-side division when fs is shared)
     __syncwarp();
+    // The tail below issues no global loads, and two thirds of a warp's life is tail: the window a later warp of this
+    // slot will stream (11 CTAs of kWPC windows per SM are resident) is requested into L2 now, so phase 1 of that warp
+    // waits an L2 instead of a DRAM round trip.  N = 4096 fp32: 2.92 -> 2.49 ns per window, N = 8192: 6.97 -> 5.85; short windows do not gain.
+    if (APDA_L2_PREFETCH && HALF >= 2048) {
+        const int64_t wn = win + (int64_t)sm_count_reg() * ((HALF >= 4096 ? APDA_K3_PF_CTAS_LONG : APDA_K3_PF_CTAS) * kWPC);
+        if (wn < batch) l2_prefetch_span(spec + wn * (int64_t)N, HALF * (int)sizeof(float2), lane, 32);
+    }
     k3_tail<float, HALF, FLEX>(mags, slots, P::SLOTS, rec_s, &nslot_s[warp], sd, thr_f, df, k, lane, win, recs, repair);
 }
 
