@@ -64,6 +64,9 @@ peaks_f64_fast_kernel(const double2 *__restrict__ spec, int64_t batch, double df
             reinterpret_cast<uint64_t *>(rec_s)[lane] = (lane % 3 == 1) ? 0x00000000ffffffffull : 0ull;
     }
 
+    // the loop below asks for four rows, then spends ~250 fp64 instructions on them: the whole half spectrum is requested
+    // into L2 up front, so every batch after the first waits an L2 instead of a DRAM round trip
+    if (APDA_L2_PREFETCH) l2_prefetch_span(spec + win * (int64_t)N, HALF * (int)sizeof(double2), sub * 32 + lane, 32 * kWPW);
     // ---- phase 1: stream the half spectrum (one bin per lane and row), magnitudes -> shared memory, double-double sums ----
     const double2 *src = spec + win * (int64_t)N + lane;
     double sx_hi = 0.0, sx_lo = 0.0, sq_hi = 0.0, sq_lo = 0.0;
