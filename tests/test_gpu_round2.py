@@ -703,3 +703,61 @@ def test_batches_of_long_windows_share_launch_sets(an):
                 assert recs[w].tobytes() == alone[0].tobytes(), (n, flexible, w)
             top = recs["pk"]["idx"][:, 0]
             assert np.array_equal(top, np.round(101.6 + 3 * np.arange(b)).astype(top.dtype)), (n, flexible)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# windowed pickers: peaks, plateaus and hot runs at every structural boundary of the warp-per-window kernels
+# ---------------------------------------------------------------------------------------------------------------
+def _edge_spectra(n, dtype):
+    """Real-valued spectra (magnitude m -> bin m + 0j) whose hot bins sit where the fast pickers change code path:
+    bin 0 / 1, the last candidate bin HALF-2 and the non-candidate HALF-1, both sides of quad (4-bin) and lane-chunk
+    (HALF/32-bin) boundaries, equal adjacent hot bins (fp32 tie flag) inside a quad, across quads, across chunks and at
+    the end of the half spectrum, descending / ascending hot runs (only one local maximum) and a hot quad holding two
+    local maxima."""
+    half, c = n // 2, (n // 2) // 32
+    rng = np.random.default_rng(n)
+    layouts = [
+        {1: 9.0, 40: 7.0, 500: 5.0},
+        {0: 50.0, 2: 8.0, 3: 7.5, 4: 9.5, 300: 6.0},
+        {half - 2: 9.0, half - 1: 4.0, 100: 7.0},
+        {half - 1: 9.0, half - 3: 6.0, 17: 7.0},
+        {c - 1: 9.0, c + 1: 8.0, 2 * c: 7.0, 3 * c - 1: 6.0, 3 * c + 2: 5.5},
+        {7: 8.0, 8: 8.0, 200: 6.0},                      # equal pair across a quad boundary
+        {c - 1: 8.5, c: 8.5, 300: 6.0},                  # equal pair across a chunk boundary
+        {101: 8.0, 102: 8.0, 103: 2.0, 400: 6.0},        # equal pair inside a quad
+        {half - 2: 7.0, half - 1: 7.0, 60: 9.0},         # equal pair at the end (no right outer neighbour)
+        {200: 10.0, 201: 9.0, 202: 8.0, 199: 8.5, 198: 7.0},   # hot run around one maximum
+        {320: 6.0, 322: 9.0, 321: 1.0, 323: 5.0},        # two local maxima in one quad
+        {4 * 77: 9.0, 4 * 77 + 3: 8.0, 4 * 78: 8.5},     # maxima at both ends of a quad and the start of the next
+        {5: 6.0, 6: 6.0, 7: 6.0, 900 % half: 9.0},       # three equal bins: no plateau top with a strict outer neighbour pair
+    ]
+    z = np.zeros((len(layouts), n), dtype=np.complex64 if dtype == np.float32 else np.complex128)
+    for w, lay in enumerate(layouts):
+        mag = (0.01 + 0.01 * rng.random(half)).astype(dtype)
+        for b_, m in lay.items():
+            mag[b_ % half] = dtype(m)
+        z[w, :half] = mag
+        z[w, half:] = mag[::-1]
+    return z
+
+
+@pytest.mark.parametrize("n", [1024, 4096, 8192])
+def test_fast_pickers_at_quad_chunk_and_end_boundaries(n, an):
+    """The specialised pickers (fp32 and fp64) against the general kernel (byte-equal records, tie status included) and the
+    oracle (index lists) on spectra whose hot bins sit on every quad / chunk / end-of-spectrum boundary."""
+    for dtype in (np.float32, np.float64):
+        z = _edge_spectra(n, dtype)
+        for flexible in (True, False):
+            fast = an.peaks(z, 250.0, flexible=flexible)
+            an.ctx.set_generic_only(True)
+            try:
+                slow = an.peaks(z, 250.0, flexible=flexible)
+            finally:
+                an.ctx.set_generic_only(False)
+            for w in range(z.shape[0]):
+                assert fast[w].tobytes() == slow[w].tobytes(), (n, dtype.__name__, flexible, w, fast[w], slow[w])
+                zl = z[w].astype(np.complex128).tolist()
+                want = ref_port.top_peaks_prominence(zl, 250.0) if flexible else ref_port.top_peaks_resolution(zl, 250.0)
+                got = _dicts(fast[w], 250.0, n, flexible)
+                assert [p["idx"] for p in got] == [p["idx"] for p in want], (n, dtype.__name__, flexible, w)
+            assert ((fast["status"] & ~16) == 0).all()
