@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-kernel counts of the SASS mnemonics that show what the shipped library uses (cuobjdump -sass on libapda_b200.so):
-TMA (UTMALDG / UTMASTG), mbarriers (SYNCS), packed fp32 (FADD2 / FMUL2 / FFMA2), warp reductions (REDUX), fp64 pipe
+TMA (UTMALDG / UTMASTG), mbarriers (SYNCS), L2 prefetch requests (CCTL.E.PF2), constant-bank twiddles (LDCU.128), packed fp32 (FADD2 / FMUL2 / FFMA2), warp reductions (REDUX), fp64 pipe
 (DFMA / DADD / DMUL), MUFU, 128-bit global accesses, and the absence of tensor-core / library code.
 
     python scripts/sass_counts.py > profiles/sass_r2.txt
@@ -13,7 +13,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "apda-fft_b200", "libapda_b200.so")
-PATTERNS = ["UTMALDG", "UTMASTG", "SYNCS", "FADD2", "FMUL2", "FFMA2", "REDUX", "DFMA", "DADD", "DMUL", "MUFU",
+PATTERNS = ["UTMALDG", "UTMASTG", "SYNCS", "CCTL.E.PF2", "LDCU.128", "FADD2", "FMUL2", "FFMA2", "REDUX", "DFMA", "DADD", "DMUL", "MUFU",
             "LDG.E.128", "STG.E.128", "LDS.128", "STS.128", "BAR.SYNC", "HMMA", "UTCHMMA", "UTCQMMA"]
 
 
