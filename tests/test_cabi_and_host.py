@@ -249,3 +249,24 @@ def test_result_packing_arrow_jsonl_and_upload_metrics(golden, tmp_path):
                 f"{{'Z': {entry!r}}}); print(json.dumps(p['metriche']))")
         ref = json.loads(subprocess.check_output([sys.executable, "-c", code], text=True))
         assert ref == json.loads(json.dumps(got))
+
+
+def test_dropins_never_hand_out_a_record_with_nonzero_status():
+    """The drop-in modules return reference-equivalent results or raise: every record batch they
+    decode goes through _cabi.check_record_status, which raises on any status bit (truncated candidate list, window of
+    another padded length, empty window, fp32 tie) and names the first offending window."""
+    from apda_fft_b200 import _cabi
+    from apda_fft_b200.records import record_dtype
+    recs = np.zeros(4, dtype=record_dtype(5))
+    _cabi.check_record_status(recs)                      # all clean: no exception
+    for bit in (_cabi.STATUS_TRUNCATED if hasattr(_cabi, "STATUS_TRUNCATED") else 1, 4, 8, _cabi.STATUS_FP32_TIE):
+        recs["status"][:] = 0
+        recs["status"][2] = bit
+        with pytest.raises(_cabi.ApdaError) as err:
+            _cabi.check_record_status(recs)
+        assert "window 2" in str(err.value) and f"status {bit}" in str(err.value)
+    # and both picker drop-ins really call it on what the library returns
+    here = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "apda-fft_b200", "utils")
+    for mod in ("get_peak_prominence.py", "get_peak_resolution.py"):
+        with open(os.path.join(here, mod)) as fh:
+            assert "check_record_status" in fh.read(), mod
